@@ -1,0 +1,59 @@
+// Host-visible description of one tcgen05 GEMM / implicit-GEMM launch.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vqa {
+
+enum : int {
+  LOAD_2D = 0,         // plain matrix.  K-major: box (64 k, rows); MN-major: box (64 mn, 64 k)
+  LOAD_CONV = 1,       // K-major A of an implicit-GEMM convolution: NHWC activations through a 4-D
+                       // tensor map; k-block -> (filter tap, 64-channel chunk); tile rows = pixel box
+  LOAD_PIXELS_MN = 2,  // MN-major operand whose contraction index runs over pixels (wgrad of a
+                       // convolution): k-block -> pixel box (n, th, tw); 64-channel chunks along MN
+};
+
+struct GemmParams {
+  int M, N;        // output extent (rows, cols); for LOAD_CONV M is implied by the pixel boxes
+  int kb_total;    // number of 64-deep k-blocks in the whole contraction
+  int a_mn, b_mn;  // 1 = operand is MN-major in global memory (contraction index is the row index)
+  int a_mode, b_mode;
+  int stage_tx_bytes;  // bytes the TMA loads of one pipeline stage deliver (A box + B boxes)
+
+  // pixel-box geometry (LOAD_CONV for A; LOAD_PIXELS_MN for A and/or B)
+  int bx_w, bx_h, bx_n;        // box extent in output pixels (w, h, images); product = rows per box
+  int tiles_w, tiles_h;        // boxes per image along w and h
+  int Wo, Ho, Nimg;            // output spatial size and image count
+  int taps_s, cchunks;         // LOAD_CONV: filter width S and 64-channel chunks per tap
+  int stride_w, stride_h, pad_w, pad_h, dil_w;  // input coord = out*stride - pad + tap*dil
+  int b_tap_cin;               // LOAD_PIXELS_MN on B: channels per tap (column n -> tap n / cin)
+  int b_taps_s;                //                      filter width used to split the tap into (r, s)
+
+  // epilogue
+  void* out;                   // bf16 or fp32, row stride ldo elements
+  long long ldo;
+  int out_fp32;
+  int out_pixels;              // 1: output rows follow the LOAD_CONV pixel boxes (NHWC), else linear
+  int atomic_out;              // split-K partial sums: fp32 red.add into a pre-zeroed output
+  const float* bias;           // [N] or null (added by split 0 only)
+  int relu;
+  const __nv_bfloat16* relu_mask;  // [M, ldm]: keep element only where mask > 0 (backward of ReLU)
+  long long ldm;
+  float drop_p;                // dropout probability (0 = off); mask from (rng seed, drop_sid, index)
+  uint32_t drop_sid;
+  const unsigned long long* rng;   // device pointer: {seed, offset}
+  const void* residual;        // added after dropout; fp32 or bf16, row stride ldr
+  long long ldr;
+  int res_fp32;
+  float alpha;                 // scale applied to the accumulator before everything else
+  int dbg_a_lbo, dbg_a_sbo, dbg_b_lbo, dbg_b_sbo;  // bring-up overrides of the MN-major descriptor strides (0 = default)
+};
+
+// Launch. tmA / tmB are host-encoded CUtensorMaps (copied into kernel parameter space).
+// bn in {64, 128, 256}; split_k >= 1.  Returns cudaError_t as int.
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn,
+                int split_k, cudaStream_t stream);
+
+}  // namespace vqa
