@@ -4,17 +4,25 @@
  * the nn.Module surface of `ResnetVQAModel` (model/resnet_vqa_model.py:28-165) driven by
  * `train_one_step` (trainer/faster_rcnn_vqa_trainer.py:391-406).  This header is the boundary a
  * maintainer binds with ctypes: plain pointers and sizes, no torch types.
+ * Each entry point names the reference call site (file:line) whose arithmetic it replaces; `tv:` is
+ * torchvision/models/resnet.py and `hf:` is transformers/models/t5/modeling_t5.py, the two third-party
+ * files the reference's model is assembled from.
  *
  * Conventions
  *   - every function returns 0 on success, non-zero on failure; `vqa_last_error()` (thread-local)
  *     describes the failure.  Nothing throws, nothing calls exit().
- *   - all pointers are DEVICE pointers owned by the caller unless stated otherwise; the library keeps
- *     no reference after the call returns, except inside a `vqa_step*` handle, which borrows the
- *     parameter / gradient / workspace buffers it was bound to until `vqa_step_destroy`.
- *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on that stream; no call
- *     synchronises the device.
+ *   - all data pointers are DEVICE pointers owned by the caller (PyTorch); the library allocates no
+ *     device memory and keeps no reference after the call returns, except inside a plan (below),
+ *     which borrows every pointer recorded into it until `vqa_plan_destroy`.
+ *   - `plan`: NULL runs the op immediately on `stream`; otherwise the fully-resolved launch (tensor
+ *     maps, pointers, shapes) is appended to the plan and nothing runs until `vqa_plan_run`.
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it; no call
+ *     synchronises the device.  Safe to call from the autograd engine's worker thread.
  *   - bf16 tensors are row-major with the innermost dimension contiguous; activations are NHWC /
  *     [tokens, features].
+ *   - dropout: counter-based Philox4x32-10 keyed by the device pair rng = {seed, offset}; an element
+ *     of stream `sid` at flat index i is dropped iff u16(philox(seed, offset, sid, i / 8), i % 8) <
+ *     p * 65536, survivors are scaled by 1/(1-p).  Forward and backward regenerate the same mask.
  */
 #ifndef VQA_B200_H_
 #define VQA_B200_H_
@@ -31,13 +39,21 @@ int vqa_version(void);
 /* bring-up aid: override the MN-major UMMA descriptor strides (bytes); zeros restore defaults */
 int vqa_debug_set_umma(int a_lbo, int a_sbo, int b_lbo, int b_sbo);
 
+/* ---- launch plans ------------------------------------------------------------------------------ */
+void* vqa_plan_create(void);
+int vqa_plan_destroy(void* plan);
+int vqa_plan_size(void* plan);                       /* number of recorded launches */
+int vqa_plan_run(void* plan, void* stream);          /* replay (through the CUDA graph if captured) */
+int vqa_plan_capture_graph(void* plan, void* stream);/* capture the recorded launches into a CUDA graph */
+
 /* ------------------------------------------------------------------------------------------------
  * tcgen05 GEMM.  out[M,N] = epilogue(alpha * op(A) op(B)^T)
  *   a_mn = 0: A is [M,K] row-major (lda);  a_mn = 1: A is stored [K,M] row-major (lda)
  *   b_mn = 0: B is [N,K] row-major (ldb);  b_mn = 1: B is stored [K,N] row-major (ldb)
- * Epilogue order: +bias[N] -> ReLU -> keep where relu_mask>0 -> dropout(p, rng, sid) -> +residual.
+ * Epilogue order: *alpha -> +bias[N] -> (+residual if res_first) -> ReLU -> keep where relu_mask>0
+ *                 -> dropout(p, rng, sid) -> (+residual if !res_first).
  * Replaces nn.Linear forward / dgrad / wgrad (model/multi_head_vision_text_attn.py:31-34,92-93,
- * model/resnet_vqa_model.py:86-88, hf T5 q/k/v/o/wi/wo).
+ * model/resnet_vqa_model.py:86-88, hf:92-103 wi/wo, hf:178-181 q/k/v/o).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   int M, N, K;
@@ -48,18 +64,19 @@ typedef struct {
   int relu;
   const void* relu_mask; long long ldm;          /* bf16 [M, ldm] */
   float drop_p; uint32_t drop_sid; const uint64_t* rng;   /* rng: device {seed, offset} */
-  const void* residual; long long ldr; int res_fp32;
+  const void* residual; long long ldr; int res_fp32; int res_first;
   float alpha;
+  int accumulate; /* 1: fp32 out += result (red.add) instead of a plain store */
   int bn;        /* output tile width: 64, 128 or 256 */
   int split_k;   /* >1: fp32 out must be zeroed by the caller; partial sums are red.add'ed */
 } vqa_gemm_args;
-int vqa_gemm_bf16(const vqa_gemm_args* a, void* stream);
+int vqa_gemm_bf16(void* plan, const vqa_gemm_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution, NHWC bf16, folded-BN bias + residual + ReLU epilogue.
  *   x [N,H,W,Cin] (stem7: [N,H,W+8,8], 3 zero pixels left / 5 right), w [Cout, R*S*Cin]
  *   (stem7: [Cout, 7*8*8]), out [N,Ho,Wo,Cout] bf16 (out_fp32=0) or fp32.
- * Replaces torchvision Conv2d+BatchNorm2d(eval)+ReLU(+identity) (tv resnet.py:89-105,143-163,197-200)
+ * Replaces torchvision Conv2d+BatchNorm2d(eval)+ReLU(+identity) (tv:89-105,143-163,197-200)
  * and the ConvTranspose2d channel projection (model/resnet_vqa_model.py:64-78,124,135).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -68,16 +85,124 @@ typedef struct {
   const float* bias; const void* residual; int relu;
   int bn;
 } vqa_conv_args;
-int vqa_conv2d_bf16(const vqa_conv_args* a, void* stream);
+int vqa_conv2d_bf16(void* plan, const vqa_conv_args* a, void* stream);
 
 /* Weight gradient of a stride-1 same-padded RxS convolution: dw[Cout, R*S*Cin] fp32 (zeroed by the
- * caller when split_k > 1) = sum_pixels dy[pix,Cout] * x[pix+tap,Cin].  (ConvTranspose2d wgrad.) */
+ * caller when split_k > 1) = sum_pixels dy[pix,Cout] * x[pix+tap,Cin].  (ConvTranspose2d wgrad,
+ * autograd of model/resnet_vqa_model.py:124,135.) */
 typedef struct {
   int N, H, W, Cin, Cout, R, S, pad;
   const void* dy; const void* x; float* dw;
   int bn, split_k;
 } vqa_conv_wgrad_args;
-int vqa_conv2d_wgrad_bf16(const vqa_conv_wgrad_args* a, void* stream);
+int vqa_conv2d_wgrad_bf16(void* plan, const vqa_conv_wgrad_args* a, void* stream);
+
+/* ---- layout / precision plumbing (weight preparation, input formatting) ------------------------- */
+int vqa_cast_f32_bf16(void* plan, const float* src, void* dst, long long n, void* stream);
+int vqa_memset_zero(void* plan, void* ptr, long long bytes, void* stream);
+int vqa_axpy_f32(void* plan, float* y, const float* x, float a, long long n, void* stream); /* y += a*x */
+/* Conv2d weight [O,I,R,S] fp32 (+ eval BatchNorm gamma/beta/mean/var, may be NULL) -> bf16
+ * [O, R, Sp, Ip] (zero padded) scaled by gamma/sqrt(var+eps), and bias[O] = beta - mean*scale.
+ * (tv:197-199 conv1/bn1 and every block's conv/bn pair; BN in eval mode, model/resnet_vqa_model.py:116,127) */
+int vqa_fold_conv_bn(void* plan, const float* w, const float* gamma, const float* beta,
+                     const float* mean, const float* var, float eps, void* w_out, float* bias_out,
+                     int O, int I, int R, int S, int Sp, int Ip, void* stream);
+/* ConvTranspose2d weight [Cin,Cout,3,3] fp32 -> equivalent Conv2d weight bf16 [Cout, 3,3, Cin] with the
+ * taps flipped; and the inverse mapping of its fp32 gradient (model/resnet_vqa_model.py:64-78). */
+int vqa_convT_weight_prep(void* plan, const float* w, void* w_out, int Cin, int Cout, void* stream);
+int vqa_convT_wgrad_unprep(void* plan, const float* dw_conv, float* dw, int Cin, int Cout, void* stream);
+/* images fp32 [N,3,H,W] -> bf16 [N,H,W+8,8] (stem layout); bf16 NHWC -> fp32 NCHW feature map */
+int vqa_image_to_stem(void* plan, const float* img, void* out, int N, int H, int W, void* stream);
+int vqa_nhwc_to_nchw_f32(void* plan, const void* x, float* out, int N, int H, int W, int C, void* stream);
+/* MaxPool2d(3, stride 2, pad 1) on bf16 NHWC (tv:200) */
+int vqa_maxpool3x3s2(void* plan, const void* x, void* out, int N, int H, int W, int C, void* stream);
+
+/* ---- T5 encoder pieces --------------------------------------------------------------------------- */
+/* nn.Embedding gather + dropout (hf:682,734): out fp32 [M,D]; backward scatter-adds into dtable. */
+int vqa_embedding_fwd(void* plan, const long long* ids, const float* table, float* out, int M, int D,
+                      int vocab, float drop_p, uint32_t sid, const uint64_t* rng, void* stream);
+int vqa_embedding_bwd(void* plan, const long long* ids, const float* dout, float* dtable, int M, int D,
+                      int vocab, float drop_p, uint32_t sid, const uint64_t* rng, void* stream);
+/* T5LayerNorm (hf:55-68): y = w * x * rsqrt(mean(x^2) + eps), then optional dropout (hf:768).
+ * y_bf16 and/or y_f32 may be NULL.  Backward: dx = (dres?) + d/dx, dw += sum_rows (atomic). */
+int vqa_rmsnorm_fwd(void* plan, const float* x, const float* w, void* y_bf16, float* y_f32,
+                    float* rstd, int M, int D, float eps, float drop_p, uint32_t sid,
+                    const uint64_t* rng, void* stream);
+int vqa_rmsnorm_bwd(void* plan, const void* dy, int dy_fp32, const float* x, const float* w,
+                    const float* rstd, const float* dres, float* dx, float* dw, int M, int D,
+                    float drop_p, uint32_t sid, const uint64_t* rng, void* stream);
+/* relative-position bias (hf:236-251): bias[h,i,j] = table[bucket[i*Lk+j], h]; gradient back to table */
+int vqa_t5_bias_build(void* plan, const float* table, const int* bucket, float* bias, int H, int L,
+                      int nbuckets, void* stream);
+int vqa_t5_bias_grad(void* plan, const float* dbias, const int* bucket, float* dtable, int H, int L,
+                     int nbuckets, void* stream);
+
+/* ---- attention (hf:308-334 T5; model/multi_head_vision_text_attn.py:73-86 SGA) ------------------ */
+typedef struct {
+  int B, H, Lq, Lk, hd;                 /* hd = 64 (T5) or 96 (SGA) */
+  const void* q; long long ldq;         /* bf16, element (b, i, h, d) at q[(b*Lq+i)*ldq + h*hd + d] */
+  const void* k; long long ldk;
+  const void* v; long long ldv;
+  void* out; long long ldo;             /* bf16 context, same indexing */
+  void* probs;                          /* bf16 [B,H,Lq,Lk] softmax output (pre-dropout), saved for backward */
+  const float* bias;                    /* fp32 [H,Lq,Lk] additive or NULL */
+  const long long* key_mask;            /* int64 [B,Lk], 0 = masked key, or NULL (hf:323-325) */
+  float scale;                          /* 1.0 (T5) or 1/sqrt(hd) (SGA) */
+  float drop_p; uint32_t sid; const uint64_t* rng;
+} vqa_attn_fwd_args;
+int vqa_attention_fwd(void* plan, const vqa_attn_fwd_args* a, void* stream);
+typedef struct {
+  int B, H, Lq, Lk, hd;
+  const void* q; long long ldq; const void* k; long long ldk; const void* v; long long ldv;
+  const void* probs; const void* dout; long long ldo;
+  void* dq; long long lddq; void* dk; long long lddk; void* dv; long long lddv;   /* bf16 */
+  float* dbias;                         /* fp32 [H,Lq,Lk] accumulated atomically, or NULL */
+  float scale; float drop_p; uint32_t sid; const uint64_t* rng;
+} vqa_attn_bwd_args;
+int vqa_attention_bwd(void* plan, const vqa_attn_bwd_args* a, void* stream);
+
+/* ---- SGA pieces ---------------------------------------------------------------------------------- */
+/* nn.LayerNorm(768) (model/multi_head_vision_text_attn.py:120-126) over z = x + dropout(sublayer),
+ * z produced by the GEMM epilogue.  Backward: dz = d/dz, dgamma/dbeta accumulated atomically. */
+int vqa_layernorm_fwd(void* plan, const float* z, const float* gamma, const float* beta, void* y_bf16,
+                      float* y_f32, float* mean, float* rstd, int M, int D, float eps, void* stream);
+int vqa_layernorm_bwd(void* plan, const float* dy, const float* z, const float* gamma,
+                      const float* mean, const float* rstd, float* dz, float* dgamma, float* dbeta,
+                      int M, int D, void* stream);
+/* g = dropout_mask(x) as bf16 (gradient entering a dropped residual branch) */
+int vqa_dropout_cast(void* plan, const float* x, void* out_bf16, long long rows, int N, float drop_p,
+                     uint32_t sid, const uint64_t* rng, void* stream);
+/* out[n] += sum_m x[m,n]  (bias gradients); x bf16 [M, ld] */
+int vqa_colsum_bf16(void* plan, const void* x, long long ld, float* out, int M, int N, void* stream);
+
+/* ---- head: AttentionPooler + classifier + loss (model/resnet_vqa_model.py:14-26,152-160) -------- */
+int vqa_pooler_fwd(void* plan, const float* x, const float* a, const float* b, float* w_out,
+                   float* pooled_f32, void* pooled_bf16, int B, int L, int D, void* stream);
+int vqa_pooler_bwd(void* plan, const float* x, const float* a, const float* w, const float* dpooled,
+                   float* dx, float* da, float* db, int B, int L, int D, void* stream);
+/* log_softmax + NLLLoss(mean): logp [B,A]; loss += -logp[b,label]/B (loss zeroed by the caller) */
+int vqa_logsoftmax_nll_fwd(void* plan, const float* logits, long long ld, const long long* labels,
+                           float* logp, float* loss, int B, int A, void* stream);
+/* dlogits[b,:] = gscale * (exp(logp) - onehot)/B + glogp terms; gloss: device scalar or NULL (=1),
+ * glogp: fp32 [B,A] upstream gradient of the log-probs or NULL.  dlogits bf16 [B, ld] (pad cols zeroed) */
+int vqa_logsoftmax_nll_bwd(void* plan, const float* logp, const long long* labels, const float* gloss,
+                           const float* glogp, void* dlogits, long long ld, int B, int A, void* stream);
+
+/* ---- optimizer step (trainer/faster_rcnn_vqa_trainer.py:399-404) -------------------------------- */
+/* out[0] += sum x^2 */
+int vqa_sumsq_f32(void* plan, const float* x, long long n, float* out, void* stream);
+/* torch.optim.AdamW(amsgrad) on a contiguous fp32 range (torch/optim/adamw.py single-tensor math:
+ * p *= 1-lr*wd; m = lerp(m,g,1-b1); v = b2*v + (1-b2)*g*g; vmax = max(vmax,v);
+ * p -= (lr/bc1) * m / (sqrt(vmax)/sqrt(bc2) + eps)); scalar combinations are formed in double on the host.
+ * gnorm_sq: device scalar holding the global sum of squared gradients (NULL = no clipping); grads are
+ * scaled by min(1, max_norm / (sqrt(gnorm_sq) + 1e-6)) like clip_grad_norm_.  shadow: bf16 copy of the
+ * updated parameters (may be NULL). */
+int vqa_adamw_amsgrad(void* plan, float* p, const float* g, float* m, float* v, float* vmax,
+                      void* shadow, long long n, double lr, double beta1, double beta2, double eps,
+                      double weight_decay, double bias_correction1, double bias_correction2,
+                      const float* gnorm_sq, float max_norm, int amsgrad, void* stream);
+/* rng[1] += 1 (new dropout masks for the next step) */
+int vqa_rng_advance(void* plan, uint64_t* rng, void* stream);
 
 #ifdef __cplusplus
 }

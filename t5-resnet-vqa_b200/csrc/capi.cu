@@ -1,6 +1,7 @@
 // extern "C" surface declared in include/vqa_b200.h.
 #include "../../include/vqa_b200.h"
 
+#include "common.cuh"
 #include "gemm_ops.cuh"
 #include "tmap.cuh"
 
@@ -15,41 +16,41 @@ int vqa_debug_set_umma(int a_lbo, int a_sbo, int b_lbo, int b_sbo) {
   return 0;
 }
 
-int vqa_gemm_bf16(const vqa_gemm_args* a, void* stream) {
+int vqa_gemm_bf16(void* plan, const vqa_gemm_args* a, void* stream) {
   Epilogue e;
   e.bias = a->bias; e.relu = a->relu;
   e.relu_mask = reinterpret_cast<const __nv_bfloat16*>(a->relu_mask); e.ldm = a->ldm;
   e.drop_p = a->drop_p; e.drop_sid = a->drop_sid;
   e.rng = reinterpret_cast<const unsigned long long*>(a->rng);
-  e.residual = a->residual; e.ldr = a->ldr; e.res_fp32 = a->res_fp32;
-  e.alpha = a->alpha;
+  e.residual = a->residual; e.ldr = a->ldr; e.res_fp32 = a->res_fp32; e.res_first = a->res_first;
+  e.alpha = a->alpha; e.accumulate = a->accumulate;
   GemmOp op;
   int r = gemm_op_init(&op, a->M, a->N, a->K, a->A, a->lda, a->a_mn, a->B, a->ldb, a->b_mn, a->out,
                        a->ldo, a->out_fp32, e, a->bn, a->split_k);
   if (r) return r;
-  return gemm_op_run(&op, static_cast<cudaStream_t>(stream));
+  return submit(plan, stream, [op](cudaStream_t s) { return gemm_op_run(&op, s); });
 }
 
-int vqa_conv2d_bf16(const vqa_conv_args* a, void* stream) {
+int vqa_conv2d_bf16(void* plan, const vqa_conv_args* a, void* stream) {
   ConvGeom g;
   g.Nimg = a->N; g.H = a->H; g.W = a->W; g.Cin = a->Cin; g.Cout = a->Cout; g.R = a->R; g.S = a->S;
   g.stride = a->stride; g.pad = a->pad; g.Ho = a->Ho; g.Wo = a->Wo; g.stem7 = a->stem7;
   Epilogue e;
-  e.bias = a->bias; e.relu = a->relu; e.residual = a->residual; e.ldr = a->Cout; e.res_fp32 = 0;
+  e.bias = a->bias; e.relu = a->relu; e.residual = a->residual; e.ldr = a->Cout; e.res_fp32 = 0; e.res_first = 1;
   GemmOp op;
   int r = conv_op_init(&op, g, a->x, a->w, a->out, a->out_fp32, e, a->bn);
   if (r) return r;
-  return gemm_op_run(&op, static_cast<cudaStream_t>(stream));
+  return submit(plan, stream, [op](cudaStream_t s) { return gemm_op_run(&op, s); });
 }
 
-int vqa_conv2d_wgrad_bf16(const vqa_conv_wgrad_args* a, void* stream) {
+int vqa_conv2d_wgrad_bf16(void* plan, const vqa_conv_wgrad_args* a, void* stream) {
   ConvGeom g;
   g.Nimg = a->N; g.H = a->H; g.W = a->W; g.Cin = a->Cin; g.Cout = a->Cout; g.R = a->R; g.S = a->S;
   g.stride = 1; g.pad = a->pad; g.Ho = a->H; g.Wo = a->W; g.stem7 = 0;
   GemmOp op;
   int r = conv_wgrad_op_init(&op, g, a->dy, a->x, a->dw, a->bn, a->split_k);
   if (r) return r;
-  return gemm_op_run(&op, static_cast<cudaStream_t>(stream));
+  return submit(plan, stream, [op](cudaStream_t s) { return gemm_op_run(&op, s); });
 }
 
 }  // extern "C"

@@ -1,0 +1,123 @@
+// Shared device helpers for the bandwidth-bound kernels (vectorised 128-bit access, warp-shuffle
+// reductions, bf16 packing) and the launch-plan recorder used by every C-ABI op.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <functional>
+#include <vector>
+
+#include "rng.cuh"
+#include "tmap.cuh"
+
+namespace vqa {
+
+// ---------------------------------------------------------------------------------------------
+// Launch plan: an ordered list of pre-built kernel launches.  Every op of the C ABI either runs
+// immediately (plan == nullptr) or is appended to a plan; vqa_plan_run replays the list on a stream
+// (optionally through an instantiated CUDA graph), so a whole forward or backward pass costs one
+// host call.  Launch descriptors (tensor maps, pointers, shapes) are resolved once at record time.
+// ---------------------------------------------------------------------------------------------
+struct Plan {
+  std::vector<std::function<int(cudaStream_t)>> ops;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+};
+
+template <class F>
+inline int submit(void* plan, void* stream, F&& fn) {
+  if (plan != nullptr) {
+    static_cast<Plan*>(plan)->ops.emplace_back(std::forward<F>(fn));
+    return 0;
+  }
+  return fn(static_cast<cudaStream_t>(stream));
+}
+
+inline int launch_status(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("%s: %s", what, cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ void load_f32x8(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store_f32x8(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+__device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* p, float (&f)[8]) {
+  unpack_bf16x8(*reinterpret_cast<const uint4*>(p), f);
+}
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) = pack_bf16x8(f);
+}
+
+// Dropout on 8 consecutive elements whose first flat index is idx (idx % 8 == 0).
+struct DropCtx {
+  unsigned long long seed, offset;
+  uint32_t thresh, sid;
+  float scale;
+  bool on;
+};
+__device__ __forceinline__ DropCtx drop_ctx(float p, uint32_t sid, const unsigned long long* rng) {
+  DropCtx c;
+  c.on = p > 0.f;
+  c.sid = sid;
+  c.thresh = 0; c.scale = 1.f; c.seed = 0; c.offset = 0;
+  if (c.on) {
+    c.seed = rng[0]; c.offset = rng[1];
+    c.thresh = drop_threshold(p);
+    c.scale = 1.f / (1.f - p);
+  }
+  return c;
+}
+__device__ __forceinline__ void drop8(const DropCtx& c, unsigned long long idx, float (&v)[8]) {
+  if (!c.on) return;
+  const Philox8 r = philox8(c.seed, c.offset, c.sid, idx >> 3);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = (r.u16(i) < c.thresh) ? 0.f : v[i] * c.scale;
+}
+
+}  // namespace vqa

@@ -207,6 +207,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       out_row = tc.m0 + row;
     }
     const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
+    const bool add_res = p.residual != nullptr && blockIdx.z == 0;
     unsigned long long seed = 0, offset = 0;
     uint32_t thresh = 0;
     float keep_scale = 1.f;
@@ -227,59 +228,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      const int nc0 = tc.n0 + c * 32;
-      if (nc0 >= p.N) break;  // warp-uniform
-      uint32_t acc[32];
-      if (num_kb > 0) {
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), acc);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0u;
-      }
-      if (!row_ok) continue;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {  // groups of 8 columns
-        const int n = nc0 + g * 8;
-        if (n >= p.N) break;
-        const bool full8 = (n + 8) <= p.N;
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[g * 8 + i]) * p.alpha;
-        if (add_bias) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (n + i < p.N) v[i] += __ldg(p.bias + n + i);
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (p.relu_mask != nullptr) {
-          const __nv_bfloat16* mp = p.relu_mask + out_row * p.ldm + n;
-          if (msk_vec && full8) {
-            const uint4 mv = __ldg(reinterpret_cast<const uint4*>(mp));
-            const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float mf = bf16_bits_to_float((mw[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu);
-              if (!(mf > 0.f)) v[i] = 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (n + i < p.N && !(__bfloat162float(mp[i]) > 0.f)) v[i] = 0.f;
-          }
-        }
-        if (p.drop_p > 0.f) {
-          const unsigned long long idx = static_cast<unsigned long long>(out_row) * p.N + n;
-          const Philox8 rnd = philox8(seed, offset, p.drop_sid, idx >> 3);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = (rnd.u16(i) < thresh) ? 0.f : v[i] * keep_scale;
-        }
-        if (p.residual != nullptr) {
+      auto add_residual = [&](float (&v)[8], int n, bool full8) {
           if (p.res_fp32) {
             const float* rp = reinterpret_cast<const float*>(p.residual) + out_row * p.ldr + n;
             if (res_vec && full8) {
@@ -306,7 +255,61 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (n + i < p.N) v[i] += __bfloat162float(rp[i]);
             }
           }
+      };
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int nc0 = tc.n0 + c * 32;
+      if (nc0 >= p.N) break;  // warp-uniform
+      uint32_t acc[32];
+      if (num_kb > 0) {
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), acc);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0u;
+      }
+      if (!row_ok) continue;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {  // groups of 8 columns
+        const int n = nc0 + g * 8;
+        if (n >= p.N) break;
+        const bool full8 = (n + 8) <= p.N;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[g * 8 + i]) * p.alpha;
+        if (add_bias) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (n + i < p.N) v[i] += __ldg(p.bias + n + i);
         }
+        if (p.res_first && add_res) add_residual(v, n, full8);
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (p.relu_mask != nullptr) {
+          const __nv_bfloat16* mp = p.relu_mask + out_row * p.ldm + n;
+          if (msk_vec && full8) {
+            const uint4 mv = __ldg(reinterpret_cast<const uint4*>(mp));
+            const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float mf = bf16_bits_to_float((mw[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu);
+              if (!(mf > 0.f)) v[i] = 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (n + i < p.N && !(__bfloat162float(mp[i]) > 0.f)) v[i] = 0.f;
+          }
+        }
+        if (p.drop_p > 0.f) {
+          const unsigned long long idx = static_cast<unsigned long long>(out_row) * p.N + n;
+          const Philox8 rnd = philox8(seed, offset, p.drop_sid, idx >> 3);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = (rnd.u16(i) < thresh) ? 0.f : v[i] * keep_scale;
+        }
+        if (!p.res_first && add_res) add_residual(v, n, full8);
         // ---- store ----
         if (p.out_fp32) {
           float* op = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n;

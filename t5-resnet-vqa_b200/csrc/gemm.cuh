@@ -47,6 +47,7 @@ struct GemmParams {
   const void* residual;        // added after dropout; fp32 or bf16, row stride ldr
   long long ldr;
   int res_fp32;
+  int res_first;              // 1: add the residual before ReLU (ResNet block), else after dropout
   float alpha;                 // scale applied to the accumulator before everything else
   int dbg_a_lbo, dbg_a_sbo, dbg_b_lbo, dbg_b_sbo;  // bring-up overrides of the MN-major descriptor strides (0 = default)
 };

@@ -19,6 +19,7 @@ void fill_epilogue(GemmParams& p, const Epilogue& e) {
   p.residual = e.residual;
   p.ldr = e.ldr;
   p.res_fp32 = e.res_fp32;
+  p.res_first = e.res_first;
   p.alpha = e.alpha;
 }
 
@@ -54,7 +55,7 @@ int gemm_op_init(GemmOp* op, int M, int N, int K, const void* A, long long lda, 
   memset(&op->p, 0, sizeof(op->p));
   op->valid = false;
   if (bn != 64 && bn != 128 && bn != 256) { set_last_error("gemm: bn must be 64/128/256"); return -1; }
-  if (split_k > 1 && !out_fp32) { set_last_error("gemm: split_k needs fp32 output"); return -1; }
+  if ((split_k > 1 || epi.accumulate) && !out_fp32) { set_last_error("gemm: split_k / accumulate need fp32 output"); return -1; }
   if ((lda & 7) || (ldb & 7)) { set_last_error("gemm: lda/ldb must be multiples of 8 elements"); return -1; }
   GemmParams& p = op->p;
   p.M = M; p.N = N;
@@ -63,7 +64,7 @@ int gemm_op_init(GemmOp* op, int M, int N, int K, const void* A, long long lda, 
   p.a_mode = LOAD_2D; p.b_mode = LOAD_2D;
   p.stage_tx_bytes = 128 * 64 * 2 + bn * 64 * 2;
   p.out = out; p.ldo = ldo; p.out_fp32 = out_fp32; p.out_pixels = 0;
-  p.atomic_out = split_k > 1 ? 1 : 0;
+  p.atomic_out = (split_k > 1 || epi.accumulate) ? 1 : 0;
   fill_epilogue(p, epi);
   int r;
   if (!a_mn) r = make_tmap_2d(&op->tmA, A, M, K, lda, 64, 128);

@@ -15,7 +15,9 @@ struct Epilogue {
   const void* residual = nullptr;
   long long ldr = 0;
   int res_fp32 = 0;
+  int res_first = 0;
   float alpha = 1.f;
+  int accumulate = 0;  // fp32 out += result (red.add) instead of store
 };
 
 struct GemmOp {

@@ -1,0 +1,311 @@
+// T5LayerNorm (RMS, hf:55-68) and nn.LayerNorm (model/multi_head_vision_text_attn.py:120-126), forward and
+// backward.  HBM-bound: one warp per row, 128-bit coalesced accesses (lane l owns columns
+// (c*32 + l)*8 .. +8 for chunk c), warp-shuffle row reductions, per-thread column partials for the
+// weight gradients reduced through shared memory and finished with one red.add per column per CTA.
+#include "../../include/vqa_b200.h"
+#include "common.cuh"
+
+using namespace vqa;
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+
+inline int norm_grid(int M) {
+  int g = (M + kWarps - 1) / kWarps;
+  if (g > 148 * 2) g = 148 * 2;
+  return g < 1 ? 1 : g;
+}
+
+// --------------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y_bf16,
+                   float* __restrict__ y_f32, float* __restrict__ rstd, int M, float eps, float drop_p,
+                   uint32_t sid, const unsigned long long* __restrict__ rng) {
+  constexpr int D = NC * 256;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const DropCtx dc = drop_ctx(drop_p, sid, rng);
+  float wv[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) load_f32x8(w + (c * 32 + lane) * 8, wv[c]);
+  for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
+    const float* xr = x + static_cast<long long>(row) * D;
+    float xv[NC][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      load_f32x8(xr + (c * 32 + lane) * 8, xv[c]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss += xv[c][i] * xv[c][i];
+    }
+    ss = warp_sum(ss);
+    const float r = rsqrtf(ss * (1.f / D) + eps);
+    if (lane == 0 && rstd != nullptr) rstd[row] = r;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = wv[c][i] * (xv[c][i] * r);
+      const long long col = (c * 32 + lane) * 8;
+      drop8(dc, static_cast<unsigned long long>(row) * D + col, o);
+      if (y_bf16 != nullptr) store_bf16x8(y_bf16 + static_cast<long long>(row) * D + col, o);
+      if (y_f32 != nullptr) store_f32x8(y_f32 + static_cast<long long>(row) * D + col, o);
+    }
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+rmsnorm_bwd_kernel(const void* __restrict__ dy, int dy_fp32, const float* __restrict__ x,
+                   const float* __restrict__ w, const float* __restrict__ rstd, const float* __restrict__ dres,
+                   float* __restrict__ dx, float* __restrict__ dw, int M, float drop_p, uint32_t sid,
+                   const unsigned long long* __restrict__ rng) {
+  constexpr int D = NC * 256;
+  __shared__ float red[kWarps][D];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const DropCtx dc = drop_ctx(drop_p, sid, rng);
+  float wv[NC][8], dwp[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    load_f32x8(w + (c * 32 + lane) * 8, wv[c]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dwp[c][i] = 0.f;
+  }
+  for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
+    const long long base = static_cast<long long>(row) * D;
+    const float r = rstd[row];
+    float xv[NC][8], g[NC][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const long long col = (c * 32 + lane) * 8;
+      load_f32x8(x + base + col, xv[c]);
+      float d[8];
+      if (dy_fp32) load_f32x8(static_cast<const float*>(dy) + base + col, d);
+      else load_bf16x8(static_cast<const __nv_bfloat16*>(dy) + base + col, d);
+      drop8(dc, static_cast<unsigned long long>(base + col), d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        g[c][i] = d[i] * wv[c][i];
+        dot += g[c][i] * xv[c][i];
+        dwp[c][i] += d[i] * xv[c][i] * r;
+      }
+    }
+    dot = warp_sum(dot);
+    const float k = r * r * r * dot * (1.f / D);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const long long col = (c * 32 + lane) * 8;
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = r * g[c][i] - xv[c][i] * k;
+      if (dres != nullptr) {
+        float dr[8];
+        load_f32x8(dres + base + col, dr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += dr[i];
+      }
+      store_f32x8(dx + base + col, o);
+    }
+  }
+  if (dw != nullptr) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[warp][(c * 32 + lane) * 8 + i] = dwp[c][i];
+    __syncthreads();
+    for (int col = threadIdx.x; col < D; col += kThreads) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < kWarps; ++j) s += red[j][col];
+      atomicAdd(dw + col, s);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+layernorm_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32, float* __restrict__ mean,
+                     float* __restrict__ rstd, int M, float eps) {
+  constexpr int D = NC * 256;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float gv[NC][8], bv[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    load_f32x8(gamma + (c * 32 + lane) * 8, gv[c]);
+    load_f32x8(beta + (c * 32 + lane) * 8, bv[c]);
+  }
+  for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
+    const long long base = static_cast<long long>(row) * D;
+    float zv[NC][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      load_f32x8(z + base + (c * 32 + lane) * 8, zv[c]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += zv[c][i];
+    }
+    const float mu = warp_sum(s) * (1.f / D);
+    float vs = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = zv[c][i] - mu; vs += d * d; }
+    const float r = rsqrtf(warp_sum(vs) * (1.f / D) + eps);
+    if (lane == 0) {
+      if (mean != nullptr) mean[row] = mu;
+      if (rstd != nullptr) rstd[row] = r;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const long long col = (c * 32 + lane) * 8;
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (zv[c][i] - mu) * r * gv[c][i] + bv[c][i];
+      if (y_bf16 != nullptr) store_bf16x8(y_bf16 + base + col, o);
+      if (y_f32 != nullptr) store_f32x8(y_f32 + base + col, o);
+    }
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kThreads)
+layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dz,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M) {
+  constexpr int D = NC * 256;
+  __shared__ float red[kWarps][D];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float gv[NC][8], dgp[NC][8], dbp[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    load_f32x8(gamma + (c * 32 + lane) * 8, gv[c]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dgp[c][i] = 0.f; dbp[c][i] = 0.f; }
+  }
+  for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
+    const long long base = static_cast<long long>(row) * D;
+    const float mu = mean[row], r = rstd[row];
+    float xh[NC][8], g[NC][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const long long col = (c * 32 + lane) * 8;
+      float zv[8], d[8];
+      load_f32x8(z + base + col, zv);
+      load_f32x8(dy + base + col, d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xh[c][i] = (zv[i] - mu) * r;
+        g[c][i] = d[i] * gv[c][i];
+        s1 += g[c][i];
+        s2 += g[c][i] * xh[c][i];
+        dgp[c][i] += d[i] * xh[c][i];
+        dbp[c][i] += d[i];
+      }
+    }
+    s1 = warp_sum(s1) * (1.f / D);
+    s2 = warp_sum(s2) * (1.f / D);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = r * (g[c][i] - s1 - xh[c][i] * s2);
+      store_f32x8(dz + base + (c * 32 + lane) * 8, o);
+    }
+  }
+  // dgamma
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][(c * 32 + lane) * 8 + i] = dgp[c][i];
+  __syncthreads();
+  for (int col = threadIdx.x; col < D; col += kThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kWarps; ++j) s += red[j][col];
+    atomicAdd(dgamma + col, s);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][(c * 32 + lane) * 8 + i] = dbp[c][i];
+  __syncthreads();
+  for (int col = threadIdx.x; col < D; col += kThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kWarps; ++j) s += red[j][col];
+    atomicAdd(dbeta + col, s);
+  }
+}
+
+#define DISPATCH_NC(D, CALL)                                                         \
+  switch ((D) / 256) {                                                               \
+    case 1: { constexpr int NC = 1; CALL; break; }                                   \
+    case 2: { constexpr int NC = 2; CALL; break; }                                   \
+    case 3: { constexpr int NC = 3; CALL; break; }                                   \
+    case 4: { constexpr int NC = 4; CALL; break; }                                   \
+    default: break;                                                                  \
+  }
+
+inline int check_d(int D, const char* what) {
+  if (D % 256 != 0 || D < 256 || D > 1024) {
+    set_last_error("%s: feature size must be 256/512/768/1024 (got %d)", what, D);
+    return -1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vqa_rmsnorm_fwd(void* plan, const float* x, const float* w, void* y_bf16, float* y_f32, float* rstd, int M,
+                    int D, float eps, float drop_p, uint32_t sid, const uint64_t* rng, void* stream) {
+  if (check_d(D, "rmsnorm_fwd")) return -1;
+  return submit(plan, stream, [=](cudaStream_t s) {
+    DISPATCH_NC(D, (rmsnorm_fwd_kernel<NC><<<norm_grid(M), kThreads, 0, s>>>(
+                       x, w, static_cast<__nv_bfloat16*>(y_bf16), y_f32, rstd, M, eps, drop_p, sid,
+                       reinterpret_cast<const unsigned long long*>(rng))));
+    return launch_status("rmsnorm_fwd");
+  });
+}
+
+int vqa_rmsnorm_bwd(void* plan, const void* dy, int dy_fp32, const float* x, const float* w, const float* rstd,
+                    const float* dres, float* dx, float* dw, int M, int D, float drop_p, uint32_t sid,
+                    const uint64_t* rng, void* stream) {
+  if (check_d(D, "rmsnorm_bwd")) return -1;
+  return submit(plan, stream, [=](cudaStream_t s) {
+    DISPATCH_NC(D, (rmsnorm_bwd_kernel<NC><<<norm_grid(M), kThreads, 0, s>>>(
+                       dy, dy_fp32, x, w, rstd, dres, dx, dw, M, drop_p, sid,
+                       reinterpret_cast<const unsigned long long*>(rng))));
+    return launch_status("rmsnorm_bwd");
+  });
+}
+
+int vqa_layernorm_fwd(void* plan, const float* z, const float* gamma, const float* beta, void* y_bf16,
+                      float* y_f32, float* mean, float* rstd, int M, int D, float eps, void* stream) {
+  if (check_d(D, "layernorm_fwd")) return -1;
+  return submit(plan, stream, [=](cudaStream_t s) {
+    DISPATCH_NC(D, (layernorm_fwd_kernel<NC><<<norm_grid(M), kThreads, 0, s>>>(
+                       z, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, eps)));
+    return launch_status("layernorm_fwd");
+  });
+}
+
+int vqa_layernorm_bwd(void* plan, const float* dy, const float* z, const float* gamma, const float* mean,
+                      const float* rstd, float* dz, float* dgamma, float* dbeta, int M, int D, void* stream) {
+  if (check_d(D, "layernorm_bwd")) return -1;
+  return submit(plan, stream, [=](cudaStream_t s) {
+    DISPATCH_NC(D, (layernorm_bwd_kernel<NC><<<norm_grid(M), kThreads, 0, s>>>(dy, z, gamma, mean, rstd, dz,
+                                                                                 dgamma, dbeta, M)));
+    return launch_status("layernorm_bwd");
+  });
+}
+
+}  // extern "C"
