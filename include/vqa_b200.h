@@ -144,7 +144,7 @@ typedef struct {
   const void* k; long long ldk;
   const void* v; long long ldv;
   void* out; long long ldo;             /* bf16 context, same indexing */
-  void* probs;                          /* bf16 [B,H,Lq,Lk] softmax output (pre-dropout), saved for backward */
+  void* probs;                          /* fp32 [B,H,Lq,Lk] softmax output (pre-dropout), saved for backward; may be NULL */
   const float* bias;                    /* fp32 [H,Lq,Lk] additive or NULL */
   const long long* key_mask;            /* int64 [B,Lk], 0 = masked key, or NULL (hf:323-325) */
   float scale;                          /* 1.0 (T5) or 1/sqrt(hd) (SGA) */

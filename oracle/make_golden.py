@@ -1,0 +1,90 @@
+"""Generates tests/golden/*.pt from the UNMODIFIED reference (run in the build container only).
+
+    python oracle/make_golden.py            # needs /root/reference; writes tests/golden/<case>.pt
+
+The reference model class is imported from /root/reference untouched.  Two monkeypatches replace its weight
+DOWNLOADS (there is no network) with random-init constructors of the same architectures; the
+deterministic state_dict of oracle.vqa_oracle.random_state_dict is then loaded with strict=True, and one
+eval-mode forward + backward on the synthetic batch is frozen: log-probs, loss, per-tensor gradient L2 norms,
+full gradients of the small tensors and a strided 128-element sample of the large ones.
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import vqa_oracle as O  # noqa: E402
+
+REF = "/root/reference"
+
+CASES = {
+    # BASELINE.json configs[0]: ResNet34, batch 4, 224x224, 32-token question, 170 answers
+    "r34_b4": dict(vision="resnet34", B=4, L=32, H=224, W=224, masked_tail=0),
+    # ResNet50 path (2048->768 projection) with a padded question (key-mask handling is observable)
+    "r50_b2_masked": dict(vision="resnet50", B=2, L=32, H=224, W=224, masked_tail=10),
+    # the reference's native collate shapes: 256x256 images (64 vision tokens), 16-token questions
+    "r18_b2_256_l16": dict(vision="resnet18", B=2, L=16, H=256, W=256, masked_tail=3),
+}
+
+
+def reference_model(vision):
+    sys.path.insert(0, REF)
+    import torchvision
+    from transformers import T5Config, T5ForQuestionAnswering
+    import model.resnet_vqa_model as ref
+    for n in ("resnet18", "resnet34", "resnet50"):
+        setattr(ref, n, (lambda name: (lambda pretrained=True: getattr(torchvision.models, name)(weights=None)))(n))
+    cfg = T5Config(vocab_size=32128, d_model=768, d_kv=64, d_ff=3072, num_layers=12, num_decoder_layers=12,
+                   num_heads=12, relative_attention_num_buckets=32, relative_attention_max_distance=128,
+                   dropout_rate=0.1, layer_norm_epsilon=1e-6, feed_forward_proj="relu")
+    T5ForQuestionAnswering.from_pretrained = staticmethod(lambda name, *a, **k: T5ForQuestionAnswering(cfg))
+    return ref.ResnetVQAModel(vision, "t5-base", answer_spaces=170)
+
+
+def sample(g):
+    f = g.flatten()
+    if f.numel() <= 2304:
+        return f.clone()
+    stride = f.numel() // 128
+    return f[::stride][:128].clone()
+
+
+def main():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    only = sys.argv[1:]
+    for name, c in CASES.items():
+        if only and name not in only:
+            continue
+        sd = O.random_state_dict(c["vision"], 170, seed=0)
+        batch = O.synthetic_batch(c["B"], c["L"], c["H"], c["W"], 170, seed=1, masked_tail=c["masked_tail"])
+        m = reference_model(c["vision"])
+        missing = m.load_state_dict(sd, strict=True)
+        m.eval()  # dropout off; gradients still flow (the backbone is eval/no_grad anyway)
+        logp, loss = m(question_input_ids=batch["question_input_ids"], decoder_question_input_ids=None,
+                       question_attention_masks=batch["question_attention_masks"],
+                       decoder_question_attention_masks=None, annotation_ids=batch["annotation_ids"],
+                       image_tensors=batch["image_tensors"])
+        loss.backward()
+        grads = {k: p.grad for k, p in m.named_parameters()}
+        none_keys = sorted(k for k, g in grads.items() if g is None)
+        gold = dict(case=c, logp=logp.detach().clone(), loss=loss.detach().clone(),
+                    grad_norm={k: float(g.norm()) for k, g in grads.items() if g is not None},
+                    grad_sample={k: sample(g) for k, g in grads.items() if g is not None},
+                    grad_none=none_keys, state_dict_keys=list(m.state_dict().keys()),
+                    versions=dict(torch=torch.__version__))
+        # cross-check the restatement right here as well
+        o_logp, o_loss, o_grads = O.forward_backward(sd, c["vision"], batch)
+        print(name, "loss ref %.6f oracle %.6f | max|dlogp| %.3e | n_grad %d n_none %d | %s" % (
+            float(loss), float(o_loss), float((logp - o_logp).abs().max()), len(gold["grad_norm"]),
+            len(none_keys), missing))
+        worst = max(float((grads[k] - o_grads[k]).norm() / (grads[k].norm() + 1e-30)) for k in o_grads)
+        print(name, "worst per-tensor grad rel diff oracle vs reference: %.3e" % worst)
+        torch.save(gold, os.path.join(out_dir, name + ".pt"))
+
+
+if __name__ == "__main__":
+    main()

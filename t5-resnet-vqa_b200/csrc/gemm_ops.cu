@@ -34,7 +34,7 @@ void choose_box(int Wo, int Ho, int Nimg, int rows, bool exact, int* bw, int* bh
     for (int h = 1; w * h <= rows && h <= max_h; ++h) {
       int n = rows / (w * h);
       if (n < 1) continue;
-      if (n > Nimg) n = Nimg;
+      if (!exact && n > Nimg) n = Nimg;  // exact boxes may overhang the batch: TMA zero-fills the missing images
       if (exact && w * h * n != rows) continue;
       const long long tiles = static_cast<long long>((Wo + w - 1) / w) * ((Ho + h - 1) / h) *
                               ((Nimg + n - 1) / n);

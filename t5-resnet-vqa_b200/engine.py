@@ -1,0 +1,413 @@
+"""Execution engine of the B200-native ResnetVQAModel step.
+
+Host side only: owns the flat parameter / gradient / bf16-shadow buffers, the activation workspace and the
+recorded launch plans (one per input shape and mode), and replays them through libvqa_b200.so.  All arithmetic
+happens in the library's sm_100a kernels; torch is used for device memory, streams and autograd plumbing.
+
+Reference path being replaced: ResnetVQAModel.forward (model/resnet_vqa_model.py:101-165) and its autograd
+backward as driven by train_one_step (trainer/faster_rcnn_vqa_trainer.py:391-406).
+"""
+import ctypes
+import math
+import os
+
+import torch
+
+from . import lib as L
+
+ALIGN = 64  # elements; every parameter starts on a 256-byte boundary of the flat fp32 buffers
+
+
+def _align(n, a=ALIGN):
+    return (n + a - 1) // a * a
+
+
+def _env_flag(name, default):
+    v = os.environ.get(name)
+    if v is None:
+        return default
+    return v not in ("0", "false", "False", "")
+
+
+def t5_relative_buckets(L_q, L_k, num_buckets=32, max_distance=128):
+    """Bidirectional relative-position buckets, evaluated exactly as transformers does (hf:189-234), int32 [Lq, Lk]."""
+    ctx = torch.arange(L_q, dtype=torch.long)[:, None]
+    mem = torch.arange(L_k, dtype=torch.long)[None, :]
+    rel = mem - ctx
+    nb = num_buckets // 2
+    buckets = (rel > 0).to(torch.long) * nb
+    rel = torch.abs(rel)
+    max_exact = nb // 2
+    is_small = rel < max_exact
+    large = max_exact + (torch.log(rel.float() / max_exact) / math.log(max_distance / max_exact)
+                         * (nb - max_exact)).to(torch.long)
+    large = torch.min(large, torch.full_like(large, nb - 1))
+    buckets = buckets + torch.where(is_small, rel, large)
+    return buckets.to(torch.int32)
+
+
+class _Rec:
+    """Thin typed front of the C ABI: appends launches to `plan` (or runs them now when plan is None)."""
+
+    def __init__(self, lib, plan, stream_fn):
+        self.lib, self.plan, self.stream_fn = lib, plan, stream_fn
+
+    def _s(self):
+        return None if self.plan is not None else self.stream_fn()
+
+    def _call(self, name, *args):
+        L.check(getattr(self.lib, name)(self.plan, *args, self._s()), name)
+
+    # ---- contractions ----
+    def gemm(self, M, N, K, A, lda, a_mn, B, ldb, b_mn, out, ldo, out_fp32, bias=None, relu=0, relu_mask=None,
+             ldm=0, drop_p=0.0, sid=0, rng=None, residual=None, ldr=0, res_fp32=1, alpha=1.0, accumulate=0,
+             bn=None, split_k=1):
+        if bn is None:
+            bn, split_k = pick_tile(M, N, K, out_fp32 and not relu and relu_mask is None and drop_p == 0.0
+                                    and accumulate, split_k)
+        a = L.GemmArgs()
+        a.M, a.N, a.K = M, N, K
+        a.A, a.lda, a.a_mn = L.ptr(A), lda, a_mn
+        a.B, a.ldb, a.b_mn = L.ptr(B), ldb, b_mn
+        a.out, a.ldo, a.out_fp32 = L.ptr(out), ldo, int(out_fp32)
+        a.bias, a.relu = L.ptr(bias), int(relu)
+        a.relu_mask, a.ldm = L.ptr(relu_mask), ldm
+        a.drop_p, a.drop_sid, a.rng = float(drop_p), sid, L.ptr(rng) if drop_p > 0 else None
+        a.residual, a.ldr, a.res_fp32, a.res_first = L.ptr(residual), ldr, int(res_fp32), 0
+        a.alpha, a.accumulate, a.bn, a.split_k = alpha, int(accumulate), bn, split_k
+        L.check(self.lib.vqa_gemm_bf16(self.plan, ctypes.byref(a), self._s()), "gemm")
+
+    def linear(self, X, M, K, ldx, W, N, out, ldo, out_fp32=0, **kw):
+        """out[M,N] = epi(X[M,K] @ W[N,K]^T)"""
+        self.gemm(M, N, K, X, ldx, 0, W, K, 0, out, ldo, out_fp32, **kw)
+
+    def dgrad(self, dY, M, N, ldy, W, K, out, ldo, out_fp32=0, **kw):
+        """out[M,K] = epi(dY[M,N] @ W[N,K])"""
+        self.gemm(M, K, N, dY, ldy, 0, W, K, 1, out, ldo, out_fp32, **kw)
+
+    def wgrad(self, dY, M, N, ldy, X, K, ldx, dW, **kw):
+        """dW[N,K] (fp32) = dY[M,N]^T @ X[M,K]"""
+        self.gemm(N, K, M, dY, ldy, 1, X, ldx, 1, dW, K, 1, **kw)
+
+    def conv(self, N, H, W, Cin, Cout, R, stride, pad, x, w, out, bias=None, residual=None, relu=1, stem7=0,
+             out_fp32=0, bn=None):
+        Ho = (H + 2 * pad - R) // stride + 1
+        Wo = (W + 2 * pad - R) // stride + 1
+        if bn is None:
+            bn = pick_conv_tile(N * Ho * Wo, Cout)
+        a = L.ConvArgs()
+        a.N, a.H, a.W, a.Cin, a.Cout, a.R, a.S = N, H, W, Cin, Cout, R, R
+        a.stride, a.pad, a.Ho, a.Wo, a.stem7 = stride, pad, Ho, Wo, stem7
+        a.x, a.w, a.out, a.out_fp32 = L.ptr(x), L.ptr(w), L.ptr(out), out_fp32
+        a.bias, a.residual, a.relu, a.bn = L.ptr(bias), L.ptr(residual), int(relu), bn
+        L.check(self.lib.vqa_conv2d_bf16(self.plan, ctypes.byref(a), self._s()), "conv2d")
+        return Ho, Wo
+
+    def conv_wgrad(self, N, H, W, Cin, Cout, dy, x, dw, bn, split_k):
+        a = L.ConvWgradArgs()
+        a.N, a.H, a.W, a.Cin, a.Cout, a.R, a.S, a.pad = N, H, W, Cin, Cout, 3, 3, 1
+        a.dy, a.x, a.dw, a.bn, a.split_k = L.ptr(dy), L.ptr(x), L.ptr(dw), bn, split_k
+        L.check(self.lib.vqa_conv2d_wgrad_bf16(self.plan, ctypes.byref(a), self._s()), "conv2d_wgrad")
+
+    def attn_fwd(self, B, H, Lq, Lk, hd, q, ldq, k, ldk, v, ldv, out, ldo, probs, bias, key_mask, scale, drop_p,
+                 sid, rng):
+        a = L.AttnFwdArgs()
+        a.B, a.H, a.Lq, a.Lk, a.hd = B, H, Lq, Lk, hd
+        a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = L.ptr(q), ldq, L.ptr(k), ldk, L.ptr(v), ldv
+        a.out, a.ldo, a.probs, a.bias, a.key_mask = L.ptr(out), ldo, L.ptr(probs), L.ptr(bias), L.ptr(key_mask)
+        a.scale, a.drop_p, a.sid, a.rng = scale, float(drop_p), sid, L.ptr(rng) if drop_p > 0 else None
+        L.check(self.lib.vqa_attention_fwd(self.plan, ctypes.byref(a), self._s()), "attention_fwd")
+
+    def attn_bwd(self, B, H, Lq, Lk, hd, q, ldq, k, ldk, v, ldv, probs, dout, ldo, dq, lddq, dk, lddk, dv, lddv,
+                 dbias, scale, drop_p, sid, rng):
+        a = L.AttnBwdArgs()
+        a.B, a.H, a.Lq, a.Lk, a.hd = B, H, Lq, Lk, hd
+        a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = L.ptr(q), ldq, L.ptr(k), ldk, L.ptr(v), ldv
+        a.probs, a.dout, a.ldo = L.ptr(probs), L.ptr(dout), ldo
+        a.dq, a.lddq, a.dk, a.lddk, a.dv, a.lddv = L.ptr(dq), lddq, L.ptr(dk), lddk, L.ptr(dv), lddv
+        a.dbias, a.scale, a.drop_p, a.sid = L.ptr(dbias), scale, float(drop_p), sid
+        a.rng = L.ptr(rng) if drop_p > 0 else None
+        L.check(self.lib.vqa_attention_bwd(self.plan, ctypes.byref(a), self._s()), "attention_bwd")
+
+    # ---- everything else: positional passthrough ----
+    def __getattr__(self, name):
+        fn_name = "vqa_" + name
+        if fn_name not in L.SIGNATURES:
+            raise AttributeError(name)
+
+        def call(*args):
+            self._call(fn_name, *[L.ptr(a) if isinstance(a, torch.Tensor) else a for a in args])
+        return call
+
+
+def pick_tile(M, N, K, can_split, split_k=1):
+    """Output tile width for the 128 x bn tcgen05 GEMM: fill the 148 SMs, prefer wide tiles."""
+    tm = (M + 127) // 128
+    for bn in (256, 128, 64):
+        if bn > 64 and N < bn:
+            continue
+        tiles = tm * ((N + bn - 1) // bn)
+        if tiles >= 120 or bn == 64:
+            return bn, 1
+    return 64, 1
+
+
+def pick_conv_tile(M, Cout):
+    tm = (M + 127) // 128
+    for bn in (256, 128, 64):
+        if Cout % bn and bn > 64:
+            continue
+        if tm * ((Cout + bn - 1) // bn) >= 140 or bn == 64:
+            return bn
+    return 64
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self.lib = L.load()
+        self.device = None
+        self.plans = {}
+        self.run_id = 0
+        self.use_graphs = _env_flag("VQA_B200_GRAPHS", True)
+        self.vision_sig = None
+        self.param_sig = None
+        self.shadow_fresh = False
+        self.proj_dirty = True
+        self._ddp = None
+
+    # ------------------------------------------------------------------------------------------
+    # flat parameter layout
+    # ------------------------------------------------------------------------------------------
+    def _layout(self):
+        m = self.model
+        big, small = [], []
+        cls = m.classification_layer
+        big.append(cls.weight); small.append(cls.bias)
+        pl = m.attention_pooler.attention[0]
+        small += [pl.weight, pl.bias]
+        for sga in reversed(list(m.sga_modules)):
+            m1, m2, mlp = sga.mhatt1, sga.mhatt2, sga.ffn.mlp
+            big += [m1.linear_v.weight, m1.linear_k.weight, m1.linear_q.weight, m1.linear_merge.weight,
+                    m2.linear_v.weight, m2.linear_k.weight, m2.linear_q.weight, m2.linear_merge.weight,
+                    mlp.fc1.weight, mlp.fc2.weight]
+            small += [m1.linear_v.bias, m1.linear_k.bias, m1.linear_q.bias, m1.linear_merge.bias,
+                      m2.linear_v.bias, m2.linear_k.bias, m2.linear_q.bias, m2.linear_merge.bias,
+                      mlp.fc1.bias, mlp.fc2.bias,
+                      sga.norm1.norm.weight, sga.norm1.norm.bias, sga.norm2.norm.weight, sga.norm2.norm.bias,
+                      sga.norm3.norm.weight, sga.norm3.norm.bias]
+        proj = m._projection()
+        big.append(proj.weight); small.append(proj.bias)
+        t5 = m.lang_model
+        for blk in reversed(list(t5.block)):
+            att, ff = blk.layer[0], blk.layer[1]
+            sa = att.SelfAttention
+            big += [sa.q.weight, sa.k.weight, sa.v.weight, sa.o.weight,
+                    ff.DenseReluDense.wi.weight, ff.DenseReluDense.wo.weight]
+            small += [att.layer_norm.weight, ff.layer_norm.weight]
+            if hasattr(sa, "relative_attention_bias"):
+                small.append(sa.relative_attention_bias.weight)
+        small.append(t5.final_layer_norm.weight)
+        small.append(t5.embed_tokens.weight)
+        return big, small
+
+    def _flatten(self, device):
+        big, small = self._layout()
+        params = big + small
+        off, offs = 0, {}
+        for p in params:
+            offs[id(p)] = off
+            off += _align(p.numel())
+        self.n_big = offs[id(small[0])]
+        self.total = off
+        self.master = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+        self.shadow = torch.zeros(off, dtype=torch.bfloat16, device=device)
+        with torch.no_grad():
+            for p in params:
+                o, n = offs[id(p)], p.numel()
+                view = self.master[o:o + n].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+        self.params = params
+        self.offs = offs
+        self.device = device
+        self.param_sig = None
+        self.shadow_fresh = False
+        self.plans = {}
+        self.rng = torch.zeros(2, dtype=torch.int64, device=device)
+        seed = int(os.environ.get("VQA_B200_SEED", torch.initial_seed() & 0x7FFFFFFFFFFFFFFF))
+        self.rng[0] = seed
+        # vision caches are rebuilt whenever the frozen weights change
+        self.vision_sig = None
+        _REGISTRY[self.master.data_ptr()] = self
+
+    def _params_on(self, device):
+        p0 = self.model.classification_layer.weight
+        return (self.device == device and p0.device == device
+                and p0.data_ptr() == self.master.data_ptr() + 4 * self.offs[id(p0)])
+
+    # pointers into the flat buffers
+    def mp(self, p):
+        return self.master.data_ptr() + 4 * self.offs[id(p)]
+
+    def gp(self, p):
+        return self.grad.data_ptr() + 4 * self.offs[id(p)]
+
+    def sp(self, p):
+        return self.shadow.data_ptr() + 2 * self.offs[id(p)]
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def rec(self, plan=None):
+        return _Rec(self.lib, plan, self._stream)
+
+    # ------------------------------------------------------------------------------------------
+    # weight preparation
+    # ------------------------------------------------------------------------------------------
+    def _vision_convs(self):
+        """(conv, bn) pairs of the frozen backbone in execution order, with their role."""
+        vm = self.model.vision_model
+        out = [("stem", vm.conv1, vm.bn1)]
+        for li, layer in enumerate([vm.layer1, vm.layer2, vm.layer3, vm.layer4]):
+            for bi, blk in enumerate(layer):
+                names = ["conv1", "conv2"] + (["conv3"] if hasattr(blk, "conv3") else [])
+                for j, nm in enumerate(names):
+                    out.append(("l%d.%d.%s" % (li, bi, nm), getattr(blk, nm), getattr(blk, "bn%d" % (j + 1))))
+                if blk.downsample is not None:
+                    out.append(("l%d.%d.ds" % (li, bi), blk.downsample[0], blk.downsample[1]))
+        return out
+
+    def _prepare_vision(self):
+        convs = self._vision_convs()
+        sig = []
+        for _, c, b in convs:
+            for t in (c.weight, b.weight, b.bias, b.running_mean, b.running_var):
+                if t.device != self.device:
+                    raise RuntimeError("vision_model parameters must live on %s" % (self.device,))
+                sig.append((t.data_ptr(), t._version))
+        sig = tuple(sig)
+        if sig == self.vision_sig:
+            return
+        r = self.rec(None)
+        self.vw, self.vb = {}, {}
+        for name, c, b in convs:
+            O, I, R, S = c.weight.shape
+            Sp, Ip = (8, 8) if name == "stem" else (S, I)
+            w = torch.empty(O * R * Sp * Ip, dtype=torch.bfloat16, device=self.device)
+            bias = torch.empty(O, dtype=torch.float32, device=self.device)
+            r.fold_conv_bn(c.weight.detach().float().contiguous(), b.weight.detach(), b.bias.detach(),
+                           b.running_mean, b.running_var, float(b.eps), w, bias, O, I, R, S, Sp, Ip)
+            self.vw[name], self.vb[name] = w, bias
+        self.vision_sig = sig
+
+    def _param_signature(self):
+        return tuple(p._version for p in self.params)
+
+    def _refresh_shadow(self):
+        """bf16 copies of the fp32 master weights (what the GEMMs read) + the conv view of the projection."""
+        sig = self._param_signature()
+        r = self.rec(None)
+        if not (self.shadow_fresh and sig == self.param_sig):
+            r.cast_f32_bf16(self.master, self.shadow, self.total)
+            self.proj_dirty = True
+        if self.proj_dirty:
+            proj = self.model._projection()
+            Cin, Cout = proj.weight.shape[0], proj.weight.shape[1]
+            r.convT_weight_prep(self.mp(proj.weight), self.proj_w, Cin, Cout)
+            self.proj_dirty = False
+        self.param_sig = sig
+        self.shadow_fresh = True
+
+    def note_fused_update(self, covered):
+        """Called by VQAFusedAdamW after it updated `covered` of this engine's parameters in place (raw
+        pointers, so no version counters moved) and wrote their bf16 shadow itself."""
+        if covered == len(self.params):
+            self.proj_dirty = True
+        else:
+            self.shadow_fresh = False
+
+    # ------------------------------------------------------------------------------------------
+    # plans
+    # ------------------------------------------------------------------------------------------
+    def _ensure(self, device):
+        if device.type != "cuda":
+            raise RuntimeError("ResnetVQAModel (B200-native) runs on CUDA only: there is no CPU fallback path; "
+                               "move the model and its inputs to a cuda device")
+        if self.device is None or not self._params_on(device):
+            for p in self.model.parameters():
+                if p.device != device:
+                    raise RuntimeError("model parameters are on %s but inputs are on %s" % (p.device, device))
+            self._flatten(device)
+            proj = self.model._projection()
+            self.proj_w = torch.empty(proj.weight.numel(), dtype=torch.bfloat16, device=device)
+
+    def prepare(self):
+        """Refresh the derived weight caches (folded BN convs, bf16 shadows) if their sources changed."""
+        self._prepare_vision()
+        self._refresh_shadow()
+
+    def get_plan(self, B, Lt, H, W, training, has_labels, want_features):
+        key = (B, Lt, H, W, bool(training), bool(has_labels), bool(want_features))
+        st = self.plans.get(key)
+        if st is None:
+            from .plan_builder import build_state
+            st = build_state(self, *key)
+            self.plans[key] = st
+        return st
+
+    def run_plan(self, plan):
+        L.check(self.lib.vqa_plan_run(plan, ctypes.c_void_p(self._stream())), "plan_run")
+
+    def forward(self, st, ids, mask, labels, images):
+        """Copy the inputs into the plan's static buffers and replay the forward plan."""
+        st.ids.copy_(ids, non_blocking=True)
+        if mask is not None:
+            st.mask.copy_(mask, non_blocking=True)
+        else:
+            st.mask.fill_(1)
+        if labels is not None:
+            st.labels.copy_(labels, non_blocking=True)
+        st.images.copy_(images, non_blocking=True)
+        self.run_plan(st.fwd)
+        self.run_id += 1
+        st.run_id = self.run_id
+        self.last_state = st
+
+    def backward(self, st, gloss, glogp):
+        if st.run_id != self.run_id:
+            raise RuntimeError("backward() after another forward(): the saved activations were overwritten")
+        if gloss is not None:
+            st.gloss.copy_(gloss.reshape(1))
+        else:
+            st.gloss.zero_()
+        if glogp is not None:
+            st.glogp.copy_(glogp)
+        elif st.glogp_used:
+            st.glogp.zero_()
+        if self._ddp is not None:
+            self._ddp.backward(self, st)
+        else:
+            for seg in st.bwd_segments:
+                self.run_plan(seg.plan)
+        if st.training:
+            self.rec(None).rng_advance(self.rng)
+
+    def __del__(self):
+        try:
+            for st in self.plans.values():
+                st.destroy(self.lib)
+        except Exception:
+            pass
+
+
+_REGISTRY = {}
+
+
+def engine_for_ptr(ptr):
+    """Engine whose flat fp32 master buffer contains device address `ptr` (used by the fused optimizer)."""
+    for base, eng in _REGISTRY.items():
+        if eng.master is not None and base <= ptr < base + 4 * eng.total:
+            return eng
+    return None

@@ -5,7 +5,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqa_b200.so")
 
-c_int, c_ll, c_vp, c_f, c_u32 = ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_float, ctypes.c_uint32
+c_int, c_ll, c_vp, c_f, c_u32, c_d = (ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_float,
+                                      ctypes.c_uint32, ctypes.c_double)
 
 
 class GemmArgs(ctypes.Structure):
@@ -16,8 +17,8 @@ class GemmArgs(ctypes.Structure):
                 ("bias", c_vp), ("relu", c_int),
                 ("relu_mask", c_vp), ("ldm", c_ll),
                 ("drop_p", c_f), ("drop_sid", c_u32), ("rng", c_vp),
-                ("residual", c_vp), ("ldr", c_ll), ("res_fp32", c_int),
-                ("alpha", c_f), ("bn", c_int), ("split_k", c_int)]
+                ("residual", c_vp), ("ldr", c_ll), ("res_fp32", c_int), ("res_first", c_int),
+                ("alpha", c_f), ("accumulate", c_int), ("bn", c_int), ("split_k", c_int)]
 
 
 class ConvArgs(ctypes.Structure):
@@ -34,28 +35,86 @@ class ConvWgradArgs(ctypes.Structure):
                 ("dy", c_vp), ("x", c_vp), ("dw", c_vp), ("bn", c_int), ("split_k", c_int)]
 
 
+class AttnFwdArgs(ctypes.Structure):
+    _fields_ = [("B", c_int), ("H", c_int), ("Lq", c_int), ("Lk", c_int), ("hd", c_int),
+                ("q", c_vp), ("ldq", c_ll), ("k", c_vp), ("ldk", c_ll), ("v", c_vp), ("ldv", c_ll),
+                ("out", c_vp), ("ldo", c_ll), ("probs", c_vp), ("bias", c_vp), ("key_mask", c_vp),
+                ("scale", c_f), ("drop_p", c_f), ("sid", c_u32), ("rng", c_vp)]
+
+
+class AttnBwdArgs(ctypes.Structure):
+    _fields_ = [("B", c_int), ("H", c_int), ("Lq", c_int), ("Lk", c_int), ("hd", c_int),
+                ("q", c_vp), ("ldq", c_ll), ("k", c_vp), ("ldk", c_ll), ("v", c_vp), ("ldv", c_ll),
+                ("probs", c_vp), ("dout", c_vp), ("ldo", c_ll),
+                ("dq", c_vp), ("lddq", c_ll), ("dk", c_vp), ("lddk", c_ll), ("dv", c_vp), ("lddv", c_ll),
+                ("dbias", c_vp), ("scale", c_f), ("drop_p", c_f), ("sid", c_u32), ("rng", c_vp)]
+
+
+# every symbol include/vqa_b200.h declares, with its argument types (tests check the library exports all)
+_P = c_vp
+SIGNATURES = {
+    "vqa_last_error": (ctypes.c_char_p, []),
+    "vqa_version": (c_int, []),
+    "vqa_debug_set_umma": (c_int, [c_int, c_int, c_int, c_int]),
+    "vqa_plan_create": (c_vp, []),
+    "vqa_plan_destroy": (c_int, [_P]),
+    "vqa_plan_size": (c_int, [_P]),
+    "vqa_plan_run": (c_int, [_P, _P]),
+    "vqa_plan_capture_graph": (c_int, [_P, _P]),
+    "vqa_gemm_bf16": (c_int, [_P, ctypes.POINTER(GemmArgs), _P]),
+    "vqa_conv2d_bf16": (c_int, [_P, ctypes.POINTER(ConvArgs), _P]),
+    "vqa_conv2d_wgrad_bf16": (c_int, [_P, ctypes.POINTER(ConvWgradArgs), _P]),
+    "vqa_cast_f32_bf16": (c_int, [_P, _P, _P, c_ll, _P]),
+    "vqa_memset_zero": (c_int, [_P, _P, c_ll, _P]),
+    "vqa_axpy_f32": (c_int, [_P, _P, _P, c_f, c_ll, _P]),
+    "vqa_fold_conv_bn": (c_int, [_P, _P, _P, _P, _P, _P, c_f, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "vqa_convT_weight_prep": (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    "vqa_convT_wgrad_unprep": (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    "vqa_image_to_stem": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "vqa_nhwc_to_nchw_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "vqa_maxpool3x3s2": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "vqa_embedding_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_f, c_u32, _P, _P]),
+    "vqa_embedding_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_f, c_u32, _P, _P]),
+    "vqa_rmsnorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_f, c_f, c_u32, _P, _P]),
+    "vqa_rmsnorm_bwd": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_f, c_u32, _P, _P]),
+    "vqa_t5_bias_build": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "vqa_t5_bias_grad": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "vqa_attention_fwd": (c_int, [_P, ctypes.POINTER(AttnFwdArgs), _P]),
+    "vqa_attention_bwd": (c_int, [_P, ctypes.POINTER(AttnBwdArgs), _P]),
+    "vqa_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_f, _P]),
+    "vqa_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "vqa_dropout_cast": (c_int, [_P, _P, _P, c_ll, c_int, c_f, c_u32, _P, _P]),
+    "vqa_colsum_bf16": (c_int, [_P, _P, c_ll, _P, c_int, c_int, _P]),
+    "vqa_pooler_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "vqa_pooler_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "vqa_logsoftmax_nll_fwd": (c_int, [_P, _P, c_ll, _P, _P, _P, c_int, c_int, _P]),
+    "vqa_logsoftmax_nll_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_ll, c_int, c_int, _P]),
+    "vqa_sumsq_f32": (c_int, [_P, _P, c_ll, _P, _P]),
+    "vqa_adamw_amsgrad": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_ll, c_d, c_d, c_d, c_d, c_d, c_d, c_d, _P, c_f,
+                                  c_int, _P]),
+    "vqa_rng_advance": (c_int, [_P, _P, _P]),
+}
+EXPORTS = list(SIGNATURES)
+
 _lib = None
 
 
 def load():
-    """Return the loaded library; raises RuntimeError if it has not been built."""
+    """Return the loaded library; raises RuntimeError if it has not been built (there is no fallback)."""
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 "libvqa_b200.so is missing (%s): run `python -c 'import __graft_entry__ as g; g.build()'`; "
-                "there is no fallback path" % LIB_PATH)
+                "there is no CPU or torch fallback path" % LIB_PATH)
         import torch  # noqa: F401  (loads libcudart.so.12 the library links against)
-        _lib = ctypes.CDLL(LIB_PATH)
-        _lib.vqa_last_error.restype = ctypes.c_char_p
-        for name in EXPORTS:
-            if name != "vqa_last_error":
-                getattr(_lib, name).restype = c_int
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
     return _lib
-
-
-# every symbol include/vqa_b200.h declares (tests check the library exports all of them)
-EXPORTS = ["vqa_last_error", "vqa_version", "vqa_debug_set_umma", "vqa_gemm_bf16", "vqa_conv2d_bf16", "vqa_conv2d_wgrad_bf16"]
 
 
 def check(rc, what=""):
@@ -69,4 +128,9 @@ def stream_ptr():
 
 
 def ptr(t):
-    return c_vp(t.data_ptr()) if t is not None else c_vp(0)
+    """Device pointer of a tensor (or None / int passthrough)."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()

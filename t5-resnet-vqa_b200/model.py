@@ -1,0 +1,159 @@
+"""Drop-in `ResnetVQAModel` (reference: model/resnet_vqa_model.py:28-231) whose training step runs in
+hand-written sm_100a kernels.  Same constructor, forward / generate_answers signatures, attribute names and
+state_dict keys as the reference, so trainer/faster_rcnn_vqa_trainer.py drives it unchanged.
+"""
+import os
+import warnings
+from collections import defaultdict
+
+import torch
+import torch.nn as nn
+
+from . import modules as M
+from .engine import Engine
+
+
+class _StepFunction(torch.autograd.Function):
+    """One autograd node for the whole model: forward replays the forward plan, backward the backward plan.
+    Gradients come back as views of the engine's flat fp32 gradient buffer (no per-parameter copies)."""
+
+    @staticmethod
+    def forward(ctx, model, st, has_labels, *params):
+        ctx.model, ctx.st = model, st
+        ctx.set_materialize_grads(False)
+        logp = st.logp.clone()
+        if has_labels:
+            return logp, st.loss.reshape(()).clone()
+        return logp
+
+    @staticmethod
+    def backward(ctx, glogp, gloss=None):
+        model, st = ctx.model, ctx.st
+        eng = model._engine
+        params = eng.params
+        # gradient accumulation across steps: an existing .grad that aliases our flat buffer must be detached
+        # from it before the buffer is overwritten
+        p0 = params[0]
+        if p0.grad is not None and p0.grad.data_ptr() == eng.gp(p0):
+            for p in params:
+                if p.grad is not None:
+                    p.grad = p.grad.clone()
+        eng.backward(st, gloss, glogp)
+        grads = []
+        g = eng.grad
+        for p in params:
+            if p.requires_grad:
+                o = eng.offs[id(p)]
+                grads.append(g[o:o + p.numel()].view(p.shape))
+            else:
+                grads.append(None)
+        return (None, None, None) + tuple(grads)
+
+
+class ResnetVQAModel(nn.Module):
+    """ResNet-18/34/50 (frozen, eval) -> ConvTranspose2d 512/2048->768 -> tokens; T5-base encoder over the
+    question; 3 x SGA; AttentionPooler; Linear(768 -> answer_spaces); log_softmax; NLLLoss."""
+
+    def __init__(self, vision_model_name: str, language_model_name: str, answer_spaces: int,
+                 fine_tune_lm_encoder: bool = True, fine_tune_lm_decoder: bool = True,
+                 fine_tune_vision: bool = True, num_attention_blocks=3, device="cpu"):
+        super().__init__()
+        if vision_model_name not in M.ResNet.CFG:
+            raise ValueError("vision_model_name must be one of %s" % sorted(M.ResNet.CFG))
+        if language_model_name != "t5-base":
+            raise ValueError("language_model_name must be 't5-base'")
+        self.vision_model_name = vision_model_name
+        self.language_model_name = language_model_name
+        self.vision_model = M.ResNet(vision_model_name)
+        self.lang_model = M.T5Encoder()
+        self.upscale_layer = M.ConvTranspose2d(512, 768, 3)
+        self.downscale_layer = M.ConvTranspose2d(2048, 768, 3)
+        self.sga_modules = nn.ModuleList([M.SGA() for _ in range(num_attention_blocks)])
+        self.classification_layer = M.Linear(768, answer_spaces)
+        self.attention_pooler = M.AttentionPooler(768)
+        self.fine_tune_lm_encoder = fine_tune_lm_encoder
+        self.fine_tune_lm_decoder = fine_tune_lm_decoder
+        self.fine_tune_vision = fine_tune_vision
+        self.device = device
+        self.num_beams = 2
+        self.max_answer_length = 5
+        self.temperature_scaler = 1.5
+        object.__setattr__(self, "_engine", Engine(self))
+        self._load_pretrained()
+
+    # the reference always starts from pretrained torchvision / HF weights (model/resnet_vqa_model.py:51-62);
+    # offline they cannot be downloaded, so they are only used when already cached locally.
+    def _load_pretrained(self):
+        mode = os.environ.get("VQA_B200_PRETRAINED", "auto")
+        if mode == "0":
+            return
+        loaded = []
+        try:
+            import torchvision
+            weights = torchvision.models.get_model_weights(self.vision_model_name).DEFAULT
+            hub = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(weights.url))
+            if os.path.exists(hub):
+                self.vision_model.load_state_dict(torch.load(hub, map_location="cpu"))
+                loaded.append("vision")
+        except Exception as e:  # pragma: no cover - depends on local caches
+            if mode == "1":
+                raise
+            warnings.warn("pretrained %s not loaded: %s" % (self.vision_model_name, e))
+        try:
+            from transformers import T5ForQuestionAnswering
+            hf = T5ForQuestionAnswering.from_pretrained(self.language_model_name, local_files_only=True)
+            self.lang_model.load_state_dict(hf.encoder.state_dict())
+            loaded.append("t5")
+        except Exception as e:  # pragma: no cover - depends on local caches
+            if mode == "1":
+                raise
+        if mode == "1" and len(loaded) != 2:
+            raise RuntimeError("VQA_B200_PRETRAINED=1 but pretrained weights are not available offline")
+        self.pretrained_loaded = loaded
+
+    def _projection(self):
+        return self.downscale_layer if self.vision_model_name == "resnet50" else self.upscale_layer
+
+    # ------------------------------------------------------------------------------------------
+    def _run(self, question_input_ids, question_attention_masks, annotation_ids, image_tensors, want_features):
+        if question_input_ids.dim() != 2 or image_tensors.dim() != 4:
+            raise ValueError("expected question_input_ids [B, L] and image_tensors [B, 3, H, W]")
+        dev = image_tensors.device
+        eng = self._engine
+        eng._ensure(dev)
+        self.vision_model.eval()  # side effect of the reference forward (model/resnet_vqa_model.py:116,127)
+        B, Lt = question_input_ids.shape
+        H, W = image_tensors.shape[2], image_tensors.shape[3]
+        has_labels = annotation_ids is not None
+        eng.prepare()
+        st = eng.get_plan(B, Lt, H, W, self.training, has_labels, want_features)
+        eng.forward(st, question_input_ids, question_attention_masks, annotation_ids, image_tensors)
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in eng.params)
+        if needs_grad:
+            out = _StepFunction.apply(self, st, has_labels, *eng.params)
+            logp, loss = (out if has_labels else (out, None))
+        else:
+            logp = st.logp.clone()
+            loss = st.loss.reshape(()).clone() if has_labels else None
+        feats = st.features.clone() if want_features else None
+        return logp, loss, feats
+
+    def forward(self, question_input_ids: torch.Tensor, decoder_question_input_ids: torch.Tensor = None,
+                question_attention_masks: torch.Tensor = None, decoder_question_attention_masks: torch.Tensor = None,
+                annotation_ids: torch.Tensor = None, image_tensors: torch.Tensor = None,
+                answer_input_ids: torch.Tensor = None, pixel_values: torch.Tensor = None,
+                answer_attention_masks: torch.Tensor = None, question_type_ids: torch.Tensor = None):
+        logp, loss, _ = self._run(question_input_ids, question_attention_masks, annotation_ids, image_tensors, False)
+        return logp, loss
+
+    def generate_answers(self, question_input_ids: torch.Tensor, decoder_question_input_ids: torch.Tensor = None,
+                         question_attention_masks: torch.Tensor = None,
+                         decoder_question_attention_masks: torch.Tensor = None, image_tensors: torch.Tensor = None,
+                         annotation_ids: torch.Tensor = None, answer_input_ids: torch.Tensor = None,
+                         pixel_values: torch.Tensor = None, answer_attention_masks: torch.Tensor = None,
+                         question_type_ids: torch.Tensor = None):
+        logp, loss, feats = self._run(question_input_ids, question_attention_masks, annotation_ids, image_tensors,
+                                      True)
+        d = defaultdict()
+        d["features"] = feats
+        return logp, loss, d

@@ -1,0 +1,159 @@
+"""Fused AdamW(amsgrad) for the reference trainer's optimizer boundary.
+
+The trainer builds its optimizer with `getattr(torch.optim, optimizer_kwargs["type"])(param_groups, **kwargs)`
+(trainer/faster_rcnn_vqa_trainer.py:265-267), so importing this package registers `torch.optim.VQAFusedAdamW`;
+naming it in the JSON config's `"type"` swaps torch's AdamW for the sm_100a kernel without touching the trainer.
+Semantics follow torch.optim.AdamW (single-tensor path, amsgrad supported): per-group lr / betas / eps /
+weight_decay, per-parameter `state[p] = {step, exp_avg, exp_avg_sq, max_exp_avg_sq}`, `state_dict()` compatible.
+
+Parameters that live in an Engine's flat fp32 buffer are updated range-by-range: adjacent parameters of one group
+are merged into a single launch that also refreshes the bf16 shadow the GEMMs read.
+"""
+import ctypes
+
+import torch
+
+from . import lib as L
+from .engine import engine_for_ptr
+
+
+class VQAFusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=False,
+                 max_grad_norm=None):
+        if lr < 0 or eps < 0 or weight_decay < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
+            raise ValueError("invalid AdamW hyper-parameters")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad)
+        super().__init__(params, defaults)
+        self.max_grad_norm = max_grad_norm  # optional fused clip_grad_norm_ (None: the trainer clips itself)
+        self._lib = None
+        self._ranges = None
+        self._sig = None
+        self._gnorm = None
+
+    def _ensure_state(self, p):
+        st = self.state[p]
+        if len(st) == 0:
+            st["step"] = torch.tensor(0.0)
+            st["exp_avg"] = None
+        return st
+
+    def _build(self):
+        """Group parameters with gradients into contiguous (param, grad) ranges and allocate flat state."""
+        ranges = []
+        for gi, group in enumerate(self.param_groups):
+            items = [p for p in group["params"] if p.grad is not None]
+            for p in items:
+                if p.dtype != torch.float32 or not p.is_cuda:
+                    raise RuntimeError("VQAFusedAdamW needs fp32 CUDA parameters (no CPU fallback)")
+                if not p.is_contiguous() or not p.grad.is_contiguous():
+                    raise RuntimeError("VQAFusedAdamW needs contiguous parameters and gradients")
+            items.sort(key=lambda p: p.data_ptr())
+            cur = None
+            for p in items:
+                pp, gp, n = p.data_ptr(), p.grad.data_ptr(), p.numel()
+                if cur is not None:
+                    gap = (pp - cur["p_end"]) // 4
+                    # merge when the parameter follows the previous one (alignment padding allowed) in BOTH buffers
+                    if 0 <= gap < 64 and (pp - cur["p_end"]) == (gp - cur["g_end"]) and cur["dev"] == p.device:
+                        cur["params"].append((p, (pp - cur["p0"]) // 4))
+                        cur["p_end"], cur["g_end"] = pp + 4 * n, gp + 4 * n
+                        continue
+                cur = dict(group=gi, p0=pp, g0=gp, p_end=pp + 4 * n, g_end=gp + 4 * n, params=[(p, 0)],
+                           dev=p.device)
+                ranges.append(cur)
+        for r in ranges:
+            n = (r["p_end"] - r["p0"]) // 4
+            r["n"] = n
+            amsgrad = self.param_groups[r["group"]]["amsgrad"]
+            # reuse existing per-parameter state (load_state_dict / previous layout), else zeros
+            m = torch.zeros(n, dtype=torch.float32, device=r["dev"])
+            v = torch.zeros_like(m)
+            vmax = torch.zeros_like(m) if amsgrad else None
+            for p, off in r["params"]:
+                st = self._ensure_state(p)
+                k = p.numel()
+                views = dict(exp_avg=m[off:off + k].view(p.shape), exp_avg_sq=v[off:off + k].view(p.shape))
+                if amsgrad:
+                    views["max_exp_avg_sq"] = vmax[off:off + k].view(p.shape)
+                for key, view in views.items():
+                    old = st.get(key)
+                    if old is not None:
+                        view.copy_(old)
+                    st[key] = view
+            r["m"], r["v"], r["vmax"] = m, v, vmax
+            eng = engine_for_ptr(r["p0"])
+            r["engine"] = eng
+            r["shadow"] = None
+            if eng is not None:
+                r["shadow"] = eng.shadow.data_ptr() + (r["p0"] - eng.master.data_ptr()) // 2
+        # per-group step counters: every state entry of a group references the same tensor
+        group_step = {}
+        for r in ranges:
+            gi = r["group"]
+            if gi not in group_step:
+                prev = [float(self.state[p]["step"]) for p, _ in r["params"]]
+                group_step[gi] = torch.tensor(max(prev) if prev else 0.0)
+            r["step"] = group_step[gi]
+            for p, _ in r["params"]:
+                self.state[p]["step"] = group_step[gi]
+        self._ranges = ranges
+
+    def _signature(self):
+        sig = []
+        for group in self.param_groups:
+            for p in group["params"]:
+                g = p.grad
+                sig.append((p.data_ptr(), g.data_ptr() if g is not None else 0))
+        return tuple(sig)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        if self._lib is None:
+            self._lib = L.load()
+        sig = self._signature()
+        if sig != self._sig:
+            self._build()
+            self._sig = sig
+        lib = self._lib
+        gnorm_ptr = None
+        if self.max_grad_norm is not None and self._ranges:
+            dev = self._ranges[0]["dev"]
+            if self._gnorm is None or self._gnorm.device != dev:
+                self._gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._gnorm.zero_()
+            s = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for r in self._ranges:
+                L.check(lib.vqa_sumsq_f32(None, r["g0"], r["n"], self._gnorm.data_ptr(), s), "sumsq")
+            gnorm_ptr = self._gnorm.data_ptr()
+        steps = {}
+        engines = {}
+        for r in self._ranges:
+            group = self.param_groups[r["group"]]
+            gi = r["group"]
+            if gi not in steps:
+                # one step counter per group, shared by its parameters' state entries (they advance together)
+                steps[gi] = float(r["step"].add_(1.0))
+            t = steps[gi]
+            b1, b2 = group["betas"]
+            s = ctypes.c_void_p(torch.cuda.current_stream(r["dev"]).cuda_stream)
+            L.check(lib.vqa_adamw_amsgrad(
+                None, r["p0"], r["g0"], r["m"].data_ptr(), r["v"].data_ptr(),
+                r["vmax"].data_ptr() if r["vmax"] is not None else None, r["shadow"], r["n"],
+                float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                1.0 - b1 ** t, 1.0 - b2 ** t, gnorm_ptr,
+                float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0,
+                int(bool(group["amsgrad"])), s), "adamw")
+            if r["engine"] is not None:
+                engines[r["engine"]] = engines.get(r["engine"], 0) + len(r["params"])
+        for eng, covered in engines.items():
+            eng.note_fused_update(covered)
+        return loss
+
+
+def register():
+    """Expose the optimizer where the reference trainer looks it up: getattr(torch.optim, "<type>")."""
+    torch.optim.VQAFusedAdamW = VQAFusedAdamW

@@ -1,0 +1,430 @@
+"""Records the forward and backward launch plans of one ResnetVQAModel step for a fixed input shape.
+
+Forward  = model/resnet_vqa_model.py:114-160 (frozen ResNet body -> ConvTranspose2d projection -> tokens;
+           T5 encoder; 3 x SGA; AttentionPooler; classifier; log_softmax + NLL).
+Backward = the autograd graph of that forward, written out by hand in reverse (no gradient reaches the frozen
+           backbone: the reference runs it under torch.no_grad()).
+Every buffer is allocated once here; the plans hold raw device pointers into them and into the engine's flat
+parameter / gradient / bf16-shadow buffers, so a step replays with two host calls (or two CUDA graph launches).
+"""
+import ctypes
+import math
+
+import torch
+
+from . import lib as L
+from .engine import t5_relative_buckets
+
+
+class Segment:
+    def __init__(self, plan, grad_lo, grad_hi):
+        self.plan, self.grad_lo, self.grad_hi = plan, grad_lo, grad_hi
+
+
+class State:
+    def destroy(self, lib):
+        for p in [self.fwd] + [s.plan for s in self.bwd_segments]:
+            if p:
+                lib.vqa_plan_destroy(p)
+        self.fwd, self.bwd_segments = None, []
+
+
+class _Alloc:
+    def __init__(self, device):
+        self.device, self.keep = device, []
+
+    def __call__(self, *shape, dtype=torch.bfloat16, zero=False):
+        t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.device)
+        self.keep.append(t)
+        return t
+
+
+def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
+    m = eng.model
+    dev = eng.device
+    lib = eng.lib
+    st = State()
+    st.training, st.run_id = training, -1
+    al = _Alloc(dev)
+    st.alloc = al
+    f32, bf16, i64 = torch.float32, torch.bfloat16, torch.int64
+    rng = eng.rng
+    D = 768
+    A = m.classification_layer.weight.shape[0]
+    Apad = (A + 7) // 8 * 8
+    p_t5 = 0.1 if training else 0.0     # T5Config.dropout_rate
+    p_sga = 0.1 if training else 0.0    # TextConfiguration.DROPOUT_R
+    sid_counter = [0]
+
+    def new_sid():
+        sid_counter[0] += 1
+        return sid_counter[0]
+
+    # ---- static inputs / outputs ----
+    st.ids = al(B, Lt, dtype=i64, zero=True)
+    st.mask = al(B, Lt, dtype=i64, zero=True)
+    st.labels = al(B, dtype=i64, zero=True)
+    st.images = al(B, 3, H, W, dtype=f32, zero=True)
+    st.logp = al(B, A, dtype=f32, zero=True)
+    st.loss = al(1, dtype=f32, zero=True)
+    st.gloss = al(1, dtype=f32, zero=True)
+    st.glogp = al(B, A, dtype=f32, zero=True)
+    st.glogp_used = False
+
+    fwd = lib.vqa_plan_create()
+    r = eng.rec(fwd)
+    M = B * Lt
+
+    # =============================================================================================
+    # frozen ResNet body (tv:266-277 without avgpool/fc), NHWC bf16, BatchNorm folded
+    # =============================================================================================
+    vm = m.vision_model
+    stem_in = al(B, H, W + 8, 8)
+    r.image_to_stem(st.images, stem_in, B, H, W)
+    H1, W1 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    c1 = al(B, H1, W1, 64)
+    r.conv(B, H, W, 8, 64, 7, 2, 3, stem_in, eng.vw["stem"], c1, bias=eng.vb["stem"], relu=1, stem7=1)
+    Hc, Wc = (H1 + 2 - 3) // 2 + 1, (W1 + 2 - 3) // 2 + 1
+    x = al(B, Hc, Wc, 64)
+    r.maxpool3x3s2(c1, x, B, H1, W1, 64)
+    C = 64
+    for li, layer in enumerate([vm.layer1, vm.layer2, vm.layer3, vm.layer4]):
+        for bi, blk in enumerate(layer):
+            pre = "l%d.%d." % (li, bi)
+            s = blk.stride
+            if hasattr(blk, "conv3"):      # Bottleneck (tv:143-163)
+                planes = blk.conv1.weight.shape[0]
+                t1 = al(B, Hc, Wc, planes)
+                r.conv(B, Hc, Wc, C, planes, 1, 1, 0, x, eng.vw[pre + "conv1"], t1, bias=eng.vb[pre + "conv1"])
+                Ho, Wo = (Hc + 2 - 3) // s + 1, (Wc + 2 - 3) // s + 1
+                t2 = al(B, Ho, Wo, planes)
+                r.conv(B, Hc, Wc, planes, planes, 3, s, 1, t1, eng.vw[pre + "conv2"], t2, bias=eng.vb[pre + "conv2"])
+                Cout = planes * 4
+                if blk.downsample is not None:
+                    idn = al(B, Ho, Wo, Cout)
+                    r.conv(B, Hc, Wc, C, Cout, 1, s, 0, x, eng.vw[pre + "ds"], idn, bias=eng.vb[pre + "ds"], relu=0)
+                else:
+                    idn = x
+                y = al(B, Ho, Wo, Cout)
+                r.conv(B, Ho, Wo, planes, Cout, 1, 1, 0, t2, eng.vw[pre + "conv3"], y, bias=eng.vb[pre + "conv3"],
+                       residual=idn, relu=1)
+            else:                          # BasicBlock (tv:89-105)
+                planes = blk.conv1.weight.shape[0]
+                Ho, Wo = (Hc + 2 - 3) // s + 1, (Wc + 2 - 3) // s + 1
+                t1 = al(B, Ho, Wo, planes)
+                r.conv(B, Hc, Wc, C, planes, 3, s, 1, x, eng.vw[pre + "conv1"], t1, bias=eng.vb[pre + "conv1"])
+                Cout = planes
+                if blk.downsample is not None:
+                    idn = al(B, Ho, Wo, Cout)
+                    r.conv(B, Hc, Wc, C, Cout, 1, s, 0, x, eng.vw[pre + "ds"], idn, bias=eng.vb[pre + "ds"], relu=0)
+                else:
+                    idn = x
+                y = al(B, Ho, Wo, Cout)
+                r.conv(B, Ho, Wo, planes, Cout, 3, 1, 1, t1, eng.vw[pre + "conv2"], y, bias=eng.vb[pre + "conv2"],
+                       residual=idn, relu=1)
+            x, C, Hc, Wc = y, Cout, Ho, Wo
+    feat, Cf, Hf, Wf = x, C, Hc, Wc
+    st.feat_shape = (B, Cf, Hf, Wf)
+    if want_features:
+        st.features = al(B, Cf, Hf, Wf, dtype=f32)
+        r.nhwc_to_nchw_f32(feat, st.features, B, Hf, Wf, Cf)
+
+    # channel projection = ConvTranspose2d(k3,s1,p1) as a 3x3 same conv with flipped/transposed weights
+    # (model/resnet_vqa_model.py:124,135) writing [B*hw, 768] tokens directly (:142-143)
+    proj = m._projection()
+    if proj.weight.shape[0] != Cf:
+        raise RuntimeError("projection expects %d channels, backbone gives %d" % (proj.weight.shape[0], Cf))
+    Ty = Hf * Wf
+    My = B * Ty
+    y0 = al(My, D)
+    r.conv(B, Hf, Wf, Cf, D, 3, 1, 1, feat, eng.proj_w, y0, bias=eng.mp(proj.bias), relu=0)
+
+    # =============================================================================================
+    # T5 encoder (hf:637-792)
+    # =============================================================================================
+    t5 = m.lang_model
+    cfg = t5.cfg
+    nH, dkv, dff, vocab = cfg["num_heads"], cfg["d_kv"], cfg["d_ff"], cfg["vocab"]
+    inner = nH * dkv
+    eps_t5 = float(cfg["eps"])
+    blocks = list(t5.block)
+    nblk = len(blocks)
+    hid = [al(M, D, dtype=f32) for _ in range(nblk + 1)]
+    sid_embed = new_sid()
+    r.embedding_fwd(st.ids, eng.mp(t5.embed_tokens.weight), hid[0], M, D, vocab, p_t5, sid_embed, rng)
+    bucket = t5_relative_buckets(Lt, Lt, cfg["num_buckets"], cfg["max_distance"]).to(dev).contiguous()
+    al.keep.append(bucket)
+    relw = blocks[0].layer[0].SelfAttention.relative_attention_bias.weight
+    pos_bias = al(nH, Lt, Lt, dtype=f32)
+    r.t5_bias_build(eng.mp(relw), bucket, pos_bias, nH, Lt, cfg["num_buckets"])
+    saved_t5 = []
+    for bi, blk in enumerate(blocks):
+        att, ff = blk.layer[0], blk.layer[1]
+        sa, dd = att.SelfAttention, ff.DenseReluDense
+        sv = dict(y1=al(M, D), rstd1=al(M, dtype=f32), qkv=al(M, 3 * inner), probs=al(B * nH * Lt * Lt, dtype=f32),
+                  ctx=al(M, inner), hmid=al(M, D, dtype=f32), y2=al(M, D), rstd2=al(M, dtype=f32), h=al(M, dff),
+                  sid_p=new_sid(), sid_o=new_sid(), sid_h=new_sid(), sid_f=new_sid())
+        r.rmsnorm_fwd(hid[bi], eng.mp(att.layer_norm.weight), sv["y1"], None, sv["rstd1"], M, D, eps_t5, 0.0, 0, None)
+        # fused q|k|v projection: the three [768,768] weights are adjacent in the flat bf16 shadow
+        r.linear(sv["y1"], M, D, D, eng.sp(sa.q.weight), 3 * inner, sv["qkv"], 3 * inner)
+        qkv = sv["qkv"]
+        r.attn_fwd(B, nH, Lt, Lt, dkv, qkv, 3 * inner, qkv.data_ptr() + 2 * inner, 3 * inner,
+                   qkv.data_ptr() + 4 * inner, 3 * inner, sv["ctx"], inner, sv["probs"], pos_bias, st.mask, 1.0,
+                   p_t5, sv["sid_p"], rng)
+        r.linear(sv["ctx"], M, inner, inner, eng.sp(sa.o.weight), D, sv["hmid"], D, out_fp32=1,
+                 drop_p=p_t5, sid=sv["sid_o"], rng=rng, residual=hid[bi], ldr=D, res_fp32=1)
+        r.rmsnorm_fwd(sv["hmid"], eng.mp(ff.layer_norm.weight), sv["y2"], None, sv["rstd2"], M, D, eps_t5, 0.0, 0, None)
+        r.linear(sv["y2"], M, D, D, eng.sp(dd.wi.weight), dff, sv["h"], dff, relu=1, drop_p=p_t5, sid=sv["sid_h"],
+                 rng=rng)
+        r.linear(sv["h"], M, dff, dff, eng.sp(dd.wo.weight), D, hid[bi + 1], D, out_fp32=1,
+                 drop_p=p_t5, sid=sv["sid_f"], rng=rng, residual=sv["hmid"], ldr=D, res_fp32=1)
+        saved_t5.append(sv)
+    text_f32, text_bf16, rstd_f = al(M, D, dtype=f32), al(M, D), al(M, dtype=f32)
+    sid_final = new_sid()
+    r.rmsnorm_fwd(hid[nblk], eng.mp(t5.final_layer_norm.weight), text_bf16, text_f32, rstd_f, M, D, eps_t5, p_t5,
+                  sid_final, rng)
+
+    # =============================================================================================
+    # SGA stack (model/multi_head_vision_text_attn.py:145-158; x = text for every layer, y = previous output)
+    # =============================================================================================
+    Hs, hd = 8, D // 8
+    scale = 1.0 / math.sqrt(hd)
+    sgas = list(m.sga_modules)
+    saved_sga = []
+    y_bf16, Ly = y0, Ty
+    out_f32 = None
+    for li, sga in enumerate(sgas):
+        Myl = B * Ly
+        m1, m2, mlp = sga.mhatt1, sga.mhatt2, sga.ffn.mlp
+        sv = dict(y=y_bf16, Ly=Ly,
+                  qkv1=al(M, 3 * D), probs1=al(B * Hs * Lt * Lt, dtype=f32), ctx1=al(M, D), z1=al(M, D, dtype=f32),
+                  mean1=al(M, dtype=f32), rstd1=al(M, dtype=f32), x1f=al(M, D, dtype=f32), x1b=al(M, D),
+                  q2=al(M, D), vk2=al(Myl, 2 * D), probs2=al(B * Hs * Lt * Ly, dtype=f32), ctx2=al(M, D),
+                  z2=al(M, D, dtype=f32), mean2=al(M, dtype=f32), rstd2=al(M, dtype=f32),
+                  x2f=al(M, D, dtype=f32), x2b=al(M, D), hm=al(M, D), z3=al(M, D, dtype=f32),
+                  mean3=al(M, dtype=f32), rstd3=al(M, dtype=f32), of=al(M, D, dtype=f32), ob=al(M, D),
+                  sid_p1=new_sid(), sid_r1=new_sid(), sid_p2=new_sid(), sid_r2=new_sid(), sid_h=new_sid(),
+                  sid_r3=new_sid())
+        # mhatt1(v=x, k=x, q=x): fused v|k|q projection
+        r.linear(text_bf16, M, D, D, eng.sp(m1.linear_v.weight), 3 * D, sv["qkv1"], 3 * D,
+                 bias=eng.mp(m1.linear_v.bias))
+        q1 = sv["qkv1"]
+        r.attn_fwd(B, Hs, Lt, Lt, hd, q1.data_ptr() + 4 * D, 3 * D, q1.data_ptr() + 2 * D, 3 * D, q1, 3 * D,
+                   sv["ctx1"], D, sv["probs1"], None, None, scale, p_sga, sv["sid_p1"], rng)
+        r.linear(sv["ctx1"], M, D, D, eng.sp(m1.linear_merge.weight), D, sv["z1"], D, out_fp32=1,
+                 bias=eng.mp(m1.linear_merge.bias), drop_p=p_sga, sid=sv["sid_r1"], rng=rng, residual=text_f32,
+                 ldr=D, res_fp32=1)
+        r.layernorm_fwd(sv["z1"], eng.mp(sga.norm1.norm.weight), eng.mp(sga.norm1.norm.bias), sv["x1b"], sv["x1f"],
+                        sv["mean1"], sv["rstd1"], M, D, float(sga.norm1.norm.eps))
+        # mhatt2(v=y, k=y, q=x1)
+        r.linear(sv["x1b"], M, D, D, eng.sp(m2.linear_q.weight), D, sv["q2"], D, bias=eng.mp(m2.linear_q.bias))
+        r.linear(y_bf16, Myl, D, D, eng.sp(m2.linear_v.weight), 2 * D, sv["vk2"], 2 * D,
+                 bias=eng.mp(m2.linear_v.bias))
+        vk = sv["vk2"]
+        r.attn_fwd(B, Hs, Lt, Ly, hd, sv["q2"], D, vk.data_ptr() + 2 * D, 2 * D, vk, 2 * D, sv["ctx2"], D,
+                   sv["probs2"], None, None, scale, p_sga, sv["sid_p2"], rng)
+        r.linear(sv["ctx2"], M, D, D, eng.sp(m2.linear_merge.weight), D, sv["z2"], D, out_fp32=1,
+                 bias=eng.mp(m2.linear_merge.bias), drop_p=p_sga, sid=sv["sid_r2"], rng=rng, residual=sv["x1f"],
+                 ldr=D, res_fp32=1)
+        r.layernorm_fwd(sv["z2"], eng.mp(sga.norm2.norm.weight), eng.mp(sga.norm2.norm.bias), sv["x2b"], sv["x2f"],
+                        sv["mean2"], sv["rstd2"], M, D, float(sga.norm2.norm.eps))
+        # FFN
+        r.linear(sv["x2b"], M, D, D, eng.sp(mlp.fc1.weight), D, sv["hm"], D, bias=eng.mp(mlp.fc1.bias), relu=1,
+                 drop_p=p_sga, sid=sv["sid_h"], rng=rng)
+        r.linear(sv["hm"], M, D, D, eng.sp(mlp.fc2.weight), D, sv["z3"], D, out_fp32=1, bias=eng.mp(mlp.fc2.bias),
+                 drop_p=p_sga, sid=sv["sid_r3"], rng=rng, residual=sv["x2f"], ldr=D, res_fp32=1)
+        r.layernorm_fwd(sv["z3"], eng.mp(sga.norm3.norm.weight), eng.mp(sga.norm3.norm.bias), sv["ob"], sv["of"],
+                        sv["mean3"], sv["rstd3"], M, D, float(sga.norm3.norm.eps))
+        saved_sga.append(sv)
+        y_bf16, Ly, out_f32 = sv["ob"], Lt, sv["of"]
+
+    # =============================================================================================
+    # head: AttentionPooler + classifier + log_softmax/NLL (model/resnet_vqa_model.py:152-160)
+    # =============================================================================================
+    pl = m.attention_pooler.attention[0]
+    cls = m.classification_layer
+    pool_w, pooled_b = al(B, Lt, dtype=f32), al(B, D)
+    r.pooler_fwd(out_f32, eng.mp(pl.weight), eng.mp(pl.bias), pool_w, None, pooled_b, B, Lt, D)
+    logits = al(B, Apad, dtype=f32, zero=True)
+    r.linear(pooled_b, B, D, D, eng.sp(cls.weight), A, logits, Apad, out_fp32=1, bias=eng.mp(cls.bias), bn=64)
+    r.logsoftmax_nll_fwd(logits, Apad, st.labels if has_labels else None, st.logp,
+                         st.loss if has_labels else None, B, A)
+    st.fwd = fwd
+    st.n_fwd_launches = lib.vqa_plan_size(fwd)
+
+    # =============================================================================================
+    # backward
+    # =============================================================================================
+    st.bwd_segments = []
+    segs = st.bwd_segments
+
+    def new_segment():
+        return lib.vqa_plan_create()
+
+    def close_segment(plan, lo_param, hi_param_end):
+        segs.append(Segment(plan, lo_param, hi_param_end))
+
+    o = eng.offs
+    # scratch shared by all layers
+    g_bf = al(M, D)            # dropout-masked residual-branch gradient (bf16 GEMM operand)
+    dpre = al(M, max(dff, D))  # gradient before ReLU
+    dsm = al(M, D)             # small bf16 [M,768] gradients (dy of a norm, dctx)
+    dqkv = al(M, 3 * D)
+    dvk = al(B * max(Ty, Lt), 2 * D)
+    dH = al(M, D, dtype=f32)   # running gradient of the T5 residual stream / SGA x-stream
+    dText = al(M, D, dtype=f32)
+    dY = [al(M, D, dtype=f32), al(M, D, dtype=f32)]
+    dX = al(M, D, dtype=f32)
+    dZ = al(M, D, dtype=f32)
+    dy0 = al(My, D)            # gradient of the vision tokens (bf16, wgrad operand)
+    dlogits = al(B, Apad, zero=True)
+    dpooled = al(B, D, dtype=f32)
+    dbias_pos = al(nH, Lt, Lt, dtype=f32)
+    proj_dw = al(D, 9 * Cf, dtype=f32)
+
+    # ---- segment 0: head + SGA + projection ----
+    bp = new_segment()
+    r = eng.rec(bp)
+    n_small = eng.total - eng.n_big
+    r.memset_zero(eng.grad.data_ptr() + 4 * eng.n_big, 4 * n_small)
+    r.memset_zero(dbias_pos, 4 * nH * Lt * Lt)
+    r.logsoftmax_nll_bwd(st.logp, st.labels if has_labels else None, st.gloss, st.glogp, dlogits, Apad, B, A)
+    st.glogp_used = True
+    r.colsum_bf16(dlogits, Apad, eng.gp(cls.bias), B, A)
+    r.wgrad(dlogits, B, A, Apad, pooled_b, D, D, eng.gp(cls.weight), bn=64)
+    r.dgrad(dlogits, B, A, Apad, eng.sp(cls.weight), D, dpooled, D, out_fp32=1, bn=64)
+    dOut = dY[0]
+    r.pooler_bwd(out_f32, eng.mp(pl.weight), pool_w, dpooled, dOut, eng.gp(pl.weight), eng.gp(pl.bias), B, Lt, D)
+
+    first_text = True
+    for li in reversed(range(len(sgas))):
+        sga, sv = sgas[li], saved_sga[li]
+        m1, m2, mlp = sga.mhatt1, sga.mhatt2, sga.ffn.mlp
+        Ly = sv["Ly"]
+        Myl = B * Ly
+        # norm3 / FFN
+        r.layernorm_bwd(dOut, sv["z3"], eng.mp(sga.norm3.norm.weight), sv["mean3"], sv["rstd3"], dZ,
+                        eng.gp(sga.norm3.norm.weight), eng.gp(sga.norm3.norm.bias), M, D)
+        r.dropout_cast(dZ, g_bf, M, D, p_sga, sv["sid_r3"], rng)
+        r.colsum_bf16(g_bf, D, eng.gp(mlp.fc2.bias), M, D)
+        r.wgrad(g_bf, M, D, D, sv["hm"], D, D, eng.gp(mlp.fc2.weight))
+        r.dgrad(g_bf, M, D, D, eng.sp(mlp.fc2.weight), D, dpre, D, relu_mask=sv["hm"], ldm=D, drop_p=p_sga,
+                sid=sv["sid_h"], rng=rng)
+        r.colsum_bf16(dpre, D, eng.gp(mlp.fc1.bias), M, D)
+        r.wgrad(dpre, M, D, D, sv["x2b"], D, D, eng.gp(mlp.fc1.weight))
+        r.dgrad(dpre, M, D, D, eng.sp(mlp.fc1.weight), D, dX, D, out_fp32=1, residual=dZ, ldr=D, res_fp32=1)
+        # norm2 / mhatt2
+        r.layernorm_bwd(dX, sv["z2"], eng.mp(sga.norm2.norm.weight), sv["mean2"], sv["rstd2"], dZ,
+                        eng.gp(sga.norm2.norm.weight), eng.gp(sga.norm2.norm.bias), M, D)
+        r.dropout_cast(dZ, g_bf, M, D, p_sga, sv["sid_r2"], rng)
+        r.colsum_bf16(g_bf, D, eng.gp(m2.linear_merge.bias), M, D)
+        r.wgrad(g_bf, M, D, D, sv["ctx2"], D, D, eng.gp(m2.linear_merge.weight))
+        r.dgrad(g_bf, M, D, D, eng.sp(m2.linear_merge.weight), D, dsm, D)
+        vk = sv["vk2"]
+        r.attn_bwd(B, Hs, Lt, Ly, hd, sv["q2"], D, vk.data_ptr() + 2 * D, 2 * D, vk, 2 * D, sv["probs2"], dsm, D,
+                   dqkv, D, dvk.data_ptr() + 2 * D, 2 * D, dvk, 2 * D, None, scale, p_sga, sv["sid_p2"], rng)
+        r.colsum_bf16(dqkv, D, eng.gp(m2.linear_q.bias), M, D)
+        r.colsum_bf16(dvk, 2 * D, eng.gp(m2.linear_v.bias), Myl, 2 * D)
+        r.wgrad(dqkv, M, D, D, sv["x1b"], D, D, eng.gp(m2.linear_q.weight))
+        r.wgrad(dvk, Myl, 2 * D, 2 * D, sv["y"], D, D, eng.gp(m2.linear_v.weight))
+        r.dgrad(dqkv, M, D, D, eng.sp(m2.linear_q.weight), D, dX, D, out_fp32=1, residual=dZ, ldr=D, res_fp32=1)
+        if li > 0:
+            dPrev = dY[1] if dOut is dY[0] else dY[0]
+            r.dgrad(dvk, Myl, 2 * D, 2 * D, eng.sp(m2.linear_v.weight), D, dPrev, D, out_fp32=1)
+        else:
+            dPrev = None
+            r.dgrad(dvk, Myl, 2 * D, 2 * D, eng.sp(m2.linear_v.weight), D, dy0, D)
+        # norm1 / mhatt1
+        r.layernorm_bwd(dX, sv["z1"], eng.mp(sga.norm1.norm.weight), sv["mean1"], sv["rstd1"], dZ,
+                        eng.gp(sga.norm1.norm.weight), eng.gp(sga.norm1.norm.bias), M, D)
+        r.dropout_cast(dZ, g_bf, M, D, p_sga, sv["sid_r1"], rng)
+        r.colsum_bf16(g_bf, D, eng.gp(m1.linear_merge.bias), M, D)
+        r.wgrad(g_bf, M, D, D, sv["ctx1"], D, D, eng.gp(m1.linear_merge.weight))
+        r.dgrad(g_bf, M, D, D, eng.sp(m1.linear_merge.weight), D, dsm, D)
+        q1 = sv["qkv1"]
+        r.attn_bwd(B, Hs, Lt, Lt, hd, q1.data_ptr() + 4 * D, 3 * D, q1.data_ptr() + 2 * D, 3 * D, q1, 3 * D,
+                   sv["probs1"], dsm, D, dqkv.data_ptr() + 4 * D, 3 * D, dqkv.data_ptr() + 2 * D, 3 * D, dqkv, 3 * D,
+                   None, scale, p_sga, sv["sid_p1"], rng)
+        r.colsum_bf16(dqkv, 3 * D, eng.gp(m1.linear_v.bias), M, 3 * D)
+        r.wgrad(dqkv, M, 3 * D, 3 * D, text_bf16, D, D, eng.gp(m1.linear_v.weight))
+        # x is the T5 output for every layer: its gradient accumulates over the three layers
+        r.dgrad(dqkv, M, 3 * D, 3 * D, eng.sp(m1.linear_v.weight), D, dText, D, out_fp32=1, residual=dZ, ldr=D,
+                res_fp32=1, accumulate=0 if first_text else 1)
+        first_text = False
+        dOut = dPrev
+
+    # projection: bias grad + wgrad of the equivalent 3x3 conv, mapped back to the ConvTranspose2d layout
+    r.colsum_bf16(dy0, D, eng.gp(proj.bias), My, D)
+    wg_bn = 256 if Cf % 256 == 0 else (128 if Cf % 128 == 0 else 64)
+    n_kb = (My + 63) // 64
+    tiles = ((D + 127) // 128) * (9 * Cf // wg_bn)
+    split = 1
+    if tiles < 148 and n_kb >= 8:
+        split = min(4, max(1, 296 // max(tiles, 1)), n_kb // 4)
+    if split > 1:
+        r.memset_zero(proj_dw, 4 * D * 9 * Cf)
+    r.conv_wgrad(B, Hf, Wf, Cf, D, dy0, feat, proj_dw, wg_bn, split)
+    r.convT_wgrad_unprep(proj_dw, eng.gp(proj.weight), Cf, D)
+    blk_last = blocks[-1].layer[0].SelfAttention.q.weight
+    close_segment(bp, 0, o[id(blk_last)])
+
+    # ---- T5 encoder backward, a few blocks per segment ----
+    bp = new_segment()
+    r = eng.rec(bp)
+    r.rmsnorm_bwd(dText, 1, hid[nblk], eng.mp(t5.final_layer_norm.weight), rstd_f, None, dH,
+                  eng.gp(t5.final_layer_norm.weight), M, D, p_t5, sid_final, rng)
+    blocks_per_seg = 3
+    seg_lo = o[id(blk_last)]
+    for bi in reversed(range(nblk)):
+        blk, sv = blocks[bi], saved_t5[bi]
+        att, ff = blk.layer[0], blk.layer[1]
+        sa, dd = att.SelfAttention, ff.DenseReluDense
+        # FFN sub-layer
+        r.dropout_cast(dH, g_bf, M, D, p_t5, sv["sid_f"], rng)
+        r.wgrad(g_bf, M, D, D, sv["h"], dff, dff, eng.gp(dd.wo.weight))
+        r.dgrad(g_bf, M, D, D, eng.sp(dd.wo.weight), dff, dpre, dff, relu_mask=sv["h"], ldm=dff, drop_p=p_t5,
+                sid=sv["sid_h"], rng=rng)
+        r.wgrad(dpre, M, dff, dff, sv["y2"], D, D, eng.gp(dd.wi.weight))
+        r.dgrad(dpre, M, dff, dff, eng.sp(dd.wi.weight), D, dsm, D)
+        r.rmsnorm_bwd(dsm, 0, sv["hmid"], eng.mp(ff.layer_norm.weight), sv["rstd2"], dH, dH,
+                      eng.gp(ff.layer_norm.weight), M, D, 0.0, 0, None)
+        # self-attention sub-layer
+        r.dropout_cast(dH, g_bf, M, D, p_t5, sv["sid_o"], rng)
+        r.wgrad(g_bf, M, D, D, sv["ctx"], inner, inner, eng.gp(sa.o.weight))
+        r.dgrad(g_bf, M, D, D, eng.sp(sa.o.weight), inner, dsm, inner)
+        qkv = sv["qkv"]
+        r.attn_bwd(B, nH, Lt, Lt, dkv, qkv, 3 * inner, qkv.data_ptr() + 2 * inner, 3 * inner,
+                   qkv.data_ptr() + 4 * inner, 3 * inner, sv["probs"], dsm, inner,
+                   dqkv, 3 * inner, dqkv.data_ptr() + 2 * inner, 3 * inner, dqkv.data_ptr() + 4 * inner, 3 * inner,
+                   dbias_pos, 1.0, p_t5, sv["sid_p"], rng)
+        r.wgrad(dqkv, M, 3 * inner, 3 * inner, sv["y1"], D, D, eng.gp(sa.q.weight))
+        r.dgrad(dqkv, M, 3 * inner, 3 * inner, eng.sp(sa.q.weight), D, dsm, D)
+        r.rmsnorm_bwd(dsm, 0, hid[bi], eng.mp(att.layer_norm.weight), sv["rstd1"], dH, dH,
+                      eng.gp(att.layer_norm.weight), M, D, 0.0, 0, None)
+        if bi > 0 and (nblk - bi) % blocks_per_seg == 0:
+            hi = o[id(blocks[bi - 1].layer[0].SelfAttention.q.weight)]
+            close_segment(bp, seg_lo, hi)
+            seg_lo = hi
+            bp = new_segment()
+            r = eng.rec(bp)
+    r.t5_bias_grad(dbias_pos, bucket, eng.gp(relw), nH, Lt, cfg["num_buckets"])
+    r.embedding_bwd(st.ids, dH, eng.gp(t5.embed_tokens.weight), M, D, vocab, p_t5, sid_embed, rng)
+    close_segment(bp, seg_lo, eng.total)
+    st.n_bwd_launches = sum(lib.vqa_plan_size(s.plan) for s in segs)
+
+    # warm every kernel once outside capture (function attributes, module loading), then capture graphs
+    if eng.use_graphs:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            sp = ctypes.c_void_p(side.cuda_stream)
+            L.check(lib.vqa_plan_run(fwd, sp), "plan warm-up (fwd)")
+            for s in segs:
+                L.check(lib.vqa_plan_run(s.plan, sp), "plan warm-up (bwd)")
+            side.synchronize()
+            L.check(lib.vqa_plan_capture_graph(fwd, sp), "graph capture (fwd)")
+            for s in segs:
+                L.check(lib.vqa_plan_capture_graph(s.plan, sp), "graph capture (bwd)")
+            side.synchronize()
+        torch.cuda.current_stream(dev).wait_stream(side)
+    return st

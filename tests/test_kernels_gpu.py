@@ -1,0 +1,440 @@
+"""Kernel-level parity (GPU): every C-ABI entry point against the matching torch fp32 op on the same inputs.
+Tolerances: bf16-operand contractions rel-Frobenius <= 6e-3 (bf16 output rounding 2^-9 dominates);
+fp32-output contractions <= 2e-5 relative to an fp32 reference fed the same bf16-rounded operands;
+bandwidth kernels <= 1e-5 (fp32) / 4e-3 (bf16 outputs)."""
+import ctypes
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import Caller, cosine, rel_fro
+
+pytestmark = pytest.mark.gpu
+BF, F32 = torch.bfloat16, torch.float32
+
+
+@pytest.fixture(scope="module")
+def C(pkg, cuda):
+    return Caller(pkg)
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=F32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda().to(dtype)
+
+
+def rng_state(seed=1234, offset=7):
+    return torch.tensor([seed, offset], dtype=torch.int64, device="cuda")
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,bn", [(2048, 768, 768, 64), (2048, 2304, 768, 256), (2048, 3072, 768, 256),
+                                      (2048, 768, 3072, 128), (64, 170, 768, 64), (200, 170, 776, 64),
+                                      (128, 768, 768, 64), (196, 1536, 768, 128)])
+def test_linear_forward_bias_relu(C, M, N, K, bn):
+    X, W, b = rnd(M, K, seed=1, dtype=BF), rnd(N, K, seed=2, scale=K ** -0.5, dtype=BF), rnd(N, seed=3)
+    ldo = (N + 7) // 8 * 8
+    out = torch.zeros(M, ldo, dtype=BF, device="cuda")
+    C.linear(X, M, K, K, W, N, out, ldo, bias=b, relu=1, bn=bn)
+    ref = F.relu(X.float() @ W.float().t() + b)
+    assert rel_fro(out[:, :N], ref) < 6e-3
+    if ldo > N:
+        assert float(out[:, N:].abs().max()) == 0.0
+
+
+def test_linear_fp32_residual_and_accumulate(C):
+    M, N, K = 2048, 768, 3072
+    X, W, R = rnd(M, K, seed=1, dtype=BF), rnd(N, K, seed=2, scale=K ** -0.5, dtype=BF), rnd(M, N, seed=3)
+    out = torch.zeros(M, N, device="cuda")
+    C.linear(X, M, K, K, W, N, out, N, out_fp32=1, residual=R, ldr=N, res_fp32=1, bn=64)
+    ref = X.float() @ W.float().t() + R
+    assert rel_fro(out, ref) < 2e-5
+    C.linear(X, M, K, K, W, N, out, N, out_fp32=1, residual=R, ldr=N, res_fp32=1, accumulate=1, bn=128)
+    assert rel_fro(out, 2 * ref) < 2e-5
+
+
+def test_split_k(C):
+    M, N, K = 256, 256, 2048
+    X, W = rnd(M, K, seed=1, dtype=BF), rnd(N, K, seed=2, dtype=BF)
+    out = torch.zeros(M, N, device="cuda")
+    C.linear(X, M, K, K, W, N, out, N, out_fp32=1, bn=128, split_k=4)
+    assert rel_fro(out, X.float() @ W.float().t()) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(2048, 768, 3072, 256), (2048, 3072, 768, 128), (64, 170, 768, 64),
+                                      (2048, 2304, 768, 128)])
+def test_dgrad_with_relu_mask(C, M, N, K, bn):
+    """dX[M,K] = (dY[M,N] @ W[N,K]) masked by saved activation > 0."""
+    ld = (N + 7) // 8 * 8
+    dY = torch.zeros(M, ld, dtype=BF, device="cuda")
+    dY[:, :N] = rnd(M, N, seed=1, dtype=BF)
+    W, act = rnd(N, K, seed=2, scale=N ** -0.5, dtype=BF), rnd(M, K, seed=3, dtype=BF)
+    out = torch.zeros(M, K, dtype=BF, device="cuda")
+    C.dgrad(dY, M, N, ld, W, K, out, K, relu_mask=act, ldm=K, bn=bn)
+    ref = (dY[:, :N].float() @ W.float()) * (act.float() > 0)
+    assert rel_fro(out, ref) < 6e-3
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(2048, 768, 768, 64), (2048, 3072, 768, 128), (2048, 768, 3072, 256),
+                                      (64, 170, 768, 64), (196, 1536, 768, 128), (2048, 2304, 768, 128)])
+def test_wgrad(C, M, N, K, bn):
+    """dW[N,K] = dY[M,N]^T @ X[M,K] (both operands MN-major)."""
+    ld = (N + 7) // 8 * 8
+    dY = torch.zeros(M, ld, dtype=BF, device="cuda")
+    dY[:, :N] = rnd(M, N, seed=1, dtype=BF)
+    X = rnd(M, K, seed=2, dtype=BF)
+    dW = torch.zeros(N, K, device="cuda")
+    C.wgrad(dY, M, N, ld, X, K, K, dW, bn=bn)
+    assert rel_fro(dW, dY[:, :N].float().t() @ X.float()) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# convolutions
+# ------------------------------------------------------------------------------------------------
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("N,H,Cin,Cout,R,s,p,bn,res", [
+    (4, 56, 64, 64, 3, 1, 1, 64, False), (4, 56, 64, 256, 1, 1, 0, 128, False),
+    (4, 28, 128, 512, 1, 1, 0, 256, True), (4, 56, 128, 128, 3, 2, 1, 128, False),
+    (4, 56, 256, 512, 1, 2, 0, 128, False), (8, 14, 256, 256, 3, 1, 1, 128, True),
+    (8, 7, 512, 512, 3, 1, 1, 64, True), (4, 8, 512, 768, 3, 1, 1, 128, False)])
+def test_conv_bias_residual_relu(C, N, H, Cin, Cout, R, s, p, bn, res):
+    x = rnd(N, Cin, H, H, seed=1, dtype=BF)
+    w = rnd(Cout, Cin, R, R, seed=2, scale=(Cin * R * R) ** -0.5, dtype=BF)
+    b = rnd(Cout, seed=3)
+    ref = F.conv2d(x.float(), w.float(), b, stride=s, padding=p)
+    r = None
+    if res:
+        r = rnd(*ref.shape, seed=4, dtype=BF)
+        ref = ref + r.float()
+    ref = F.relu(ref)
+    out = torch.zeros(N, ref.shape[2], ref.shape[3], Cout, dtype=BF, device="cuda")
+    wk = w.permute(0, 2, 3, 1).contiguous()
+    C.conv(N, H, H, Cin, Cout, R, s, p, nhwc(x), wk, out, bias=b, residual=nhwc(r) if res else None, relu=1, bn=bn)
+    assert rel_fro(out, nhwc(ref)) < 6e-3
+
+
+@pytest.mark.parametrize("N,H", [(2, 224), (2, 64), (3, 256)])
+def test_stem_fold_pack_maxpool(C, N, H):
+    """image_to_stem + fold_conv_bn + stem conv + maxpool == conv7x7/2 -> BN(eval) -> ReLU -> MaxPool(3,2,1)."""
+    img = torch.rand(N, 3, H, H, generator=torch.Generator().manual_seed(5)).cuda()
+    w = rnd(64, 3, 7, 7, seed=6, scale=147 ** -0.5)
+    gamma, beta = 0.5 + torch.rand(64).cuda(), rnd(64, seed=7, scale=0.1)
+    mean, var = rnd(64, seed=8, scale=0.1), 0.5 + torch.rand(64).cuda()
+    ref = F.relu(F.batch_norm(F.conv2d(img, w, None, 2, 3), mean, var, gamma, beta, False, 0.0, 1e-5))
+    ref = F.max_pool2d(ref, 3, 2, 1)
+    xp = torch.empty(N, H, H + 8, 8, dtype=BF, device="cuda")
+    C.image_to_stem(img, xp, N, H, H)
+    wk = torch.empty(64 * 7 * 8 * 8, dtype=BF, device="cuda")
+    bias = torch.empty(64, device="cuda")
+    C.fold_conv_bn(w, gamma, beta, mean, var, 1e-5, wk, bias, 64, 3, 7, 7, 8, 8)
+    Ho = (H + 6 - 7) // 2 + 1
+    c1 = torch.zeros(N, Ho, Ho, 64, dtype=BF, device="cuda")
+    C.conv(N, H, H, 8, 64, 7, 2, 3, xp, wk, c1, bias=bias, relu=1, stem7=1, bn=64)
+    Hp = (Ho + 2 - 3) // 2 + 1
+    out = torch.zeros(N, Hp, Hp, 64, dtype=BF, device="cuda")
+    C.maxpool3x3s2(c1, out, N, Ho, Ho, 64)
+    assert rel_fro(out, nhwc(ref)) < 8e-3
+
+
+@pytest.mark.parametrize("N,H,Cin,bn,split", [(8, 7, 512, 256, 1), (16, 7, 2048, 256, 2), (4, 8, 512, 128, 1)])
+def test_convT_projection_forward_and_wgrad(C, N, H, Cin, bn, split):
+    """ConvTranspose2d(k3,s1,p1) == 3x3 same conv on the prepared weight; wgrad maps back to [Cin,Cout,3,3]."""
+    Cout = 768
+    x = rnd(N, Cin, H, H, seed=1, dtype=BF)
+    w = rnd(Cin, Cout, 3, 3, seed=2, scale=(Cout * 9) ** -0.5).requires_grad_(True)
+    b = rnd(Cout, seed=3)
+    ref = F.conv_transpose2d(x.float(), w, b, 1, 1)
+    dy = rnd(N, Cout, H, H, seed=4, dtype=BF)
+    ref.backward(dy.float())
+    wk = torch.empty(Cout * 9 * Cin, dtype=BF, device="cuda")
+    C.convT_weight_prep(w.detach(), wk, Cin, Cout)
+    out = torch.zeros(N * H * H, Cout, dtype=BF, device="cuda")
+    C.conv(N, H, H, Cin, Cout, 3, 1, 1, nhwc(x), wk, out, bias=b, relu=0)
+    assert rel_fro(out, nhwc(ref.detach()).view(-1, Cout)) < 8e-3
+    dwc = torch.zeros(Cout, 9 * Cin, device="cuda")
+    C.conv_wgrad(N, H, H, Cin, Cout, nhwc(dy), nhwc(x), dwc, bn, split)
+    dw = torch.empty_like(w)
+    C.convT_wgrad_unprep(dwc, dw, Cin, Cout)
+    assert rel_fro(dw, w.grad) < 2e-5
+    bsum = torch.zeros(Cout, device="cuda")
+    C.colsum_bf16(nhwc(dy), Cout, bsum, N * H * H, Cout)
+    assert rel_fro(bsum, dy.float().sum((0, 2, 3))) < 1e-5
+
+
+def test_nhwc_to_nchw(C):
+    x = rnd(3, 7, 7, 512, seed=1, dtype=BF)
+    out = torch.empty(3, 512, 7, 7, device="cuda")
+    C.nhwc_to_nchw_f32(x, out, 3, 7, 7, 512)
+    assert torch.equal(out, x.float().permute(0, 3, 1, 2))
+
+
+# ------------------------------------------------------------------------------------------------
+# norms
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M", [128, 2048, 77])
+def test_rmsnorm_fwd_bwd(C, M):
+    D = 768
+    x = rnd(M, D, seed=1, scale=3.0).requires_grad_(True)
+    w = (0.75 + 0.5 * torch.rand(D)).cuda().requires_grad_(True)
+    var = x.pow(2).mean(-1, keepdim=True)
+    y = w * (x * torch.rsqrt(var + 1e-6))
+    dy, dres = rnd(M, D, seed=2), rnd(M, D, seed=3)
+    y.backward(dy)
+    yb, yf, rstd = torch.empty(M, D, dtype=BF, device="cuda"), torch.empty(M, D, device="cuda"), torch.empty(M, device="cuda")
+    C.rmsnorm_fwd(x.detach(), w.detach(), yb, yf, rstd, M, D, 1e-6, 0.0, 0, None)
+    assert rel_fro(yf, y.detach()) < 1e-5 and rel_fro(yb, y.detach()) < 4e-3
+    dx, dw = torch.empty(M, D, device="cuda"), torch.zeros(D, device="cuda")
+    C.rmsnorm_bwd(dy, 1, x.detach(), w.detach(), rstd, dres, dx, dw, M, D, 0.0, 0, None)
+    assert rel_fro(dx, x.grad + dres) < 1e-5 and rel_fro(dw, w.grad) < 1e-5
+    # bf16 upstream gradient, in-place residual accumulation (dx aliases dres)
+    dyb = dy.to(BF)
+    acc = dres.clone()
+    dw.zero_()
+    C.rmsnorm_bwd(dyb, 0, x.detach(), w.detach(), rstd, acc, acc, dw, M, D, 0.0, 0, None)
+    x.grad = None
+    w.grad = None
+    y2 = w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6))
+    y2.backward(dyb.float())
+    assert rel_fro(acc, x.grad + dres) < 1e-5 and rel_fro(dw, w.grad) < 1e-5
+
+
+@pytest.mark.parametrize("M", [128, 2048, 50])
+def test_layernorm_fwd_bwd(C, M):
+    D = 768
+    z = rnd(M, D, seed=1, scale=2.0).requires_grad_(True)
+    g = (0.75 + 0.5 * torch.rand(D)).cuda().requires_grad_(True)
+    b = rnd(D, seed=2, scale=0.1).requires_grad_(True)
+    y = F.layer_norm(z, (D,), g, b, 1e-5)
+    dy = rnd(M, D, seed=3)
+    y.backward(dy)
+    yb, yf = torch.empty(M, D, dtype=BF, device="cuda"), torch.empty(M, D, device="cuda")
+    mean, rstd = torch.empty(M, device="cuda"), torch.empty(M, device="cuda")
+    C.layernorm_fwd(z.detach(), g.detach(), b.detach(), yb, yf, mean, rstd, M, D, 1e-5)
+    assert rel_fro(yf, y.detach()) < 1e-5 and rel_fro(yb, y.detach()) < 4e-3
+    dz, dg, db = torch.empty(M, D, device="cuda"), torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    C.layernorm_bwd(dy, z.detach(), g.detach(), mean, rstd, dz, dg, db, M, D)
+    assert rel_fro(dz, z.grad) < 1e-5 and rel_fro(dg, g.grad) < 1e-5 and rel_fro(db, b.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# T5 embedding / bias
+# ------------------------------------------------------------------------------------------------
+def test_embedding_and_bias(C, pkg):
+    from t5_resnet_vqa_b200.engine import t5_relative_buckets
+    M, D, V = 256, 768, 1000
+    ids = torch.randint(0, V, (M,), generator=torch.Generator().manual_seed(0)).cuda()
+    ids[:8] = 3  # duplicates exercise the scatter-add
+    table = rnd(V, D, seed=1).requires_grad_(True)
+    out = torch.empty(M, D, device="cuda")
+    C.embedding_fwd(ids, table.detach(), out, M, D, V, 0.0, 0, None)
+    assert torch.equal(out, table.detach()[ids])
+    dout = rnd(M, D, seed=2)
+    F.embedding(ids, table).backward(dout)
+    dt = torch.zeros(V, D, device="cuda")
+    C.embedding_bwd(ids, dout, dt, M, D, V, 0.0, 0, None)
+    assert rel_fro(dt, table.grad) < 1e-6
+    H, Lq = 12, 32
+    bucket = t5_relative_buckets(Lq, Lq).cuda()
+    tb = rnd(32, H, seed=3).requires_grad_(True)
+    ref = tb[bucket.long()].permute(2, 0, 1)
+    bias = torch.empty(H, Lq, Lq, device="cuda")
+    C.t5_bias_build(tb.detach(), bucket, bias, H, Lq, 32)
+    assert torch.equal(bias, ref.detach())
+    db = rnd(H, Lq, Lq, seed=4)
+    ref.backward(db)
+    dtb = torch.zeros(32, H, device="cuda")
+    C.t5_bias_grad(db, bucket, dtb, H, Lq, 32)
+    assert rel_fro(dtb, tb.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,Lq,Lk,hd,t5", [(4, 12, 32, 32, 64, True), (3, 12, 16, 16, 64, True),
+                                             (4, 8, 32, 32, 96, False), (4, 8, 32, 49, 96, False),
+                                             (2, 8, 16, 64, 96, False), (2, 8, 32, 196, 96, False)])
+def test_attention_fwd_bwd(C, B, H, Lq, Lk, hd, t5):
+    D = H * hd
+    q = rnd(B * Lq, D, seed=1, scale=1.0 if not t5 else 0.4, dtype=BF)
+    k = rnd(B * Lk, D, seed=2, scale=1.0 if not t5 else 0.4, dtype=BF)
+    v = rnd(B * Lk, D, seed=3, dtype=BF)
+    dO = rnd(B * Lq, D, seed=4, dtype=BF)
+    bias = mask = None
+    scale = 1.0 if t5 else 1.0 / math.sqrt(hd)
+    qf, kf, vf = [t.float().requires_grad_(True) for t in (q, k, v)]
+    qh = qf.view(B, Lq, H, hd).transpose(1, 2)
+    kh = kf.view(B, Lk, H, hd).transpose(1, 2)
+    vh = vf.view(B, Lk, H, hd).transpose(1, 2)
+    s = torch.matmul(qh, kh.transpose(-1, -2)) * scale
+    if t5:
+        bias = rnd(H, Lq, Lk, seed=5).requires_grad_(True)
+        mask = torch.ones(B, Lk, dtype=torch.long, device="cuda")
+        mask[:, Lk - 5:] = 0
+        mask[0] = 1
+        s = s + bias[None] + (1.0 - mask[:, None, None, :].float()) * torch.finfo(torch.float32).min
+    p = F.softmax(s, dim=-1)
+    o = torch.matmul(p, vh).transpose(1, 2).reshape(B * Lq, D)
+    o.backward(dO.float())
+    out = torch.zeros(B * Lq, D, dtype=BF, device="cuda")
+    probs = torch.zeros(B * H * Lq * Lk, dtype=F32, device="cuda")
+    C.attn_fwd(B, H, Lq, Lk, hd, q, D, k, D, v, D, out, D, probs, bias.detach() if t5 else None, mask, scale, 0.0, 0, None)
+    assert rel_fro(out, o.detach()) < 6e-3
+    assert rel_fro(probs.view(B, H, Lq, Lk), p.detach()) < 2e-3
+    dq, dk, dv = [torch.zeros_like(t) for t in (q, k, v)]
+    dbias = torch.zeros(H, Lq, Lk, device="cuda") if t5 else None
+    C.attn_bwd(B, H, Lq, Lk, hd, q, D, k, D, v, D, probs, dO, D, dq, D, dk, D, dv, D, dbias, scale, 0.0, 0, None)
+    assert rel_fro(dq, qf.grad) < 1.5e-2 and rel_fro(dk, kf.grad) < 1.5e-2 and rel_fro(dv, vf.grad) < 1.5e-2
+    assert cosine(dq, qf.grad) > 0.9999 and cosine(dk, kf.grad) > 0.9999
+    if t5:
+        assert rel_fro(dbias, bias.grad) < 1.5e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# dropout: keep-rate, scale, and forward/backward mask identity
+# ------------------------------------------------------------------------------------------------
+def test_dropout_mask_consistency(C):
+    M, N, K, p = 2048, 768, 768, 0.1
+    rng = rng_state()
+    ones = torch.ones(M, N, device="cuda")
+    m1 = torch.empty(M, N, dtype=BF, device="cuda")
+    C.dropout_cast(ones, m1, M, N, p, 11, rng)
+    keep = float((m1 > 0).float().mean())
+    assert abs(keep - 0.9) < 2e-3
+    assert torch.allclose(m1[m1 > 0].float(), torch.tensor(1 / 0.9).cuda(), rtol=4e-3)
+    # the GEMM epilogue regenerates the same mask for the same (sid, rng)
+    X = torch.eye(K, dtype=BF, device="cuda").repeat(M // K + 1, 1)[:M].contiguous()
+    W = torch.ones(N, K, dtype=BF, device="cuda")
+    out = torch.empty(M, N, dtype=BF, device="cuda")
+    C.linear(X, M, K, K, W, N, out, N, drop_p=p, sid=11, rng=rng, bn=128)
+    assert torch.equal(out > 0, m1 > 0)
+    m2 = torch.empty_like(m1)
+    C.dropout_cast(ones, m2, M, N, p, 12, rng)      # another stream id -> another mask
+    assert not torch.equal(m2 > 0, m1 > 0)
+    C.rng_advance(rng)
+    C.dropout_cast(ones, m2, M, N, p, 11, rng)      # next step -> another mask
+    assert not torch.equal(m2 > 0, m1 > 0)
+    assert int(rng[1]) == 8
+
+
+# ------------------------------------------------------------------------------------------------
+# head
+# ------------------------------------------------------------------------------------------------
+def test_pooler_and_loss(C):
+    B, Lq, D, A = 64, 32, 768, 170
+    x = rnd(B, Lq, D, seed=1).requires_grad_(True)
+    a = rnd(1, D, seed=2, scale=D ** -0.5).requires_grad_(True)
+    b = rnd(1, seed=3).requires_grad_(True)
+    w = F.softmax(F.linear(x, a, b), dim=1).transpose(1, 2)
+    pooled = torch.bmm(w, x).squeeze(1)
+    dp = rnd(B, D, seed=4)
+    pooled.backward(dp)
+    wo, pf, pb = torch.empty(B, Lq, device="cuda"), torch.empty(B, D, device="cuda"), torch.empty(B, D, dtype=BF, device="cuda")
+    C.pooler_fwd(x.detach(), a.detach(), b.detach(), wo, pf, pb, B, Lq, D)
+    assert rel_fro(pf, pooled.detach()) < 1e-5 and rel_fro(pb, pooled.detach()) < 4e-3
+    dx, da, db = torch.empty(B, Lq, D, device="cuda"), torch.zeros(D, device="cuda"), torch.zeros(1, device="cuda")
+    C.pooler_bwd(x.detach(), a.detach(), wo, dp, dx, da, db, B, Lq, D)
+    assert rel_fro(dx, x.grad) < 1e-5 and rel_fro(da, a.grad.flatten()) < 1e-4
+    assert abs(float(db) - float(b.grad)) < 1e-4
+    # log_softmax + NLL
+    ld = 176
+    logits = torch.zeros(B, ld, device="cuda")
+    logits[:, :A] = rnd(B, A, seed=5, scale=2.0)
+    lg = logits[:, :A].clone().requires_grad_(True)
+    labels = torch.randint(0, A, (B,), generator=torch.Generator().manual_seed(6)).cuda()
+    ref_lp = F.log_softmax(lg, -1)
+    ref_loss = F.nll_loss(ref_lp, labels)
+    gl = torch.tensor([0.7], device="cuda")
+    glp = rnd(B, A, seed=7, scale=0.01)
+    (ref_loss * gl[0] + (ref_lp * glp).sum()).backward()
+    lp, loss = torch.empty(B, A, device="cuda"), torch.zeros(1, device="cuda")
+    C.logsoftmax_nll_fwd(logits, ld, labels, lp, loss, B, A)
+    assert rel_fro(lp, ref_lp.detach()) < 1e-6 and abs(float(loss) - float(ref_loss)) < 1e-5
+    dl = torch.empty(B, ld, dtype=BF, device="cuda")
+    C.logsoftmax_nll_bwd(lp, labels, gl, glp, dl, ld, B, A)
+    assert rel_fro(dl[:, :A], lg.grad) < 4e-3 and float(dl[:, A:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer
+# ------------------------------------------------------------------------------------------------
+def test_adamw_amsgrad_matches_torch(C, pkg):
+    n = 1_000_003
+    p0 = rnd(n, seed=1)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref], lr=5e-3, weight_decay=0.1, amsgrad=True)
+    mine = p0.clone()
+    m, v, vm = torch.zeros_like(mine), torch.zeros_like(mine), torch.zeros_like(mine)
+    shadow = torch.empty(n, dtype=BF, device="cuda")
+    lib = pkg.lib.load()
+    s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for t in range(1, 6):
+        g = rnd(n, seed=10 + t, scale=1.0 / t)
+        ref.grad = g.clone()
+        opt.step()
+        pkg.lib.check(lib.vqa_adamw_amsgrad(None, mine.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                            vm.data_ptr(), shadow.data_ptr(), n, 5e-3, 0.9, 0.999, 1e-8, 0.1,
+                                            1 - 0.9 ** t, 1 - 0.999 ** t, None, 0.0, 1, s))
+    assert float((mine - ref.detach()).abs().max()) < 2e-6
+    st = opt.state[ref]
+    assert rel_fro(m, st["exp_avg"]) < 1e-6 and rel_fro(v, st["exp_avg_sq"]) < 1e-6
+    assert rel_fro(vm, st["max_exp_avg_sq"]) < 1e-6
+    assert torch.equal(shadow, mine.to(BF))
+    ss = torch.zeros(1, device="cuda")
+    C.sumsq_f32(mine, n, ss)
+    assert abs(float(ss) / float(mine.double().pow(2).sum()) - 1) < 1e-5
+
+
+def test_fused_optimizer_clip_matches_clip_grad_norm(C, pkg):
+    torch.manual_seed(0)
+    ps = [rnd(1000, 64, seed=i) for i in range(4)]
+    ref = [p.clone().requires_grad_(True) for p in ps]
+    mine = [p.clone().requires_grad_(True) for p in ps]
+    o_ref = torch.optim.AdamW([{"params": ref[:2], "lr": 1e-3}, {"params": ref[2:], "lr": 5e-4}],
+                              weight_decay=0.1, amsgrad=True)
+    o_mine = torch.optim.VQAFusedAdamW([{"params": mine[:2], "lr": 1e-3}, {"params": mine[2:], "lr": 5e-4}],
+                                       weight_decay=0.1, amsgrad=True, max_grad_norm=1.0)
+    for step in range(3):
+        for a, b in zip(ref, mine):
+            g = rnd(*a.shape, seed=100 + step)
+            a.grad, b.grad = g.clone(), g.clone()
+        torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        o_ref.step()
+        o_mine.step()
+    for a, b in zip(ref, mine):
+        assert float((a - b).abs().max()) < 2e-6
+    sd = o_mine.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq", "max_exp_avg_sq"}
+
+
+# ------------------------------------------------------------------------------------------------
+# plans
+# ------------------------------------------------------------------------------------------------
+def test_plan_replay_and_graph(C, pkg):
+    from t5_resnet_vqa_b200.engine import _Rec
+    lib = pkg.lib.load()
+    plan = lib.vqa_plan_create()
+    r = _Rec(lib, plan, None)
+    M, N, K = 256, 256, 256
+    X, W = rnd(M, K, seed=1, dtype=BF), rnd(N, K, seed=2, dtype=BF)
+    y = torch.zeros(M, N, device="cuda")
+    acc = torch.zeros(M, N, device="cuda")
+    r.linear(X, M, K, K, W, N, y, N, out_fp32=1, bn=128)
+    r.axpy_f32(acc, y, 1.0, M * N)
+    assert lib.vqa_plan_size(plan) == 2
+    assert float(acc.abs().max()) == 0.0            # nothing ran while recording
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        sp = ctypes.c_void_p(side.cuda_stream)
+        pkg.lib.check(lib.vqa_plan_run(plan, sp))
+        pkg.lib.check(lib.vqa_plan_capture_graph(plan, sp))
+        pkg.lib.check(lib.vqa_plan_run(plan, sp))
+        side.synchronize()
+    assert rel_fro(acc, 2 * (X.float() @ W.float().t())) < 2e-5
+    lib.vqa_plan_destroy(plan)
