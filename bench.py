@@ -1,0 +1,377 @@
+"""Headline benchmark: train samples/s of the ResnetVQAModel step (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = the reference trainer's train_one_step (trainer/faster_rcnn_vqa_trainer.py:391-406): zero_grad ->
+model(**batch) -> loss.backward() -> clip_grad_norm_(1.0) -> AdamW(amsgrad, wd 0.1).step() -> LambdaLR.step(),
+model.train() (dropout 0.1 on), on BASELINE configs[1]: ResNet50 + T5-base encoder + 3xSGA, 64 samples per
+GPU, 224x224 images, 32-token questions, 170 answers, synthetic data, random-init weights.  N GPUs = N
+replicas of that per-GPU batch (weak scaling; N=8 is BASELINE's global batch 512) with the gradient all-reduce.
+
+`value`  : device-resident inputs, K steps timed with CUDA events, max over ranks.
+`e2e`    : the same step called with PINNED HOST tensors (H2D copies inside the timed region) plus the
+           trainer's per-step `loss.item()` device->host read.
+`roofline`: every launch of the forward/backward plans is timed live with CUDA events (vqa_plan_profile);
+           the dominant kernel family is the tcgen05 GEMM / implicit-GEMM conv kernel; achieved = its
+           algorithmic FLOPs per step / its summed launch durations; peak from MEASURED_PEAKS.json.
+`cpu_baseline` / --impl reference: the oracle port of the reference step (fp32, torch CPU) on the host cores,
+           on a bounded sample (ResNet50, batch 4).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+VISION, PER_GPU_BATCH, L_TEXT, IMG, ANSWERS = "resnet50", 64, 32, 224, 170
+TRAIN_GFLOP_PER_SAMPLE = 30.95   # SURVEY.md section 8d / BASELINE.md section 3 (forward 16.23 + backward 14.72)
+LRS = dict(lang=0.005, scaler=0.0005, sga=0.0005, pooler=0.0005, classifier=1e-5, vision=0.008)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 7] or \
+               [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(float(r[2]) for r in rows)}
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference arm / CPU baseline: the oracle port of the reference step on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, batch=4):
+    import torch
+    from oracle import vqa_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.random_state_dict(VISION, ANSWERS, seed=0)
+    keys = O.trainable_keys(sd, VISION)
+    params = {k: sd[k].clone().requires_grad_(True) for k in keys}
+    work = dict(sd)
+    work.update(params)
+
+    def group(pred, lr):
+        return {"params": [params[k] for k in keys if pred(k)], "lr": lr}
+    groups = [group(lambda k: k.startswith("lang_model."), LRS["lang"]),
+              group(lambda k: k.startswith("downscale_layer."), LRS["scaler"]),
+              group(lambda k: k.startswith("sga_modules."), LRS["sga"]),
+              group(lambda k: k.startswith("attention_pooler."), LRS["pooler"]),
+              group(lambda k: k.startswith("classification_layer."), LRS["classifier"])]
+    opt = torch.optim.AdamW(groups, weight_decay=0.1, amsgrad=True)
+    data = O.synthetic_batch(batch, L_TEXT, IMG, IMG, ANSWERS, seed=1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        # eval-mode dropout (the port has no dropout): slightly LESS work than the reference's train() step
+        logp, loss = O.forward(work, VISION, data["question_input_ids"], data["question_attention_masks"],
+                               data["annotation_ids"], data["image_tensors"])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)
+        opt.step()
+        float(loss)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    ms = 1000.0 * sum(times) / len(times)
+    return dict(value=batch / (ms / 1000.0), ms_per_step=ms, cores=torch.get_num_threads(), batch=batch,
+                sample="ResNet50+T5-base+3xSGA fp32 train step, batch %d (1/16 of the 64-sample GPU step), %d timed "
+                       "steps after %d warm-up, torch CPU %d threads" % (batch, steps, warmup, torch.get_num_threads()))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, 6), min(args.warmup, 2)
+    r = cpu_reference_steps(steps, max(warmup, 1))
+    line = {"impl": "reference", "metric": "train samples/s", "value": r["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": max(warmup, 1), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ResNet50+T5-base-encoder+3xSGA train step, 224x224, 32-token question, 170 answers; "
+                                   "CPU sample batch %d" % r["batch"]},
+            "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                             "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def build_trainer_objects(model, total_steps):
+    """Optimizer + schedule exactly as FasterRcnnVQATrainer._init_optimizer/_init_lr_scheduler build them
+    (trainer/faster_rcnn_vqa_trainer.py:231-287), with "type": "VQAFusedAdamW" in optimizer_kwargs."""
+    import torch
+    groups = [{"params": model.vision_model.parameters(), "lr": LRS["vision"], "model_name": "Vision Model"},
+              {"params": model.lang_model.parameters(), "lr": LRS["lang"], "model_name": "Language Model"},
+              {"params": model.downscale_layer.parameters(), "lr": LRS["scaler"], "model_name": "DownScaler Layer"},
+              {"params": model.sga_modules.parameters(), "lr": LRS["sga"], "model_name": "Self-Guided Attention Module"},
+              {"params": model.attention_pooler.parameters(), "lr": LRS["pooler"], "model_name": "Attention Pooler"},
+              {"params": model.classification_layer.parameters(), "lr": LRS["classifier"], "model_name": "Classifier Layer"}]
+    opt = getattr(torch.optim, os.environ.get("VQA_BENCH_OPTIMIZER", "VQAFusedAdamW"))(
+        groups, weight_decay=0.1, amsgrad=True)
+    warm = min(max(total_steps // 10, 1), 10000)
+
+    def lr_lambda(step):  # transformers.get_linear_schedule_with_warmup
+        if step < warm:
+            return float(step) / float(max(1, warm))
+        return max(0.0, float(total_steps - step) / float(max(1, total_steps - warm)))
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda)
+    return opt, sched
+
+
+def train_one_step(model, opt, sched, batch, read_loss):
+    import torch
+    opt.zero_grad()
+    logp, loss = model(**batch)
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+    opt.step()
+    sched.step()
+    return loss.item() if read_loss else loss
+
+
+def profile_plans(pkg, model, st):
+    """Per-launch device times of the forward and backward plans (eager replay with CUDA events)."""
+    import torch
+    lib = pkg.lib.load()
+    eng = model._engine
+    side = torch.cuda.Stream()
+    rows = []
+    with torch.cuda.stream(side):
+        sp = ctypes.c_void_p(side.cuda_stream)
+        for plan in [st.fwd] + [s.plan for s in st.bwd_segments]:
+            n = lib.vqa_plan_size(plan)
+            best = None
+            for _ in range(3):
+                ms = (ctypes.c_float * n)()
+                pkg.lib.check(lib.vqa_plan_profile(plan, sp, ms, 3000), "plan_profile")
+                cur = list(ms)
+                best = cur if best is None else [min(a, b) for a, b in zip(best, cur)]
+            for i in range(n):
+                name, fl, by = ctypes.c_char_p(), ctypes.c_double(), ctypes.c_double()
+                lib.vqa_plan_op_info(plan, i, ctypes.byref(name), ctypes.byref(fl), ctypes.byref(by))
+                rows.append((name.value.decode(), fl.value, by.value, best[i]))
+    torch.cuda.synchronize()
+    return rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE: 64)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-json", default=None, help="write the per-launch timing table here")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (use with "
+                         "ncu --profile-from-start off); prints no bench line")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    os.environ.setdefault("VQA_B200_PRETRAINED", "0")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    import t5_resnet_vqa_b200 as pkg
+
+    torch.manual_seed(0)
+    model = pkg.ResnetVQAModel(VISION, "t5-base", answer_spaces=ANSWERS)
+    model.to(dev).train()
+    B = args.batch
+    g = torch.Generator().manual_seed(1 + rank)
+    host = dict(
+        question_input_ids=torch.randint(2, 32100, (B, L_TEXT), generator=g).pin_memory(),
+        decoder_question_input_ids=None,
+        question_attention_masks=torch.ones(B, L_TEXT, dtype=torch.long).pin_memory(),
+        decoder_question_attention_masks=None,
+        annotation_ids=torch.randint(0, ANSWERS, (B,), generator=g).pin_memory(),
+        image_tensors=torch.rand(B, 3, IMG, IMG, generator=g).pin_memory())
+    devb = {k: (v.to(dev) if v is not None else None) for k, v in host.items()}
+    total_steps = 2 * (warmup + args.steps) + 16
+    opt, sched = build_trainer_objects(model, total_steps)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also records the plans and captures the CUDA graphs) ----
+    for _ in range(warmup):
+        train_one_step(model, opt, sched, devb, read_loss=False)
+    barrier()
+    st = model._engine.last_state
+    n_opt_launches = len(opt._ranges) if hasattr(opt, "_ranges") and opt._ranges else 0
+
+    if args.ncu_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        train_one_step(model, opt, sched, devb, read_loss=True)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_step": "done"}))
+        return
+
+    # ---- timed: device-resident inputs ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        loss = train_one_step(model, opt, sched, devb, read_loss=False)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    last_loss = float(loss)
+
+    # ---- timed: end to end from pinned host memory, loss read back every step ----
+    for _ in range(2):
+        train_one_step(model, opt, sched, host, read_loss=True)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        train_one_step(model, opt, sched, host, read_loss=True)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline: live per-launch timing of the plans ----
+    pk = peaks()
+    rows = profile_plans(pkg, model, st)
+    fam = {}
+    for name, fl, by, ms in rows:
+        f = fam.setdefault(name, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        f["launches"] += 1; f["ms"] += ms; f["flops"] += fl; f["bytes"] += by
+    step_ms_profiled = sum(f["ms"] for f in fam.values())
+    tens = [fam[k] for k in ("gemm", "conv", "conv_wgrad") if k in fam]
+    t_ms = sum(f["ms"] for f in tens)
+    t_fl = sum(f["flops"] for f in tens)
+    t_n = sum(f["launches"] for f in tens)
+    achieved_tf = t_fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all %d GEMM / implicit-GEMM conv launches of one step)" % t_n,
+                "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": achieved_tf / pk["tf_sustained"], "traffic": None,
+                "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                "flops_per_step": t_fl, "ms_per_step_in_kernel": t_ms,
+                "share_of_profiled_step": t_ms / step_ms_profiled if step_ms_profiled else None}
+    if args.profile_json:
+        with open(args.profile_json, "w") as f:
+            json.dump({"families": fam, "rows": rows[:2000], "profiled_step_ms": step_ms_profiled}, f, indent=1)
+
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step / 1000.0)
+    e2e_value = world * B / (ms_e2e / args.steps / 1000.0)
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if v is not None)
+    launches_per_step = st.n_fwd_launches + st.n_bwd_launches + n_opt_launches + 2  # + shadow prep, rng advance
+    line = {
+        "metric": "train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "ResNet50 + T5-base encoder + 3xSGA train step (fwd+bwd+clip+AdamW-amsgrad), batch %d per GPU, "
+                               "224x224 images, 32-token questions, 170 answers, dropout on" % B,
+                   "global_batch": world * B, "parallelism": "dp%d" % world,
+                   "l2": "working set per step (activations + 567 MB fp32 gradients + 2.3 GB optimizer state) exceeds the 126 MB L2",
+                   "optimizer": type(opt).__name__, "cuda_graphs": bool(model._engine.use_graphs)},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
+        "roofline": roofline,
+        "step_frac_of_tensor_peak": (value / world) * TRAIN_GFLOP_PER_SAMPLE * 1e9 / (pk["tf_sustained"] * 1e12),
+        "clocks": clocks,
+        "loss": last_loss,
+    }
+    if "adamw" in fam or True:
+        line["kernel_families"] = {k: {"launches": v["launches"], "ms": round(v["ms"], 4)}
+                                   for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:12]}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if not args.no_cpu_baseline and world == 1:
+        r = cpu_reference_steps(3, 1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"]}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

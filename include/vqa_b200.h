@@ -45,6 +45,10 @@ int vqa_plan_destroy(void* plan);
 int vqa_plan_size(void* plan);                       /* number of recorded launches */
 int vqa_plan_run(void* plan, void* stream);          /* replay (through the CUDA graph if captured) */
 int vqa_plan_capture_graph(void* plan, void* stream);/* capture the recorded launches into a CUDA graph */
+/* measurement aid: eager replay with a CUDA event between launches; ms_out[vqa_plan_size] device durations
+ * (synchronises the stream).  op_info: kernel family and the algorithmic flops / HBM bytes of launch i. */
+int vqa_plan_profile(void* plan, void* stream, float* ms_out, int spin_us);
+int vqa_plan_op_info(void* plan, int i, const char** name, double* flops, double* bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * tcgen05 GEMM.  out[M,N] = epilogue(alpha * op(A) op(B)^T)

@@ -333,6 +333,7 @@ int vqa_attention_fwd(void* plan, const vqa_attn_fwd_args* x, void* stream) {
   int r = hd == 64 ? ensure_smem<attention_fwd_kernel<64>>(smem, "attention_fwd")
                    : ensure_smem<attention_fwd_kernel<96>>(smem, "attention_fwd");
   if (r) return r;
+  note_op("attention_fwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     if (hd == 64) attention_fwd_kernel<64><<<a.B * a.H, kThreads, smem, s>>>(a);
     else attention_fwd_kernel<96><<<a.B * a.H, kThreads, smem, s>>>(a);
@@ -359,6 +360,7 @@ int vqa_attention_bwd(void* plan, const vqa_attn_bwd_args* x, void* stream) {
   int r = hd == 64 ? ensure_smem<attention_bwd_kernel<64>>(smem, "attention_bwd")
                    : ensure_smem<attention_bwd_kernel<96>>(smem, "attention_bwd");
   if (r) return r;
+  note_op("attention_bwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     if (hd == 64) attention_bwd_kernel<64><<<a.B * a.H, kThreads, smem, s>>>(a);
     else attention_bwd_kernel<96><<<a.B * a.H, kThreads, smem, s>>>(a);

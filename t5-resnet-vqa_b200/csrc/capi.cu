@@ -28,6 +28,7 @@ int vqa_gemm_bf16(void* plan, const vqa_gemm_args* a, void* stream) {
   int r = gemm_op_init(&op, a->M, a->N, a->K, a->A, a->lda, a->a_mn, a->B, a->ldb, a->b_mn, a->out,
                        a->ldo, a->out_fp32, e, a->bn, a->split_k);
   if (r) return r;
+  note_op("gemm", 2.0 * a->M * a->N * a->K, 0.0);
   return submit(plan, stream, [op](cudaStream_t s) { return gemm_op_run(&op, s); });
 }
 
@@ -40,6 +41,8 @@ int vqa_conv2d_bf16(void* plan, const vqa_conv_args* a, void* stream) {
   GemmOp op;
   int r = conv_op_init(&op, g, a->x, a->w, a->out, a->out_fp32, e, a->bn);
   if (r) return r;
+  // algorithmic MACs of the convolution (the stem's zero-padded taps/channels are not counted)
+  note_op("conv", 2.0 * a->N * a->Ho * a->Wo * a->Cout * a->R * a->S * (a->stem7 ? 3 : a->Cin), 0.0);
   return submit(plan, stream, [op](cudaStream_t s) { return gemm_op_run(&op, s); });
 }
 
@@ -50,6 +53,7 @@ int vqa_conv2d_wgrad_bf16(void* plan, const vqa_conv_wgrad_args* a, void* stream
   GemmOp op;
   int r = conv_wgrad_op_init(&op, g, a->dy, a->x, a->dw, a->bn, a->split_k);
   if (r) return r;
+  note_op("conv_wgrad", 2.0 * a->N * a->H * a->W * a->Cout * a->R * a->S * a->Cin, 0.0);
   return submit(plan, stream, [op](cudaStream_t s) { return gemm_op_run(&op, s); });
 }
 

@@ -19,18 +19,38 @@ namespace vqa {
 // (optionally through an instantiated CUDA graph), so a whole forward or backward pass costs one
 // host call.  Launch descriptors (tensor maps, pointers, shapes) are resolved once at record time.
 // ---------------------------------------------------------------------------------------------
+struct OpNote {
+  const char* name = "";   // static string: kernel family
+  double flops = 0.0;      // algorithmic floating-point operations of the launch (0 for bandwidth kernels)
+  double bytes = 0.0;      // algorithmic HBM bytes of the launch (0 when not stated)
+};
 struct Plan {
   std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<OpNote> notes;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
 };
 
+// Annotation of the NEXT submitted launch (set by each C entry point just before submit()).
+inline OpNote& pending_note() {
+  static thread_local OpNote n;
+  return n;
+}
+inline void note_op(const char* name, double flops, double bytes) {
+  OpNote& n = pending_note();
+  n.name = name; n.flops = flops; n.bytes = bytes;
+}
+
 template <class F>
 inline int submit(void* plan, void* stream, F&& fn) {
   if (plan != nullptr) {
-    static_cast<Plan*>(plan)->ops.emplace_back(std::forward<F>(fn));
+    Plan* p = static_cast<Plan*>(plan);
+    p->ops.emplace_back(std::forward<F>(fn));
+    p->notes.push_back(pending_note());
+    pending_note() = OpNote();
     return 0;
   }
+  pending_note() = OpNote();
   return fn(static_cast<cudaStream_t>(stream));
 }
 

@@ -254,6 +254,7 @@ int vqa_cast_f32_bf16(void* plan, const float* src, void* dst, long long n, void
     set_last_error("cast: pointers must be 16-byte aligned");
     return -1;
   }
+  note_op("cast_f32_bf16", 0.0, 6.0 * static_cast<double>(n));
   return submit(plan, stream, [=](cudaStream_t s) {
     cast_f32_bf16_kernel<<<grid_for((n >> 3) + 8, 256), 256, 0, s>>>(src, static_cast<__nv_bfloat16*>(dst), n);
     return launch_status("cast_f32_bf16");
@@ -261,6 +262,7 @@ int vqa_cast_f32_bf16(void* plan, const float* src, void* dst, long long n, void
 }
 
 int vqa_memset_zero(void* plan, void* ptr, long long bytes, void* stream) {
+  note_op("memset", 0.0, static_cast<double>(bytes));
   return submit(plan, stream, [=](cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(ptr, 0, static_cast<size_t>(bytes), s);
     if (e != cudaSuccess) { set_last_error("memset: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
@@ -269,6 +271,7 @@ int vqa_memset_zero(void* plan, void* ptr, long long bytes, void* stream) {
 }
 
 int vqa_axpy_f32(void* plan, float* y, const float* x, float a, long long n, void* stream) {
+  note_op("axpy", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     axpy_kernel<<<grid_for((n >> 2) + 4, 256), 256, 0, s>>>(y, x, a, n);
     return launch_status("axpy");
@@ -278,6 +281,7 @@ int vqa_axpy_f32(void* plan, float* y, const float* x, float a, long long n, voi
 int vqa_fold_conv_bn(void* plan, const float* w, const float* gamma, const float* beta, const float* mean,
                      const float* var, float eps, void* w_out, float* bias_out, int O, int I, int R, int S,
                      int Sp, int Ip, void* stream) {
+  note_op("fold_conv_bn", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     const long long total = static_cast<long long>(O) * R * Sp * Ip;
     int grid = grid_for(total, 256);
@@ -289,6 +293,7 @@ int vqa_fold_conv_bn(void* plan, const float* w, const float* gamma, const float
 }
 
 int vqa_convT_weight_prep(void* plan, const float* w, void* w_out, int Cin, int Cout, void* stream) {
+  note_op("convT_weight_prep", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     dim3 grid((Cout * 9 + 31) / 32, (Cin + 31) / 32), block(32, 8);
     transpose_flip9_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(w, static_cast<__nv_bfloat16*>(w_out), Cin, Cout * 9);
@@ -298,6 +303,7 @@ int vqa_convT_weight_prep(void* plan, const float* w, void* w_out, int Cin, int 
 
 int vqa_convT_wgrad_unprep(void* plan, const float* dw_conv, float* dw, int Cin, int Cout, void* stream) {
   // dw[ci, co*9 + t] = dw_conv[co*9 + 8 - t, ci]
+  note_op("convT_wgrad_unprep", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     dim3 grid((Cin + 31) / 32, (Cout * 9 + 31) / 32), block(32, 8);
     transpose_fliprow9_kernel<<<grid, block, 0, s>>>(dw_conv, dw, Cout * 9, Cin);
@@ -306,6 +312,7 @@ int vqa_convT_wgrad_unprep(void* plan, const float* dw_conv, float* dw, int Cin,
 }
 
 int vqa_image_to_stem(void* plan, const float* img, void* out, int N, int H, int W, void* stream) {
+  note_op("image_to_stem", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     const long long total = static_cast<long long>(N) * H * (W + 8);
     image_to_stem_kernel<<<grid_for(total, 256, 16), 256, 0, s>>>(img, static_cast<uint4*>(out), N, H, W);
@@ -314,6 +321,7 @@ int vqa_image_to_stem(void* plan, const float* img, void* out, int N, int H, int
 }
 
 int vqa_nhwc_to_nchw_f32(void* plan, const void* x, float* out, int N, int H, int W, int C, void* stream) {
+  note_op("nhwc_to_nchw", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     dim3 grid((C + 31) / 32, (H * W + 31) / 32, N), block(32, 8);
     nhwc_to_nchw_kernel<<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16*>(x), out, H * W, C);
@@ -323,6 +331,7 @@ int vqa_nhwc_to_nchw_f32(void* plan, const void* x, float* out, int N, int H, in
 
 int vqa_maxpool3x3s2(void* plan, const void* x, void* out, int N, int H, int W, int C, void* stream) {
   if (C % 8) { set_last_error("maxpool: C must be a multiple of 8"); return -1; }
+  note_op("maxpool3x3s2", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long total = static_cast<long long>(N) * Ho * Wo * (C / 8);
@@ -335,6 +344,7 @@ int vqa_maxpool3x3s2(void* plan, const void* x, void* out, int N, int H, int W, 
 int vqa_dropout_cast(void* plan, const float* x, void* out_bf16, long long rows, int N, float drop_p, uint32_t sid,
                      const uint64_t* rng, void* stream) {
   if (N % 8) { set_last_error("dropout_cast: N must be a multiple of 8"); return -1; }
+  note_op("dropout_cast", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     const long long n8 = rows * N / 8;
     dropout_cast_kernel<<<grid_for(n8, 256), 256, 0, s>>>(x, static_cast<__nv_bfloat16*>(out_bf16), n8, drop_p, sid,
@@ -344,6 +354,7 @@ int vqa_dropout_cast(void* plan, const float* x, void* out_bf16, long long rows,
 }
 
 int vqa_colsum_bf16(void* plan, const void* x, long long ld, float* out, int M, int N, void* stream) {
+  note_op("colsum_bf16", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     dim3 block(32, 8);
     int gy = (M + 63) / 64;

@@ -172,6 +172,7 @@ extern "C" {
 int vqa_pooler_fwd(void* plan, const float* x, const float* a, const float* b, float* w_out, float* pooled_f32,
                    void* pooled_bf16, int B, int L, int D, void* stream) {
   if (D % 4) { set_last_error("pooler: D must be a multiple of 4"); return -1; }
+  note_op("pooler_fwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     pooler_fwd_kernel<<<B, kPoolThreads, L * sizeof(float), s>>>(x, a, b, w_out, pooled_f32,
                                                                  static_cast<__nv_bfloat16*>(pooled_bf16), L, D);
@@ -182,6 +183,7 @@ int vqa_pooler_fwd(void* plan, const float* x, const float* a, const float* b, f
 int vqa_pooler_bwd(void* plan, const float* x, const float* a, const float* w, const float* dpooled, float* dx,
                    float* da, float* db, int B, int L, int D, void* stream) {
   if (D % 4) { set_last_error("pooler: D must be a multiple of 4"); return -1; }
+  note_op("pooler_bwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     pooler_bwd_kernel<<<B, kPoolThreads, L * sizeof(float), s>>>(x, a, w, dpooled, dx, da, db, L, D);
     return launch_status("pooler_bwd");
@@ -191,6 +193,7 @@ int vqa_pooler_bwd(void* plan, const float* x, const float* a, const float* w, c
 int vqa_logsoftmax_nll_fwd(void* plan, const float* logits, long long ld, const long long* labels, float* logp,
                            float* loss, int B, int A, void* stream) {
   if (B > 8192) { set_last_error("logsoftmax_nll: batch > 8192 not supported"); return -1; }
+  note_op("logsoftmax_nll_fwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     logsoftmax_nll_fwd_kernel<<<1, 1024, B * sizeof(float), s>>>(logits, ld, labels, logp, loss, B, A);
     return launch_status("logsoftmax_nll_fwd");
@@ -199,6 +202,7 @@ int vqa_logsoftmax_nll_fwd(void* plan, const float* logits, long long ld, const 
 
 int vqa_logsoftmax_nll_bwd(void* plan, const float* logp, const long long* labels, const float* gloss,
                            const float* glogp, void* dlogits, long long ld, int B, int A, void* stream) {
+  note_op("logsoftmax_nll_bwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     logsoftmax_nll_bwd_kernel<<<B, 32, 0, s>>>(logp, labels, gloss, glogp, static_cast<__nv_bfloat16*>(dlogits), ld,
                                                B, A);

@@ -268,6 +268,7 @@ extern "C" {
 int vqa_rmsnorm_fwd(void* plan, const float* x, const float* w, void* y_bf16, float* y_f32, float* rstd, int M,
                     int D, float eps, float drop_p, uint32_t sid, const uint64_t* rng, void* stream) {
   if (check_d(D, "rmsnorm_fwd")) return -1;
+  note_op("rmsnorm_fwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     DISPATCH_NC(D, (rmsnorm_fwd_kernel<NC><<<norm_grid(M), kThreads, 0, s>>>(
                        x, w, static_cast<__nv_bfloat16*>(y_bf16), y_f32, rstd, M, eps, drop_p, sid,
@@ -280,6 +281,7 @@ int vqa_rmsnorm_bwd(void* plan, const void* dy, int dy_fp32, const float* x, con
                     const float* dres, float* dx, float* dw, int M, int D, float drop_p, uint32_t sid,
                     const uint64_t* rng, void* stream) {
   if (check_d(D, "rmsnorm_bwd")) return -1;
+  note_op("rmsnorm_bwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     DISPATCH_NC(D, (rmsnorm_bwd_kernel<NC><<<norm_grid(M), kThreads, 0, s>>>(
                        dy, dy_fp32, x, w, rstd, dres, dx, dw, M, drop_p, sid,
@@ -291,6 +293,7 @@ int vqa_rmsnorm_bwd(void* plan, const void* dy, int dy_fp32, const float* x, con
 int vqa_layernorm_fwd(void* plan, const float* z, const float* gamma, const float* beta, void* y_bf16,
                       float* y_f32, float* mean, float* rstd, int M, int D, float eps, void* stream) {
   if (check_d(D, "layernorm_fwd")) return -1;
+  note_op("layernorm_fwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     DISPATCH_NC(D, (layernorm_fwd_kernel<NC><<<norm_grid(M), kThreads, 0, s>>>(
                        z, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, eps)));
@@ -301,6 +304,7 @@ int vqa_layernorm_fwd(void* plan, const float* z, const float* gamma, const floa
 int vqa_layernorm_bwd(void* plan, const float* dy, const float* z, const float* gamma, const float* mean,
                       const float* rstd, float* dz, float* dgamma, float* dbeta, int M, int D, void* stream) {
   if (check_d(D, "layernorm_bwd")) return -1;
+  note_op("layernorm_bwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     DISPATCH_NC(D, (layernorm_bwd_kernel<NC><<<norm_grid(M), kThreads, 0, s>>>(dy, z, gamma, mean, rstd, dz,
                                                                                  dgamma, dbeta, M)));

@@ -115,6 +115,7 @@ extern "C" {
 
 int vqa_sumsq_f32(void* plan, const float* x, long long n, float* out, void* stream) {
   if (reinterpret_cast<uintptr_t>(x) & 15) { set_last_error("sumsq: pointer must be 16-byte aligned"); return -1; }
+  note_op("sumsq", 0.0, 4.0 * static_cast<double>(n));
   return submit(plan, stream, [=](cudaStream_t s) {
     sumsq_kernel<<<stream_grid((n >> 2) + 4, 256), 256, 0, s>>>(x, n, out);
     return launch_status("sumsq");
@@ -142,6 +143,7 @@ int vqa_adamw_amsgrad(void* plan, float* p, const float* g, float* m, float* v, 
   h.step_size = static_cast<float>(lr / bias_correction1);
   h.bc2_sqrt = static_cast<float>(sqrt(bias_correction2));
   h.max_norm = max_norm; h.amsgrad = amsgrad;
+  note_op("adamw", 0.0, (amsgrad ? 36.0 : 28.0) * static_cast<double>(n) + (shadow ? 2.0 * n : 0.0));
   return submit(plan, stream, [=](cudaStream_t s) {
     adamw_kernel<<<stream_grid((n >> 2) + 4, 256), 256, 0, s>>>(p, g, m, v, vmax, static_cast<__nv_bfloat16*>(shadow), n, h,
                                                                 gnorm_sq);
@@ -150,6 +152,7 @@ int vqa_adamw_amsgrad(void* plan, float* p, const float* g, float* m, float* v, 
 }
 
 int vqa_rng_advance(void* plan, uint64_t* rng, void* stream) {
+  note_op("rng_advance", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     rng_advance_kernel<<<1, 1, 0, s>>>(reinterpret_cast<unsigned long long*>(rng));
     return launch_status("rng_advance");

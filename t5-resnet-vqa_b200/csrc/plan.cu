@@ -75,4 +75,49 @@ int vqa_plan_capture_graph(void* plan, void* stream) {
   return 0;
 }
 
+// ---- per-launch timing of a recorded plan (bench.py's roofline numbers) --------------------------------
+// Replays the plan eagerly with one CUDA event between consecutive launches; a short device-side spin in
+// front lets the host queue everything before the first launch starts, so the event-to-event times are the
+// launches' back-to-back device durations, not host enqueue gaps.  ms_out has vqa_plan_size(plan) entries.
+__global__ void vqa_spin_kernel(long long ns) {
+  long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < ns);
+}
+
+int vqa_plan_profile(void* plan, void* stream, float* ms_out, int spin_us) {
+  if (plan == nullptr) { set_last_error("plan_profile: null plan"); return -1; }
+  Plan* p = static_cast<Plan*>(plan);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = p->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) cudaEventCreate(&e);
+  int rc = 0;
+  if (spin_us > 0) vqa_spin_kernel<<<1, 1, 0, s>>>(static_cast<long long>(spin_us) * 1000);
+  for (size_t i = 0; i < n && rc == 0; ++i) {
+    cudaEventRecord(ev[i], s);
+    rc = p->ops[i](s);
+  }
+  cudaEventRecord(ev[n], s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (rc == 0 && e != cudaSuccess) {
+    set_last_error("plan_profile: %s", cudaGetErrorString(e));
+    rc = static_cast<int>(e);
+  }
+  if (rc == 0)
+    for (size_t i = 0; i < n; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+  for (auto& ev_i : ev) cudaEventDestroy(ev_i);
+  return rc;
+}
+
+int vqa_plan_op_info(void* plan, int i, const char** name, double* flops, double* bytes) {
+  if (plan == nullptr) return -1;
+  Plan* p = static_cast<Plan*>(plan);
+  if (i < 0 || i >= static_cast<int>(p->notes.size())) { set_last_error("plan_op_info: index out of range"); return -1; }
+  *name = p->notes[i].name; *flops = p->notes[i].flops; *bytes = p->notes[i].bytes;
+  return 0;
+}
+
 }  // extern "C"

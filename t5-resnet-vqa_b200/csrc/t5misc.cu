@@ -72,6 +72,7 @@ extern "C" {
 int vqa_embedding_fwd(void* plan, const long long* ids, const float* table, float* out, int M, int D, int vocab,
                       float drop_p, uint32_t sid, const uint64_t* rng, void* stream) {
   if (D % 8) { set_last_error("embedding: D must be a multiple of 8"); return -1; }
+  note_op("embedding_fwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     int grid = (M + 7) / 8;
     if (grid > 148 * 8) grid = 148 * 8;
@@ -84,6 +85,7 @@ int vqa_embedding_fwd(void* plan, const long long* ids, const float* table, floa
 int vqa_embedding_bwd(void* plan, const long long* ids, const float* dout, float* dtable, int M, int D, int vocab,
                       float drop_p, uint32_t sid, const uint64_t* rng, void* stream) {
   if (D % 8) { set_last_error("embedding: D must be a multiple of 8"); return -1; }
+  note_op("embedding_bwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     int grid = (M + 7) / 8;
     if (grid > 148 * 8) grid = 148 * 8;
@@ -96,6 +98,7 @@ int vqa_embedding_bwd(void* plan, const long long* ids, const float* dout, float
 int vqa_t5_bias_build(void* plan, const float* table, const int* bucket, float* bias, int H, int L, int nbuckets,
                       void* stream) {
   (void)nbuckets;
+  note_op("t5_bias_build", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     const int total = H * L * L;
     t5_bias_build_kernel<<<(total + 255) / 256, 256, 0, s>>>(table, bucket, bias, H, L * L);
@@ -106,6 +109,7 @@ int vqa_t5_bias_build(void* plan, const float* table, const int* bucket, float* 
 int vqa_t5_bias_grad(void* plan, const float* dbias, const int* bucket, float* dtable, int H, int L, int nbuckets,
                      void* stream) {
   (void)nbuckets;
+  note_op("t5_bias_grad", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     const int total = H * L * L;
     t5_bias_grad_kernel<<<(total + 255) / 256, 256, 0, s>>>(dbias, bucket, dtable, H, L * L);

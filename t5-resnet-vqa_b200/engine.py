@@ -342,6 +342,8 @@ class Engine:
             self._flatten(device)
             proj = self.model._projection()
             self.proj_w = torch.empty(proj.weight.numel(), dtype=torch.bfloat16, device=device)
+            from .ddp import maybe_enable
+            maybe_enable(self)
 
     def prepare(self):
         """Refresh the derived weight caches (folded BN convs, bf16 shadows) if their sources changed."""

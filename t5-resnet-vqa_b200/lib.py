@@ -61,6 +61,9 @@ SIGNATURES = {
     "vqa_plan_size": (c_int, [_P]),
     "vqa_plan_run": (c_int, [_P, _P]),
     "vqa_plan_capture_graph": (c_int, [_P, _P]),
+    "vqa_plan_profile": (c_int, [_P, _P, _P, c_int]),
+    "vqa_plan_op_info": (c_int, [_P, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_d),
+                                 ctypes.POINTER(c_d)]),
     "vqa_gemm_bf16": (c_int, [_P, ctypes.POINTER(GemmArgs), _P]),
     "vqa_conv2d_bf16": (c_int, [_P, ctypes.POINTER(ConvArgs), _P]),
     "vqa_conv2d_wgrad_bf16": (c_int, [_P, ctypes.POINTER(ConvWgradArgs), _P]),

@@ -118,7 +118,9 @@ class ResnetVQAModel(nn.Module):
     def _run(self, question_input_ids, question_attention_masks, annotation_ids, image_tensors, want_features):
         if question_input_ids.dim() != 2 or image_tensors.dim() != 4:
             raise ValueError("expected question_input_ids [B, L] and image_tensors [B, 3, H, W]")
-        dev = image_tensors.device
+        # the model's device decides (inputs may still be in pinned host memory: they are copied straight into
+        # the plan's static device buffers, which is the trainer's `v.to(device)` folded into the step)
+        dev = self.classification_layer.weight.device
         eng = self._engine
         eng._ensure(dev)
         self.vision_model.eval()  # side effect of the reference forward (model/resnet_vqa_model.py:116,127)
