@@ -214,6 +214,7 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE: 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-launch timing table here")
+    ap.add_argument("--breakdown", action="store_true", help="also print a per-phase device/host time breakdown")
     ap.add_argument("--ncu-step", action="store_true",
                     help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (use with "
                          "ncu --profile-from-start off); prints no bench line")
@@ -289,6 +290,33 @@ def main():
     t_wall1 = time.time()
     ms_total = e0.elapsed_time(e1)
     last_loss = float(loss)
+
+    if args.breakdown and rank == 0:
+        import time as _t
+        names = ["zero_grad", "forward", "backward", "clip", "optimizer"]
+        acc_d = {n: 0.0 for n in names}
+        acc_h = {n: 0.0 for n in names}
+        reps = 10
+        for _ in range(reps):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            hs = []
+            torch.cuda.synchronize()
+            evs[0].record(); hs.append(_t.perf_counter())
+            opt.zero_grad()
+            evs[1].record(); hs.append(_t.perf_counter())
+            logp, loss = model(**devb)
+            evs[2].record(); hs.append(_t.perf_counter())
+            loss.backward()
+            evs[3].record(); hs.append(_t.perf_counter())
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            evs[4].record(); hs.append(_t.perf_counter())
+            opt.step(); sched.step()
+            evs[5].record(); hs.append(_t.perf_counter())
+            torch.cuda.synchronize()
+            for i, n in enumerate(names):
+                acc_d[n] += evs[i].elapsed_time(evs[i + 1]) / reps
+                acc_h[n] += (hs[i + 1] - hs[i]) * 1e3 / reps
+        print(json.dumps({"breakdown_device_ms": acc_d, "breakdown_host_enqueue_ms": acc_h}), file=sys.stderr)
 
     # ---- timed: end to end from pinned host memory, loss read back every step ----
     for _ in range(2):

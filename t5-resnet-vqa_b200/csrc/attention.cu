@@ -71,6 +71,7 @@ struct FwdArgs {
 template <int HD>
 __global__ void __launch_bounds__(kThreads)
 attention_fwd_kernel(const FwdArgs a) {
+  pdl_grid_sync();
   constexpr int RW = (HD + 2) / 2;
   constexpr int DQ = HD / 4;  // head dims per thread in the P V phase
   extern __shared__ uint32_t smem[];
@@ -168,6 +169,7 @@ struct BwdArgs {
 template <int HD>
 __global__ void __launch_bounds__(kThreads)
 attention_bwd_kernel(const BwdArgs a) {
+  pdl_grid_sync();
   constexpr int RW = (HD + 2) / 2;
   constexpr int DQ = HD / 4;
   extern __shared__ uint32_t smem[];
@@ -335,8 +337,8 @@ int vqa_attention_fwd(void* plan, const vqa_attn_fwd_args* x, void* stream) {
   if (r) return r;
   note_op("attention_fwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    if (hd == 64) attention_fwd_kernel<64><<<a.B * a.H, kThreads, smem, s>>>(a);
-    else attention_fwd_kernel<96><<<a.B * a.H, kThreads, smem, s>>>(a);
+    if (hd == 64) launch_pdl(attention_fwd_kernel<64>, dim3(a.B * a.H), dim3(kThreads), smem, s, a);
+    else launch_pdl(attention_fwd_kernel<96>, dim3(a.B * a.H), dim3(kThreads), smem, s, a);
     return launch_status("attention_fwd");
   });
 }
@@ -362,8 +364,8 @@ int vqa_attention_bwd(void* plan, const vqa_attn_bwd_args* x, void* stream) {
   if (r) return r;
   note_op("attention_bwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    if (hd == 64) attention_bwd_kernel<64><<<a.B * a.H, kThreads, smem, s>>>(a);
-    else attention_bwd_kernel<96><<<a.B * a.H, kThreads, smem, s>>>(a);
+    if (hd == 64) launch_pdl(attention_bwd_kernel<64>, dim3(a.B * a.H), dim3(kThreads), smem, s, a);
+    else launch_pdl(attention_bwd_kernel<96>, dim3(a.B * a.H), dim3(kThreads), smem, s, a);
     return launch_status("attention_bwd");
   });
 }

@@ -64,6 +64,38 @@ inline int launch_status(const char* what) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of the library is launched with the programmatic-stream-
+// serialization attribute and starts with griddepcontrol.launch_dependents (+ its smem / barrier / TMEM
+// prologue, where it has one) followed by griddepcontrol.wait before its first global-memory access: the
+// next kernel's launch latency and prologue overlap the tail of the previous one, while `wait` (which
+// returns only when the preceding grid has completed and flushed) keeps the stream's data dependencies.
+// The edges survive CUDA-graph capture as programmatic dependencies.  VQA_B200_PDL=0 disables it.
+// ---------------------------------------------------------------------------------------------
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_grid_sync() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
+// ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -21,6 +21,7 @@ inline int grid_for(long long work_items, int threads, int max_waves = 8) {
 // ---- cast -------------------------------------------------------------------------------------
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                      long long n) {
+  pdl_grid_sync();
   const long long nvec = n >> 3;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -35,6 +36,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 }
 
 __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, long long n) {
+  pdl_grid_sync();
   const long long nvec = n >> 2;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
@@ -55,6 +57,7 @@ __global__ void fold_conv_bn_kernel(const float* __restrict__ w, const float* __
                                     const float* __restrict__ var, float eps,
                                     __nv_bfloat16* __restrict__ w_out, float* __restrict__ bias_out,
                                     int O, int I, int R, int S, int Sp, int Ip) {
+  pdl_grid_sync();
   const long long total = static_cast<long long>(O) * R * Sp * Ip;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
@@ -87,6 +90,7 @@ __global__ void fold_conv_bn_kernel(const float* __restrict__ w, const float* __
 //   dst[(g*9 + 8 - t), r] = src[r, g*9 + t]
 template <typename TOut>
 __global__ void transpose_flip9_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int R0, int C0) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -109,6 +113,7 @@ __global__ void transpose_flip9_kernel(const float* __restrict__ src, TOut* __re
 // src fp32 [R0 = G*9, C0] -> dst fp32 [C0, R0] with the tap flip on the source row:
 //   dst[c, g*9 + 8 - t] = src[g*9 + t, c]
 __global__ void transpose_fliprow9_kernel(const float* __restrict__ src, float* __restrict__ dst, int R0, int C0) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -127,6 +132,7 @@ __global__ void transpose_fliprow9_kernel(const float* __restrict__ src, float* 
 
 // ---- stem packing -----------------------------------------------------------------------------
 __global__ void image_to_stem_kernel(const float* __restrict__ img, uint4* __restrict__ out, int N, int H, int W) {
+  pdl_grid_sync();
   const int Wp = W + 8;
   const long long total = static_cast<long long>(N) * H * Wp;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -149,6 +155,7 @@ __global__ void image_to_stem_kernel(const float* __restrict__ img, uint4* __res
 
 // x bf16 [N, HW, C] -> out fp32 [N, C, HW]
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int HW, int C) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int c0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
@@ -168,6 +175,7 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* 
 // ---- max-pool 3x3 / stride 2 / pad 1, NHWC bf16, 8 channels per thread -------------------------
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                     int N, int H, int W, int C, int Ho, int Wo) {
+  pdl_grid_sync();
   const int C8 = C >> 3;
   const long long total = static_cast<long long>(N) * Ho * Wo * C8;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -201,6 +209,7 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
 // ---- dropout-mask cast: out_bf16 = dropmask(x) --------------------------------------------------
 __global__ void dropout_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n8,
                                     float drop_p, uint32_t sid, const unsigned long long* __restrict__ rng) {
+  pdl_grid_sync();
   const DropCtx dc = drop_ctx(drop_p, sid, rng);
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
@@ -214,6 +223,7 @@ __global__ void dropout_cast_kernel(const float* __restrict__ x, __nv_bfloat16* 
 // ---- column sums: out[n] += sum_m x[m, n] ------------------------------------------------------
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out,
                                    int M, int N) {
+  pdl_grid_sync();
   __shared__ float red[8][32][9];
   const int cg = blockIdx.x * 32 + threadIdx.x;  // 8-column group
   const int n0 = cg * 8;
@@ -256,7 +266,7 @@ int vqa_cast_f32_bf16(void* plan, const float* src, void* dst, long long n, void
   }
   note_op("cast_f32_bf16", 0.0, 6.0 * static_cast<double>(n));
   return submit(plan, stream, [=](cudaStream_t s) {
-    cast_f32_bf16_kernel<<<grid_for((n >> 3) + 8, 256), 256, 0, s>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+    launch_pdl(cast_f32_bf16_kernel, dim3(grid_for((n >> 3) + 8, 256)), dim3(256), 0, s, src, static_cast<__nv_bfloat16*>(dst), n);
     return launch_status("cast_f32_bf16");
   });
 }
@@ -273,7 +283,7 @@ int vqa_memset_zero(void* plan, void* ptr, long long bytes, void* stream) {
 int vqa_axpy_f32(void* plan, float* y, const float* x, float a, long long n, void* stream) {
   note_op("axpy", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    axpy_kernel<<<grid_for((n >> 2) + 4, 256), 256, 0, s>>>(y, x, a, n);
+    launch_pdl(axpy_kernel, dim3(grid_for((n >> 2) + 4, 256)), dim3(256), 0, s, y, x, a, n);
     return launch_status("axpy");
   });
 }
@@ -286,7 +296,7 @@ int vqa_fold_conv_bn(void* plan, const float* w, const float* gamma, const float
     const long long total = static_cast<long long>(O) * R * Sp * Ip;
     int grid = grid_for(total, 256);
     if (grid * 256 < O) grid = (O + 255) / 256;
-    fold_conv_bn_kernel<<<grid, 256, 0, s>>>(w, gamma, beta, mean, var, eps, static_cast<__nv_bfloat16*>(w_out),
+    launch_pdl(fold_conv_bn_kernel, dim3(grid), dim3(256), 0, s, w, gamma, beta, mean, var, eps, static_cast<__nv_bfloat16*>(w_out),
                                              bias_out, O, I, R, S, Sp, Ip);
     return launch_status("fold_conv_bn");
   });
@@ -296,7 +306,7 @@ int vqa_convT_weight_prep(void* plan, const float* w, void* w_out, int Cin, int 
   note_op("convT_weight_prep", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     dim3 grid((Cout * 9 + 31) / 32, (Cin + 31) / 32), block(32, 8);
-    transpose_flip9_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(w, static_cast<__nv_bfloat16*>(w_out), Cin, Cout * 9);
+    launch_pdl(transpose_flip9_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, s, w, static_cast<__nv_bfloat16*>(w_out), Cin, Cout * 9);
     return launch_status("convT_weight_prep");
   });
 }
@@ -306,7 +316,7 @@ int vqa_convT_wgrad_unprep(void* plan, const float* dw_conv, float* dw, int Cin,
   note_op("convT_wgrad_unprep", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     dim3 grid((Cin + 31) / 32, (Cout * 9 + 31) / 32), block(32, 8);
-    transpose_fliprow9_kernel<<<grid, block, 0, s>>>(dw_conv, dw, Cout * 9, Cin);
+    launch_pdl(transpose_fliprow9_kernel, dim3(grid), dim3(block), 0, s, dw_conv, dw, Cout * 9, Cin);
     return launch_status("convT_wgrad_unprep");
   });
 }
@@ -315,7 +325,7 @@ int vqa_image_to_stem(void* plan, const float* img, void* out, int N, int H, int
   note_op("image_to_stem", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     const long long total = static_cast<long long>(N) * H * (W + 8);
-    image_to_stem_kernel<<<grid_for(total, 256, 16), 256, 0, s>>>(img, static_cast<uint4*>(out), N, H, W);
+    launch_pdl(image_to_stem_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, s, img, static_cast<uint4*>(out), N, H, W);
     return launch_status("image_to_stem");
   });
 }
@@ -324,7 +334,7 @@ int vqa_nhwc_to_nchw_f32(void* plan, const void* x, float* out, int N, int H, in
   note_op("nhwc_to_nchw", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     dim3 grid((C + 31) / 32, (H * W + 31) / 32, N), block(32, 8);
-    nhwc_to_nchw_kernel<<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16*>(x), out, H * W, C);
+    launch_pdl(nhwc_to_nchw_kernel, dim3(grid), dim3(block), 0, s, static_cast<const __nv_bfloat16*>(x), out, H * W, C);
     return launch_status("nhwc_to_nchw");
   });
 }
@@ -335,7 +345,7 @@ int vqa_maxpool3x3s2(void* plan, const void* x, void* out, int N, int H, int W, 
   return submit(plan, stream, [=](cudaStream_t s) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long total = static_cast<long long>(N) * Ho * Wo * (C / 8);
-    maxpool3x3s2_kernel<<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x),
+    launch_pdl(maxpool3x3s2_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(x),
                                                                    static_cast<__nv_bfloat16*>(out), N, H, W, C, Ho, Wo);
     return launch_status("maxpool3x3s2");
   });
@@ -347,7 +357,7 @@ int vqa_dropout_cast(void* plan, const float* x, void* out_bf16, long long rows,
   note_op("dropout_cast", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     const long long n8 = rows * N / 8;
-    dropout_cast_kernel<<<grid_for(n8, 256), 256, 0, s>>>(x, static_cast<__nv_bfloat16*>(out_bf16), n8, drop_p, sid,
+    launch_pdl(dropout_cast_kernel, dim3(grid_for(n8, 256)), dim3(256), 0, s, x, static_cast<__nv_bfloat16*>(out_bf16), n8, drop_p, sid,
                                                           reinterpret_cast<const unsigned long long*>(rng));
     return launch_status("dropout_cast");
   });
@@ -361,7 +371,7 @@ int vqa_colsum_bf16(void* plan, const void* x, long long ld, float* out, int M, 
     if (gy > 64) gy = 64;
     if (gy < 1) gy = 1;
     dim3 grid((N + 255) / 256, gy);
-    colsum_bf16_kernel<<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld, out, M, N);
+    launch_pdl(colsum_bf16_kernel, dim3(grid), dim3(block), 0, s, static_cast<const __nv_bfloat16*>(x), ld, out, M, N);
     return launch_status("colsum_bf16");
   });
 }

@@ -15,6 +15,29 @@ enum : int {
                        // convolution): k-block -> pixel box (n, th, tw); 64-channel chunks along MN
 };
 
+// Division by a run-time constant as a multiply-high + shift (the tile scheduler and the pixel-box row mapping
+// divide by launch constants once per tile per thread; a hardware-free `/` costs ~25 instructions each).
+// Exact for 0 <= n < 2^31 and 1 <= d < 2^31.
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(int dv) {
+  FastDiv f;
+  f.d = static_cast<uint32_t>(dv < 1 ? 1 : dv);
+  if (f.d == 1) { f.mul = 0; f.shr = 0; return f; }
+  uint32_t l = 0;
+  while ((1ull << l) < f.d) ++l;                       // ceil(log2 d)
+  const unsigned long long m = ((1ull << (31 + l)) + f.d - 1) / f.d;   // ceil(2^(31+l) / d)  (< 2^32)
+  f.mul = static_cast<uint32_t>(m);
+  f.shr = l - 1;                                        // q = (n * m) >> (31 + l) = mulhi(n, m) >> (l - 1)
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f) {
+  return f.d == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), f.mul) >> f.shr);
+}
+#endif
+
 struct GemmParams {
   int M, N;        // output extent (rows, cols); for LOAD_CONV M is implied by the pixel boxes
   int kb_total;    // number of 64-deep k-blocks in the whole contraction
@@ -25,6 +48,7 @@ struct GemmParams {
   // pixel-box geometry (LOAD_CONV for A; LOAD_PIXELS_MN for A and/or B)
   int bx_w, bx_h, bx_n;        // box extent in output pixels (w, h, images); product = rows per box
   int tiles_w, tiles_h;        // boxes per image along w and h
+  FastDiv fd_tiles_w, fd_tiles_h, fd_bx_w, fd_bx_h;   // divisors of the fields above
   int Wo, Ho, Nimg;            // output spatial size and image count
   int taps_s, cchunks;         // LOAD_CONV: filter width S and 64-channel chunks per tap
   int stride_w, stride_h, pad_w, pad_h, dil_w;  // input coord = out*stride - pad + tap*dil

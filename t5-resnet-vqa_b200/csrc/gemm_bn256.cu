@@ -1,0 +1,9 @@
+// Instantiations of the tcgen05 GEMM kernel for the 128 x 256 output tile (see gemm_kernel.cuh).
+#include "gemm_kernel.cuh"
+
+namespace vqa {
+int launch_gemm_bn256(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int tiles_m, int tiles_n,
+                     int splits, cudaStream_t stream) {
+  return launch_bn<256, 3>(tmA, tmB, p, tiles_m, tiles_n, splits, stream);
+}
+}  // namespace vqa

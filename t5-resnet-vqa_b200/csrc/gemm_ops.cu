@@ -195,6 +195,8 @@ void gemm_debug_set_umma(int a_lbo, int a_sbo, int b_lbo, int b_sbo) {
 int gemm_op_run(const GemmOp* op, cudaStream_t stream) {
   if (!op->valid) { set_last_error("gemm_op_run: op not initialised"); return -1; }
   GemmParams p = op->p;
+  p.fd_tiles_w = make_fastdiv(p.tiles_w); p.fd_tiles_h = make_fastdiv(p.tiles_h);
+  p.fd_bx_w = make_fastdiv(p.bx_w); p.fd_bx_h = make_fastdiv(p.bx_h);
   p.dbg_a_lbo = g_dbg[0]; p.dbg_a_sbo = g_dbg[1]; p.dbg_b_lbo = g_dbg[2]; p.dbg_b_sbo = g_dbg[3];
   int r = launch_gemm(op->tmA, op->tmB, p, op->bn, op->split_k, stream);
   if (r) set_last_error("gemm launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));

@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(kPoolThreads)
 pooler_fwd_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ bptr,
                   float* __restrict__ w_out, float* __restrict__ pooled_f32, __nv_bfloat16* __restrict__ pooled_bf16,
                   int L, int D) {
+  pdl_grid_sync();
   extern __shared__ float sc[];  // [L]
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(kPoolThreads)
 pooler_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a, const float* __restrict__ w,
                   const float* __restrict__ dpooled, float* __restrict__ dx, float* __restrict__ da,
                   float* __restrict__ db, int L, int D) {
+  pdl_grid_sync();
   extern __shared__ float sm[];  // ds[L]
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,6 +116,7 @@ pooler_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a, cons
 __global__ void __launch_bounds__(1024)
 logsoftmax_nll_fwd_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ labels,
                           float* __restrict__ logp, float* __restrict__ loss, int B, int A) {
+  pdl_grid_sync();
   extern __shared__ float nll[];  // [B]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int row = warp; row < B; row += 32) {
@@ -144,6 +147,7 @@ logsoftmax_nll_fwd_kernel(const float* __restrict__ logits, long long ld, const 
 __global__ void logsoftmax_nll_bwd_kernel(const float* __restrict__ logp, const long long* __restrict__ labels,
                                           const float* __restrict__ gloss, const float* __restrict__ glogp,
                                           __nv_bfloat16* __restrict__ dlogits, long long ld, int B, int A) {
+  pdl_grid_sync();
   const int row = blockIdx.x;
   const int lane = threadIdx.x;  // one warp per row
   const float gl = (labels != nullptr) ? (gloss != nullptr ? gloss[0] : 1.f) / static_cast<float>(B) : 0.f;
@@ -174,7 +178,7 @@ int vqa_pooler_fwd(void* plan, const float* x, const float* a, const float* b, f
   if (D % 4) { set_last_error("pooler: D must be a multiple of 4"); return -1; }
   note_op("pooler_fwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    pooler_fwd_kernel<<<B, kPoolThreads, L * sizeof(float), s>>>(x, a, b, w_out, pooled_f32,
+    launch_pdl(pooler_fwd_kernel, dim3(B), dim3(kPoolThreads), L * sizeof(float), s, x, a, b, w_out, pooled_f32,
                                                                  static_cast<__nv_bfloat16*>(pooled_bf16), L, D);
     return launch_status("pooler_fwd");
   });
@@ -185,7 +189,7 @@ int vqa_pooler_bwd(void* plan, const float* x, const float* a, const float* w, c
   if (D % 4) { set_last_error("pooler: D must be a multiple of 4"); return -1; }
   note_op("pooler_bwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    pooler_bwd_kernel<<<B, kPoolThreads, L * sizeof(float), s>>>(x, a, w, dpooled, dx, da, db, L, D);
+    launch_pdl(pooler_bwd_kernel, dim3(B), dim3(kPoolThreads), L * sizeof(float), s, x, a, w, dpooled, dx, da, db, L, D);
     return launch_status("pooler_bwd");
   });
 }
@@ -195,7 +199,7 @@ int vqa_logsoftmax_nll_fwd(void* plan, const float* logits, long long ld, const 
   if (B > 8192) { set_last_error("logsoftmax_nll: batch > 8192 not supported"); return -1; }
   note_op("logsoftmax_nll_fwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    logsoftmax_nll_fwd_kernel<<<1, 1024, B * sizeof(float), s>>>(logits, ld, labels, logp, loss, B, A);
+    launch_pdl(logsoftmax_nll_fwd_kernel, dim3(1), dim3(1024), B * sizeof(float), s, logits, ld, labels, logp, loss, B, A);
     return launch_status("logsoftmax_nll_fwd");
   });
 }
@@ -204,7 +208,7 @@ int vqa_logsoftmax_nll_bwd(void* plan, const float* logp, const long long* label
                            const float* glogp, void* dlogits, long long ld, int B, int A, void* stream) {
   note_op("logsoftmax_nll_bwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    logsoftmax_nll_bwd_kernel<<<B, 32, 0, s>>>(logp, labels, gloss, glogp, static_cast<__nv_bfloat16*>(dlogits), ld,
+    launch_pdl(logsoftmax_nll_bwd_kernel, dim3(B), dim3(32), 0, s, logp, labels, gloss, glogp, static_cast<__nv_bfloat16*>(dlogits), ld,
                                                B, A);
     return launch_status("logsoftmax_nll_bwd");
   });

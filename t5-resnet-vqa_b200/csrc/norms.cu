@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(kThreads)
 rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y_bf16,
                    float* __restrict__ y_f32, float* __restrict__ rstd, int M, float eps, float drop_p,
                    uint32_t sid, const unsigned long long* __restrict__ rng) {
+  pdl_grid_sync();
   constexpr int D = NC * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const DropCtx dc = drop_ctx(drop_p, sid, rng);
@@ -62,6 +63,7 @@ rmsnorm_bwd_kernel(const void* __restrict__ dy, int dy_fp32, const float* __rest
                    const float* __restrict__ w, const float* __restrict__ rstd, const float* __restrict__ dres,
                    float* __restrict__ dx, float* __restrict__ dw, int M, float drop_p, uint32_t sid,
                    const unsigned long long* __restrict__ rng) {
+  pdl_grid_sync();
   constexpr int D = NC * 256;
   __shared__ float red[kWarps][D];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(kThreads)
 layernorm_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32, float* __restrict__ mean,
                      float* __restrict__ rstd, int M, float eps) {
+  pdl_grid_sync();
   constexpr int D = NC * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float gv[NC][8], bv[NC][8];
@@ -177,6 +180,7 @@ __global__ void __launch_bounds__(kThreads)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dz,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int M) {
+  pdl_grid_sync();
   constexpr int D = NC * 256;
   __shared__ float red[kWarps][D];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -270,8 +274,7 @@ int vqa_rmsnorm_fwd(void* plan, const float* x, const float* w, void* y_bf16, fl
   if (check_d(D, "rmsnorm_fwd")) return -1;
   note_op("rmsnorm_fwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    DISPATCH_NC(D, (rmsnorm_fwd_kernel<NC><<<norm_grid(M), kThreads, 0, s>>>(
-                       x, w, static_cast<__nv_bfloat16*>(y_bf16), y_f32, rstd, M, eps, drop_p, sid,
+    DISPATCH_NC(D, (launch_pdl(rmsnorm_fwd_kernel<NC>, dim3(norm_grid(M)), dim3(kThreads), 0, s, x, w, static_cast<__nv_bfloat16*>(y_bf16), y_f32, rstd, M, eps, drop_p, sid,
                        reinterpret_cast<const unsigned long long*>(rng))));
     return launch_status("rmsnorm_fwd");
   });
@@ -283,8 +286,7 @@ int vqa_rmsnorm_bwd(void* plan, const void* dy, int dy_fp32, const float* x, con
   if (check_d(D, "rmsnorm_bwd")) return -1;
   note_op("rmsnorm_bwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    DISPATCH_NC(D, (rmsnorm_bwd_kernel<NC><<<norm_grid(M), kThreads, 0, s>>>(
-                       dy, dy_fp32, x, w, rstd, dres, dx, dw, M, drop_p, sid,
+    DISPATCH_NC(D, (launch_pdl(rmsnorm_bwd_kernel<NC>, dim3(norm_grid(M)), dim3(kThreads), 0, s, dy, dy_fp32, x, w, rstd, dres, dx, dw, M, drop_p, sid,
                        reinterpret_cast<const unsigned long long*>(rng))));
     return launch_status("rmsnorm_bwd");
   });
@@ -295,8 +297,7 @@ int vqa_layernorm_fwd(void* plan, const float* z, const float* gamma, const floa
   if (check_d(D, "layernorm_fwd")) return -1;
   note_op("layernorm_fwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    DISPATCH_NC(D, (layernorm_fwd_kernel<NC><<<norm_grid(M), kThreads, 0, s>>>(
-                       z, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, eps)));
+    DISPATCH_NC(D, (launch_pdl(layernorm_fwd_kernel<NC>, dim3(norm_grid(M)), dim3(kThreads), 0, s, z, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd, M, eps)));
     return launch_status("layernorm_fwd");
   });
 }
@@ -306,7 +307,7 @@ int vqa_layernorm_bwd(void* plan, const float* dy, const float* z, const float* 
   if (check_d(D, "layernorm_bwd")) return -1;
   note_op("layernorm_bwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    DISPATCH_NC(D, (layernorm_bwd_kernel<NC><<<norm_grid(M), kThreads, 0, s>>>(dy, z, gamma, mean, rstd, dz,
+    DISPATCH_NC(D, (launch_pdl(layernorm_bwd_kernel<NC>, dim3(norm_grid(M)), dim3(kThreads), 0, s, dy, z, gamma, mean, rstd, dz,
                                                                                  dgamma, dbeta, M)));
     return launch_status("layernorm_bwd");
   });

@@ -12,6 +12,7 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  pdl_grid_sync();
   __shared__ float red[8];
   float acc = 0.f;
   const long long nvec = n >> 2;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              float* __restrict__ vmax, __nv_bfloat16* __restrict__ shadow, long long n, AdamHyper h,
              const float* __restrict__ gnorm_sq) {
+  pdl_grid_sync();
   float clip = 1.f;
   if (gnorm_sq != nullptr) {
     const float norm = __fsqrt_rn(gnorm_sq[0]);
@@ -101,7 +103,8 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
-__global__ void rng_advance_kernel(unsigned long long* rng) { rng[1] += 1ull; }
+__global__ void rng_advance_kernel(unsigned long long* rng) {
+  pdl_grid_sync(); rng[1] += 1ull; }
 
 inline int stream_grid(long long items, int threads) {
   long long b = (items + threads - 1) / threads;
@@ -117,7 +120,7 @@ int vqa_sumsq_f32(void* plan, const float* x, long long n, float* out, void* str
   if (reinterpret_cast<uintptr_t>(x) & 15) { set_last_error("sumsq: pointer must be 16-byte aligned"); return -1; }
   note_op("sumsq", 0.0, 4.0 * static_cast<double>(n));
   return submit(plan, stream, [=](cudaStream_t s) {
-    sumsq_kernel<<<stream_grid((n >> 2) + 4, 256), 256, 0, s>>>(x, n, out);
+    launch_pdl(sumsq_kernel, dim3(stream_grid((n >> 2) + 4, 256)), dim3(256), 0, s, x, n, out);
     return launch_status("sumsq");
   });
 }
@@ -145,7 +148,7 @@ int vqa_adamw_amsgrad(void* plan, float* p, const float* g, float* m, float* v, 
   h.max_norm = max_norm; h.amsgrad = amsgrad;
   note_op("adamw", 0.0, (amsgrad ? 36.0 : 28.0) * static_cast<double>(n) + (shadow ? 2.0 * n : 0.0));
   return submit(plan, stream, [=](cudaStream_t s) {
-    adamw_kernel<<<stream_grid((n >> 2) + 4, 256), 256, 0, s>>>(p, g, m, v, vmax, static_cast<__nv_bfloat16*>(shadow), n, h,
+    launch_pdl(adamw_kernel, dim3(stream_grid((n >> 2) + 4, 256)), dim3(256), 0, s, p, g, m, v, vmax, static_cast<__nv_bfloat16*>(shadow), n, h,
                                                                 gnorm_sq);
     return launch_status("adamw");
   });
@@ -154,7 +157,7 @@ int vqa_adamw_amsgrad(void* plan, float* p, const float* g, float* m, float* v, 
 int vqa_rng_advance(void* plan, uint64_t* rng, void* stream) {
   note_op("rng_advance", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    rng_advance_kernel<<<1, 1, 0, s>>>(reinterpret_cast<unsigned long long*>(rng));
+    launch_pdl(rng_advance_kernel, dim3(1), dim3(1), 0, s, reinterpret_cast<unsigned long long*>(rng));
     return launch_status("rng_advance");
   });
 }

@@ -80,6 +80,7 @@ int vqa_plan_capture_graph(void* plan, void* stream) {
 // front lets the host queue everything before the first launch starts, so the event-to-event times are the
 // launches' back-to-back device durations, not host enqueue gaps.  ms_out has vqa_plan_size(plan) entries.
 __global__ void vqa_spin_kernel(long long ns) {
+  pdl_grid_sync();
   long long t0, t1;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   do {
@@ -95,7 +96,7 @@ int vqa_plan_profile(void* plan, void* stream, float* ms_out, int spin_us) {
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) cudaEventCreate(&e);
   int rc = 0;
-  if (spin_us > 0) vqa_spin_kernel<<<1, 1, 0, s>>>(static_cast<long long>(spin_us) * 1000);
+  if (spin_us > 0) launch_pdl(vqa_spin_kernel, dim3(1), dim3(1), 0, s, static_cast<long long>(spin_us) * 1000);
   for (size_t i = 0; i < n && rc == 0; ++i) {
     cudaEventRecord(ev[i], s);
     rc = p->ops[i](s);

@@ -11,6 +11,7 @@ namespace {
 __global__ void embedding_fwd_kernel(const long long* __restrict__ ids, const float* __restrict__ table,
                                      float* __restrict__ out, int M, int D, int vocab, float drop_p, uint32_t sid,
                                      const unsigned long long* __restrict__ rng) {
+  pdl_grid_sync();
   const DropCtx dc = drop_ctx(drop_p, sid, rng);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -31,6 +32,7 @@ __global__ void embedding_fwd_kernel(const long long* __restrict__ ids, const fl
 __global__ void embedding_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dout,
                                      float* __restrict__ dtable, int M, int D, int vocab, float drop_p,
                                      uint32_t sid, const unsigned long long* __restrict__ rng) {
+  pdl_grid_sync();
   const DropCtx dc = drop_ctx(drop_p, sid, rng);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -51,6 +53,7 @@ __global__ void embedding_bwd_kernel(const long long* __restrict__ ids, const fl
 
 __global__ void t5_bias_build_kernel(const float* __restrict__ table, const int* __restrict__ bucket,
                                      float* __restrict__ bias, int H, int LL) {
+  pdl_grid_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= H * LL) return;
   const int h = idx / LL, ij = idx - h * LL;
@@ -59,6 +62,7 @@ __global__ void t5_bias_build_kernel(const float* __restrict__ table, const int*
 
 __global__ void t5_bias_grad_kernel(const float* __restrict__ dbias, const int* __restrict__ bucket,
                                     float* __restrict__ dtable, int H, int LL) {
+  pdl_grid_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= H * LL) return;
   const int h = idx / LL, ij = idx - h * LL;
@@ -76,7 +80,7 @@ int vqa_embedding_fwd(void* plan, const long long* ids, const float* table, floa
   return submit(plan, stream, [=](cudaStream_t s) {
     int grid = (M + 7) / 8;
     if (grid > 148 * 8) grid = 148 * 8;
-    embedding_fwd_kernel<<<grid, 256, 0, s>>>(ids, table, out, M, D, vocab, drop_p, sid,
+    launch_pdl(embedding_fwd_kernel, dim3(grid), dim3(256), 0, s, ids, table, out, M, D, vocab, drop_p, sid,
                                               reinterpret_cast<const unsigned long long*>(rng));
     return launch_status("embedding_fwd");
   });
@@ -89,7 +93,7 @@ int vqa_embedding_bwd(void* plan, const long long* ids, const float* dout, float
   return submit(plan, stream, [=](cudaStream_t s) {
     int grid = (M + 7) / 8;
     if (grid > 148 * 8) grid = 148 * 8;
-    embedding_bwd_kernel<<<grid, 256, 0, s>>>(ids, dout, dtable, M, D, vocab, drop_p, sid,
+    launch_pdl(embedding_bwd_kernel, dim3(grid), dim3(256), 0, s, ids, dout, dtable, M, D, vocab, drop_p, sid,
                                               reinterpret_cast<const unsigned long long*>(rng));
     return launch_status("embedding_bwd");
   });
@@ -101,7 +105,7 @@ int vqa_t5_bias_build(void* plan, const float* table, const int* bucket, float* 
   note_op("t5_bias_build", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     const int total = H * L * L;
-    t5_bias_build_kernel<<<(total + 255) / 256, 256, 0, s>>>(table, bucket, bias, H, L * L);
+    launch_pdl(t5_bias_build_kernel, dim3((total + 255) / 256), dim3(256), 0, s, table, bucket, bias, H, L * L);
     return launch_status("t5_bias_build");
   });
 }
@@ -112,7 +116,7 @@ int vqa_t5_bias_grad(void* plan, const float* dbias, const int* bucket, float* d
   note_op("t5_bias_grad", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     const int total = H * L * L;
-    t5_bias_grad_kernel<<<(total + 255) / 256, 256, 0, s>>>(dbias, bucket, dtable, H, L * L);
+    launch_pdl(t5_bias_grad_kernel, dim3((total + 255) / 256), dim3(256), 0, s, dbias, bucket, dtable, H, L * L);
     return launch_status("t5_bias_grad");
   });
 }

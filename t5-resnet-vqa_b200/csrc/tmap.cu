@@ -1,8 +1,10 @@
 #include "tmap.cuh"
+#include "common.cuh"
 
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace vqa {
 
@@ -24,6 +26,15 @@ int load_encode() {
   return 0;
 }
 }  // namespace
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VQA_B200_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;

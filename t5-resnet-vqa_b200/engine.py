@@ -140,26 +140,39 @@ class _Rec:
         return call
 
 
+N_SM = 148
+
+
+def _tile_cost(tiles, bn):
+    """Relative time of a persistent launch: waves over the SMs x (tile width + fixed per-tile cost in columns:
+    the A-tile load, pipeline fill and the epilogue's fixed part)."""
+    waves = (tiles + N_SM - 1) // N_SM
+    return waves * (bn + 48)
+
+
 def pick_tile(M, N, K, can_split, split_k=1):
-    """Output tile width for the 128 x bn tcgen05 GEMM: fill the 148 SMs, prefer wide tiles."""
+    """Output tile width for the persistent 128 x bn tcgen05 GEMM (one CTA per SM)."""
     tm = (M + 127) // 128
+    best = None
     for bn in (256, 128, 64):
-        if bn > 64 and N < bn:
+        if bn > 64 and N <= bn // 2:
             continue
-        tiles = tm * ((N + bn - 1) // bn)
-        if tiles >= 120 or bn == 64:
-            return bn, 1
-    return 64, 1
+        cost = _tile_cost(tm * ((N + bn - 1) // bn), bn)
+        if best is None or cost < best[0]:
+            best = (cost, bn)
+    return best[1], 1
 
 
 def pick_conv_tile(M, Cout):
     tm = (M + 127) // 128
+    best = None
     for bn in (256, 128, 64):
-        if Cout % bn and bn > 64:
+        if bn > 64 and Cout <= bn // 2:
             continue
-        if tm * ((Cout + bn - 1) // bn) >= 140 or bn == 64:
-            return bn
-    return 64
+        cost = _tile_cost(tm * ((Cout + bn - 1) // bn), bn)
+        if best is None or cost < best[0]:
+            best = (cost, bn)
+    return best[1]
 
 
 class Engine:
