@@ -1,0 +1,145 @@
+"""CPU: host-side logic of the drop-in module - reference state_dict layout, flat parameter layout, tile
+heuristics, optimizer registration, loud failure without CUDA, and the data-parallel gradient averaging over
+gloo with world_size 2."""
+import os
+import socket
+
+import pytest
+import torch
+
+
+@pytest.fixture(scope="module")
+def model(pkg):
+    os.environ["VQA_B200_PRETRAINED"] = "0"
+    torch.manual_seed(0)
+    return pkg.ResnetVQAModel("resnet34", "t5-base", answer_spaces=170)
+
+
+def test_state_dict_layout_matches_reference(model):
+    from oracle import vqa_oracle as O
+    spec = O.state_dict_spec("resnet34", 170)
+    sd = model.state_dict()
+    assert list(sd.keys()) == [k for k, _, _ in spec]
+    assert len(sd) == 403                                      # SURVEY 8b [probe]
+    for k, shape, _ in spec:
+        assert tuple(sd[k].shape) == tuple(shape), k
+    assert sum(p.numel() for p in model.parameters()) == 166_985_555
+    for v in sd.values():
+        assert v.dtype in (torch.float32, torch.int64)
+    # strict load of a reference-layout state_dict, both directions
+    ref = O.random_state_dict("resnet34", 170, seed=0)
+    model.load_state_dict(ref, strict=True)
+    assert torch.equal(model.state_dict()["sga_modules.1.mhatt2.linear_k.bias"], ref["sga_modules.1.mhatt2.linear_k.bias"])
+
+
+def test_trainer_facing_attributes(model):
+    for name in ("vision_model", "lang_model", "upscale_layer", "downscale_layer", "sga_modules", "attention_pooler",
+                 "classification_layer"):
+        assert len(list(getattr(model, name).parameters())) > 0
+    assert model.vision_model_name == "resnet34" and model.device == "cpu"
+    import inspect
+    sig = list(inspect.signature(model.forward).parameters)
+    assert sig[:6] == ["question_input_ids", "decoder_question_input_ids", "question_attention_masks",
+                       "decoder_question_attention_masks", "annotation_ids", "image_tensors"]
+    assert set(sig[6:]) == {"answer_input_ids", "pixel_values", "answer_attention_masks", "question_type_ids"}
+
+
+def test_flat_layout_covers_exactly_the_trainable_tensors(model):
+    from oracle import vqa_oracle as O
+    eng = model._engine
+    big, small = eng._layout()
+    names = {id(p): k for k, p in model.named_parameters()}
+    got = sorted(names[id(p)] for p in big + small)
+    want = sorted(O.trainable_keys(model.state_dict(), "resnet34"))
+    assert got == want
+    assert len(set(id(p) for p in big + small)) == len(big) + len(small)
+    # fused projections need their weights adjacent and in this order
+    order = [names[id(p)] for p in big]
+    i = order.index("lang_model.block.3.layer.0.SelfAttention.q.weight")
+    assert order[i + 1].endswith("block.3.layer.0.SelfAttention.k.weight")
+    assert order[i + 2].endswith("block.3.layer.0.SelfAttention.v.weight")
+    j = order.index("sga_modules.1.mhatt1.linear_v.weight")
+    assert order[j + 1].endswith("mhatt1.linear_k.weight") and order[j + 2].endswith("mhatt1.linear_q.weight")
+    # the embedding table is last: its dense gradient is all-reduced in the final bucket
+    assert names[id(small[-1])] == "lang_model.embed_tokens.weight"
+
+
+def test_no_cpu_fallback(model):
+    from oracle import vqa_oracle as O
+    b = O.synthetic_batch(1, 16, 64, 64, 170, seed=1)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        model(b["question_input_ids"], None, b["question_attention_masks"], None, b["annotation_ids"],
+              b["image_tensors"])
+    with pytest.raises(RuntimeError, match="parameter container"):
+        model.sga_modules[0](torch.zeros(1, 4, 768), torch.zeros(1, 4, 768))
+
+
+def test_optimizer_is_registered_where_the_trainer_looks(pkg):
+    assert getattr(torch.optim, "VQAFusedAdamW") is pkg.VQAFusedAdamW
+    p = torch.nn.Parameter(torch.zeros(8))
+    opt = torch.optim.VQAFusedAdamW([{"params": [p], "lr": 1e-3, "model_name": "x"}], weight_decay=0.1, amsgrad=True)
+    assert opt.param_groups[0]["model_name"] == "x" and opt.param_groups[0]["amsgrad"] is True
+    p.grad = torch.ones(8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        opt.step()
+
+
+def test_tile_heuristics_and_buckets(pkg):
+    from t5_resnet_vqa_b200 import engine as E
+    from oracle import vqa_oracle as O
+    for M, N in [(2048, 768), (2048, 2304), (64, 170), (200704, 64), (3136, 2048), (128, 768)]:
+        bn, sk = E.pick_tile(M, N, 768, False)
+        assert bn in (64, 128, 256) and sk == 1
+    assert E.pick_tile(64, 170, 768, False)[0] <= 128
+    for L in (16, 32, 20):
+        assert torch.equal(E.t5_relative_buckets(L, L).long(), O.t5_buckets(L, L))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _ddp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from t5_resnet_vqa_b200 import ddp
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+
+    class Seg:
+        def __init__(self, lo, hi):
+            self.grad_lo, self.grad_hi = lo, hi
+    total = 1000
+    segs = [Seg(0, 300), Seg(300, 640), Seg(640, 1000)]
+    ranges = ddp.segment_ranges(segs, total)
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(total, generator=g)
+    mine = flat.clone()
+    for lo, hi in ranges:
+        ddp.average_range(flat, lo, hi)
+    others = [torch.randn(total, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+    want = sum(others) / world
+    ok = torch.allclose(flat, want, atol=1e-6) and not torch.equal(mine, flat)
+    try:
+        ddp.segment_ranges([Seg(0, 300), Seg(310, 1000)], total)
+        ok = False
+    except RuntimeError:
+        pass
+    out.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gradient_averaging_two_ranks_gloo(pkg):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
