@@ -45,6 +45,13 @@ int vqa_plan_destroy(void* plan);
 int vqa_plan_size(void* plan);                       /* number of recorded launches */
 int vqa_plan_run(void* plan, void* stream);          /* replay (through the CUDA graph if captured) */
 int vqa_plan_capture_graph(void* plan, void* stream);/* capture the recorded launches into a CUDA graph */
+/* Two-lane plans: launches recorded after vqa_plan_set_lane(plan, 1) replay on a plan-owned side stream and
+ * overlap lane 0 (parallel graph branches).  vqa_plan_fork: lane 1 waits for everything recorded on lane 0 so
+ * far; vqa_plan_join: lane 0 waits for lane 1.  A plan is always joined at its end.  The caller must keep the
+ * two lanes' buffers disjoint between a fork and the next join. */
+int vqa_plan_set_lane(void* plan, int lane);
+int vqa_plan_fork(void* plan);
+int vqa_plan_join(void* plan);
 /* measurement aid: eager replay with a CUDA event between launches; ms_out[vqa_plan_size] device durations
  * (synchronises the stream).  op_info: kernel family and the algorithmic flops / HBM bytes of launch i. */
 int vqa_plan_profile(void* plan, void* stream, float* ms_out, int spin_us);
@@ -132,9 +139,12 @@ int vqa_embedding_bwd(void* plan, const long long* ids, const float* dout, float
 int vqa_rmsnorm_fwd(void* plan, const float* x, const float* w, void* y_bf16, float* y_f32,
                     float* rstd, int M, int D, float eps, float drop_p, uint32_t sid,
                     const uint64_t* rng, void* stream);
+/* g_out (bf16 [M,D], may be NULL): dropout-masked copy of dx under stream g_sid / probability g_drop_p, i.e.
+ * the gradient entering the next residual branch, produced here instead of by a separate vqa_dropout_cast. */
 int vqa_rmsnorm_bwd(void* plan, const void* dy, int dy_fp32, const float* x, const float* w,
                     const float* rstd, const float* dres, float* dx, float* dw, int M, int D,
-                    float drop_p, uint32_t sid, const uint64_t* rng, void* stream);
+                    float drop_p, uint32_t sid, const uint64_t* rng, void* g_out, float g_drop_p,
+                    uint32_t g_sid, void* stream);
 /* relative-position bias (hf:236-251): bias[h,i,j] = table[bucket[i*Lk+j], h]; gradient back to table */
 int vqa_t5_bias_build(void* plan, const float* table, const int* bucket, float* bias, int H, int L,
                       int nbuckets, void* stream);
@@ -170,9 +180,12 @@ int vqa_attention_bwd(void* plan, const vqa_attn_bwd_args* a, void* stream);
  * z produced by the GEMM epilogue.  Backward: dz = d/dz, dgamma/dbeta accumulated atomically. */
 int vqa_layernorm_fwd(void* plan, const float* z, const float* gamma, const float* beta, void* y_bf16,
                       float* y_f32, float* mean, float* rstd, int M, int D, float eps, void* stream);
+/* g_out / g_colsum (may be NULL): dropout-masked bf16 copy of dz (stream g_sid) and its column sums += (the
+ * bias gradient of the residual branch's last Linear). */
 int vqa_layernorm_bwd(void* plan, const float* dy, const float* z, const float* gamma,
                       const float* mean, const float* rstd, float* dz, float* dgamma, float* dbeta,
-                      int M, int D, void* stream);
+                      int M, int D, void* g_out, float g_drop_p, uint32_t g_sid, const uint64_t* rng,
+                      float* g_colsum, void* stream);
 /* g = dropout_mask(x) as bf16 (gradient entering a dropped residual branch) */
 int vqa_dropout_cast(void* plan, const float* x, void* out_bf16, long long rows, int N, float drop_p,
                      uint32_t sid, const uint64_t* rng, void* stream);

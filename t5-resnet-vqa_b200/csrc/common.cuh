@@ -24,9 +24,21 @@ struct OpNote {
   double flops = 0.0;      // algorithmic floating-point operations of the launch (0 for bandwidth kernels)
   double bytes = 0.0;      // algorithmic HBM bytes of the launch (0 when not stated)
 };
+// Two lanes: lane 0 replays on the caller's stream, lane 1 on a plan-owned side stream, ordered only by
+// explicit fork (lane 1 waits for lane 0's position) and join (lane 0 waits for lane 1) markers.  Independent
+// chains - the frozen backbone next to the T5 encoder, weight gradients next to the data-gradient chain - then
+// overlap on the GPU; in a captured graph they become parallel branches.
+enum : int { PLAN_LAUNCH = 0, PLAN_FORK = 1, PLAN_JOIN = 2 };
 struct Plan {
-  std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<std::function<int(cudaStream_t)>> ops;   // launches only (notes[i] describes ops[i])
   std::vector<OpNote> notes;
+  std::vector<int> lanes;                               // lane of ops[i]
+  struct Step { int kind; int op; };                    // replay order: launches interleaved with fork / join
+  std::vector<Step> steps;
+  int cur_lane = 0;
+  bool lane1_open = false;                              // lane 1 has work not yet joined
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
 };
@@ -47,6 +59,9 @@ inline int submit(void* plan, void* stream, F&& fn) {
     Plan* p = static_cast<Plan*>(plan);
     p->ops.emplace_back(std::forward<F>(fn));
     p->notes.push_back(pending_note());
+    p->lanes.push_back(p->cur_lane);
+    p->steps.push_back({PLAN_LAUNCH, static_cast<int>(p->ops.size()) - 1});
+    if (p->cur_lane == 1) p->lane1_open = true;
     pending_note() = OpNote();
     return 0;
   }

@@ -62,12 +62,14 @@ __global__ void __launch_bounds__(kThreads)
 rmsnorm_bwd_kernel(const void* __restrict__ dy, int dy_fp32, const float* __restrict__ x,
                    const float* __restrict__ w, const float* __restrict__ rstd, const float* __restrict__ dres,
                    float* __restrict__ dx, float* __restrict__ dw, int M, float drop_p, uint32_t sid,
-                   const unsigned long long* __restrict__ rng) {
+                   const unsigned long long* __restrict__ rng, __nv_bfloat16* __restrict__ g_out, float g_drop_p,
+                   uint32_t g_sid) {
   pdl_grid_sync();
   constexpr int D = NC * 256;
   __shared__ float red[kWarps][D];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const DropCtx dc = drop_ctx(drop_p, sid, rng);
+  const DropCtx dcg = drop_ctx(g_out != nullptr ? g_drop_p : 0.f, g_sid, rng);
   float wv[NC][8], dwp[NC][8];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -110,6 +112,10 @@ rmsnorm_bwd_kernel(const void* __restrict__ dy, int dy_fp32, const float* __rest
         for (int i = 0; i < 8; ++i) o[i] += dr[i];
       }
       store_f32x8(dx + base + col, o);
+      if (g_out != nullptr) {   // dropout-masked bf16 copy: the GEMM operand of the next sub-layer's backward
+        drop8(dcg, static_cast<unsigned long long>(base + col), o);
+        store_bf16x8(g_out + base + col, o);
+      }
     }
   }
   if (dw != nullptr) {
@@ -179,11 +185,19 @@ template <int NC>
 __global__ void __launch_bounds__(kThreads)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dz,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
+                     __nv_bfloat16* __restrict__ g_out, float g_drop_p, uint32_t g_sid,
+                     const unsigned long long* __restrict__ rng, float* __restrict__ g_colsum) {
   pdl_grid_sync();
   constexpr int D = NC * 256;
   __shared__ float red[kWarps][D];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const DropCtx dcg = drop_ctx(g_out != nullptr ? g_drop_p : 0.f, g_sid, rng);
+  float gsp[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gsp[c][i] = 0.f;
   float gv[NC][8], dgp[NC][8], dbp[NC][8];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -220,6 +234,12 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, 
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = r * (g[c][i] - s1 - xh[c][i] * s2);
       store_f32x8(dz + base + (c * 32 + lane) * 8, o);
+      if (g_out != nullptr) {   // masked bf16 copy for the branch GEMMs + its column sum (the branch's bias grad)
+        drop8(dcg, static_cast<unsigned long long>(base + (c * 32 + lane) * 8), o);
+        store_bf16x8(g_out + base + (c * 32 + lane) * 8, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gsp[c][i] += o[i];
+      }
     }
   }
   // dgamma
@@ -245,6 +265,20 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, 
 #pragma unroll
     for (int j = 0; j < kWarps; ++j) s += red[j][col];
     atomicAdd(dbeta + col, s);
+  }
+  if (g_out != nullptr && g_colsum != nullptr) {
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[warp][(c * 32 + lane) * 8 + i] = gsp[c][i];
+    __syncthreads();
+    for (int col = threadIdx.x; col < D; col += kThreads) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < kWarps; ++j) s += red[j][col];
+      atomicAdd(g_colsum + col, s);
+    }
   }
 }
 
@@ -282,12 +316,13 @@ int vqa_rmsnorm_fwd(void* plan, const float* x, const float* w, void* y_bf16, fl
 
 int vqa_rmsnorm_bwd(void* plan, const void* dy, int dy_fp32, const float* x, const float* w, const float* rstd,
                     const float* dres, float* dx, float* dw, int M, int D, float drop_p, uint32_t sid,
-                    const uint64_t* rng, void* stream) {
+                    const uint64_t* rng, void* g_out, float g_drop_p, uint32_t g_sid, void* stream) {
   if (check_d(D, "rmsnorm_bwd")) return -1;
   note_op("rmsnorm_bwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     DISPATCH_NC(D, (launch_pdl(rmsnorm_bwd_kernel<NC>, dim3(norm_grid(M)), dim3(kThreads), 0, s, dy, dy_fp32, x, w, rstd, dres, dx, dw, M, drop_p, sid,
-                       reinterpret_cast<const unsigned long long*>(rng))));
+                       reinterpret_cast<const unsigned long long*>(rng), static_cast<__nv_bfloat16*>(g_out), g_drop_p,
+                       g_sid)));
     return launch_status("rmsnorm_bwd");
   });
 }
@@ -303,12 +338,14 @@ int vqa_layernorm_fwd(void* plan, const float* z, const float* gamma, const floa
 }
 
 int vqa_layernorm_bwd(void* plan, const float* dy, const float* z, const float* gamma, const float* mean,
-                      const float* rstd, float* dz, float* dgamma, float* dbeta, int M, int D, void* stream) {
+                      const float* rstd, float* dz, float* dgamma, float* dbeta, int M, int D, void* g_out,
+                      float g_drop_p, uint32_t g_sid, const uint64_t* rng, float* g_colsum, void* stream) {
   if (check_d(D, "layernorm_bwd")) return -1;
   note_op("layernorm_bwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    DISPATCH_NC(D, (launch_pdl(layernorm_bwd_kernel<NC>, dim3(norm_grid(M)), dim3(kThreads), 0, s, dy, z, gamma, mean, rstd, dz,
-                                                                                 dgamma, dbeta, M)));
+    DISPATCH_NC(D, (launch_pdl(layernorm_bwd_kernel<NC>, dim3(norm_grid(M)), dim3(kThreads), 0, s, dy, z, gamma, mean, rstd, dz, dgamma, dbeta, M,
+                       static_cast<__nv_bfloat16*>(g_out), g_drop_p, g_sid,
+                       reinterpret_cast<const unsigned long long*>(rng), g_colsum)));
     return launch_status("layernorm_bwd");
   });
 }

@@ -14,6 +14,9 @@ int vqa_plan_destroy(void* plan) {
   Plan* p = static_cast<Plan*>(plan);
   if (p->exec) cudaGraphExecDestroy(p->exec);
   if (p->graph) cudaGraphDestroy(p->graph);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
+  if (p->side) cudaStreamDestroy(p->side);
   delete p;
   return 0;
 }
@@ -22,11 +25,73 @@ int vqa_plan_size(void* plan) {
   return plan ? static_cast<int>(static_cast<Plan*>(plan)->ops.size()) : 0;
 }
 
+int vqa_plan_set_lane(void* plan, int lane) {
+  if (plan == nullptr || (lane != 0 && lane != 1)) { set_last_error("plan_set_lane: bad arguments"); return -1; }
+  static_cast<Plan*>(plan)->cur_lane = lane;
+  return 0;
+}
+
+int vqa_plan_fork(void* plan) {
+  if (plan == nullptr) return -1;
+  Plan* p = static_cast<Plan*>(plan);
+  p->steps.push_back({PLAN_FORK, -1});
+  return 0;
+}
+
+int vqa_plan_join(void* plan) {
+  if (plan == nullptr) return -1;
+  Plan* p = static_cast<Plan*>(plan);
+  p->steps.push_back({PLAN_JOIN, -1});
+  p->lane1_open = false;
+  return 0;
+}
+
+static int ensure_side(Plan* p) {
+  if (p->side != nullptr) return 0;
+  cudaError_t e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
+  if (e != cudaSuccess) { set_last_error("plan side stream: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+  return 0;
+}
+
 static int replay(Plan* p, cudaStream_t s) {
-  for (auto& op : p->ops) {
-    int r = op(s);
-    if (r) return r;
+  bool forked = false;   // lane 1 has been ordered after lane 0 at least once in this replay
+  bool open = false;     // lane 1 holds work lane 0 has not waited for
+  for (const Plan::Step& st : p->steps) {
+    if (st.kind == PLAN_LAUNCH) {
+      cudaStream_t target = s;
+      if (p->lanes[st.op] == 1) {
+        int r = ensure_side(p);
+        if (r) return r;
+        if (!forked) {   // implicit fork: lane 1 never runs ahead of the point where the plan started
+          cudaEventRecord(p->ev_fork, s);
+          cudaStreamWaitEvent(p->side, p->ev_fork, 0);
+          forked = true;
+        }
+        target = p->side;
+        open = true;
+      }
+      int r = p->ops[st.op](target);
+      if (r) return r;
+    } else if (st.kind == PLAN_FORK) {
+      int r = ensure_side(p);
+      if (r) return r;
+      cudaEventRecord(p->ev_fork, s);
+      cudaStreamWaitEvent(p->side, p->ev_fork, 0);
+      forked = true;
+    } else if (open) {  // PLAN_JOIN
+      cudaEventRecord(p->ev_join, p->side);
+      cudaStreamWaitEvent(s, p->ev_join, 0);
+      open = false;
+    }
   }
+  if (open) {  // a plan always ends joined: its caller only knows lane 0's stream
+    cudaEventRecord(p->ev_join, p->side);
+    cudaStreamWaitEvent(s, p->ev_join, 0);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_last_error("plan replay: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
   return 0;
 }
 

@@ -58,6 +58,19 @@ class _Rec:
     def _call(self, name, *args):
         L.check(getattr(self.lib, name)(self.plan, *args, self._s()), name)
 
+    # ---- lanes (parallel branches of a plan) ----
+    def lane(self, n):
+        if self.plan is not None:
+            L.check(self.lib.vqa_plan_set_lane(self.plan, n), "plan_set_lane")
+
+    def fork(self):
+        if self.plan is not None:
+            L.check(self.lib.vqa_plan_fork(self.plan), "plan_fork")
+
+    def join(self):
+        if self.plan is not None:
+            L.check(self.lib.vqa_plan_join(self.plan), "plan_join")
+
     # ---- contractions ----
     def gemm(self, M, N, K, A, lda, a_mn, B, ldb, b_mn, out, ldo, out_fp32, bias=None, relu=0, relu_mask=None,
              ldm=0, drop_p=0.0, sid=0, rng=None, residual=None, ldr=0, res_fp32=1, alpha=1.0, accumulate=0,
@@ -132,7 +145,7 @@ class _Rec:
     # ---- everything else: positional passthrough ----
     def __getattr__(self, name):
         fn_name = "vqa_" + name
-        if fn_name not in L.SIGNATURES:
+        if fn_name not in L.SIGNATURES or fn_name.startswith("vqa_plan_"):
             raise AttributeError(name)
 
         def call(*args):
@@ -183,6 +196,7 @@ class Engine:
         self.plans = {}
         self.run_id = 0
         self.use_graphs = _env_flag("VQA_B200_GRAPHS", True)
+        self.use_lanes = _env_flag("VQA_B200_LANES", True)
         self.vision_sig = None
         self.param_sig = None
         self.shadow_fresh = False

@@ -61,6 +61,9 @@ SIGNATURES = {
     "vqa_plan_size": (c_int, [_P]),
     "vqa_plan_run": (c_int, [_P, _P]),
     "vqa_plan_capture_graph": (c_int, [_P, _P]),
+    "vqa_plan_set_lane": (c_int, [_P, c_int]),
+    "vqa_plan_fork": (c_int, [_P]),
+    "vqa_plan_join": (c_int, [_P]),
     "vqa_plan_profile": (c_int, [_P, _P, _P, c_int]),
     "vqa_plan_op_info": (c_int, [_P, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_d),
                                  ctypes.POINTER(c_d)]),
@@ -79,13 +82,14 @@ SIGNATURES = {
     "vqa_embedding_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_f, c_u32, _P, _P]),
     "vqa_embedding_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_f, c_u32, _P, _P]),
     "vqa_rmsnorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_f, c_f, c_u32, _P, _P]),
-    "vqa_rmsnorm_bwd": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_f, c_u32, _P, _P]),
+    "vqa_rmsnorm_bwd": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_f, c_u32, _P, _P, c_f, c_u32,
+                                _P]),
     "vqa_t5_bias_build": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "vqa_t5_bias_grad": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "vqa_attention_fwd": (c_int, [_P, ctypes.POINTER(AttnFwdArgs), _P]),
     "vqa_attention_bwd": (c_int, [_P, ctypes.POINTER(AttnBwdArgs), _P]),
     "vqa_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_f, _P]),
-    "vqa_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "vqa_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, c_f, c_u32, _P, _P, _P]),
     "vqa_dropout_cast": (c_int, [_P, _P, _P, c_ll, c_int, c_f, c_u32, _P, _P]),
     "vqa_colsum_bf16": (c_int, [_P, _P, c_ll, _P, c_int, c_int, _P]),
     "vqa_pooler_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),

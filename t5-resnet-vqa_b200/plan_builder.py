@@ -78,6 +78,11 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     # =============================================================================================
     # frozen ResNet body (tv:266-277 without avgpool/fc), NHWC bf16, BatchNorm folded
     # =============================================================================================
+    # The backbone + projection chain is independent of the T5 encoder: it is recorded on lane 1 and overlaps the
+    # encoder (lane 0) until the first guided attention needs the vision tokens.
+    two_lanes = eng.use_lanes
+    if two_lanes:
+        r.lane(1)
     vm = m.vision_model
     stem_in = al(B, H, W + 8, 8)
     r.image_to_stem(st.images, stem_in, B, H, W)
@@ -138,6 +143,8 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     My = B * Ty
     y0 = al(My, D)
     r.conv(B, Hf, Wf, Cf, D, 3, 1, 1, feat, eng.proj_w, y0, bias=eng.mp(proj.bias), relu=0)
+    if two_lanes:
+        r.lane(0)
 
     # =============================================================================================
     # T5 encoder (hf:637-792)
@@ -218,6 +225,8 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
                         sv["mean1"], sv["rstd1"], M, D, float(sga.norm1.norm.eps))
         # mhatt2(v=y, k=y, q=x1)
         r.linear(sv["x1b"], M, D, D, eng.sp(m2.linear_q.weight), D, sv["q2"], D, bias=eng.mp(m2.linear_q.bias))
+        if li == 0 and two_lanes:
+            r.join()    # the vision tokens (lane 1) are needed from here on
         r.linear(y_bf16, Myl, D, D, eng.sp(m2.linear_v.weight), 2 * D, sv["vk2"], 2 * D,
                  bias=eng.mp(m2.linear_v.bias))
         vk = sv["vk2"]
@@ -303,10 +312,10 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
         Ly = sv["Ly"]
         Myl = B * Ly
         # norm3 / FFN
+        # LayerNorm backward also emits the dropout-masked bf16 branch gradient and its column sums (bias grad)
         r.layernorm_bwd(dOut, sv["z3"], eng.mp(sga.norm3.norm.weight), sv["mean3"], sv["rstd3"], dZ,
-                        eng.gp(sga.norm3.norm.weight), eng.gp(sga.norm3.norm.bias), M, D)
-        r.dropout_cast(dZ, g_bf, M, D, p_sga, sv["sid_r3"], rng)
-        r.colsum_bf16(g_bf, D, eng.gp(mlp.fc2.bias), M, D)
+                        eng.gp(sga.norm3.norm.weight), eng.gp(sga.norm3.norm.bias), M, D,
+                        g_bf, p_sga, sv["sid_r3"], rng, eng.gp(mlp.fc2.bias))
         r.wgrad(g_bf, M, D, D, sv["hm"], D, D, eng.gp(mlp.fc2.weight))
         r.dgrad(g_bf, M, D, D, eng.sp(mlp.fc2.weight), D, dpre, D, relu_mask=sv["hm"], ldm=D, drop_p=p_sga,
                 sid=sv["sid_h"], rng=rng)
@@ -315,9 +324,8 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
         r.dgrad(dpre, M, D, D, eng.sp(mlp.fc1.weight), D, dX, D, out_fp32=1, residual=dZ, ldr=D, res_fp32=1)
         # norm2 / mhatt2
         r.layernorm_bwd(dX, sv["z2"], eng.mp(sga.norm2.norm.weight), sv["mean2"], sv["rstd2"], dZ,
-                        eng.gp(sga.norm2.norm.weight), eng.gp(sga.norm2.norm.bias), M, D)
-        r.dropout_cast(dZ, g_bf, M, D, p_sga, sv["sid_r2"], rng)
-        r.colsum_bf16(g_bf, D, eng.gp(m2.linear_merge.bias), M, D)
+                        eng.gp(sga.norm2.norm.weight), eng.gp(sga.norm2.norm.bias), M, D,
+                        g_bf, p_sga, sv["sid_r2"], rng, eng.gp(m2.linear_merge.bias))
         r.wgrad(g_bf, M, D, D, sv["ctx2"], D, D, eng.gp(m2.linear_merge.weight))
         r.dgrad(g_bf, M, D, D, eng.sp(m2.linear_merge.weight), D, dsm, D)
         vk = sv["vk2"]
@@ -336,9 +344,8 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
             r.dgrad(dvk, Myl, 2 * D, 2 * D, eng.sp(m2.linear_v.weight), D, dy0, D)
         # norm1 / mhatt1
         r.layernorm_bwd(dX, sv["z1"], eng.mp(sga.norm1.norm.weight), sv["mean1"], sv["rstd1"], dZ,
-                        eng.gp(sga.norm1.norm.weight), eng.gp(sga.norm1.norm.bias), M, D)
-        r.dropout_cast(dZ, g_bf, M, D, p_sga, sv["sid_r1"], rng)
-        r.colsum_bf16(g_bf, D, eng.gp(m1.linear_merge.bias), M, D)
+                        eng.gp(sga.norm1.norm.weight), eng.gp(sga.norm1.norm.bias), M, D,
+                        g_bf, p_sga, sv["sid_r1"], rng, eng.gp(m1.linear_merge.bias))
         r.wgrad(g_bf, M, D, D, sv["ctx1"], D, D, eng.gp(m1.linear_merge.weight))
         r.dgrad(g_bf, M, D, D, eng.sp(m1.linear_merge.weight), D, dsm, D)
         q1 = sv["qkv1"]
@@ -371,8 +378,10 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     # ---- T5 encoder backward, a few blocks per segment ----
     bp = new_segment()
     r = eng.rec(bp)
+    # every RMSNorm backward also writes the dropout-masked bf16 gradient the NEXT residual branch consumes
     r.rmsnorm_bwd(dText, 1, hid[nblk], eng.mp(t5.final_layer_norm.weight), rstd_f, None, dH,
-                  eng.gp(t5.final_layer_norm.weight), M, D, p_t5, sid_final, rng)
+                  eng.gp(t5.final_layer_norm.weight), M, D, p_t5, sid_final, rng,
+                  g_bf, p_t5, saved_t5[nblk - 1]["sid_f"])
     blocks_per_seg = 3
     seg_lo = o[id(blk_last)]
     for bi in reversed(range(nblk)):
@@ -380,16 +389,14 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
         att, ff = blk.layer[0], blk.layer[1]
         sa, dd = att.SelfAttention, ff.DenseReluDense
         # FFN sub-layer
-        r.dropout_cast(dH, g_bf, M, D, p_t5, sv["sid_f"], rng)
         r.wgrad(g_bf, M, D, D, sv["h"], dff, dff, eng.gp(dd.wo.weight))
         r.dgrad(g_bf, M, D, D, eng.sp(dd.wo.weight), dff, dpre, dff, relu_mask=sv["h"], ldm=dff, drop_p=p_t5,
                 sid=sv["sid_h"], rng=rng)
         r.wgrad(dpre, M, dff, dff, sv["y2"], D, D, eng.gp(dd.wi.weight))
         r.dgrad(dpre, M, dff, dff, eng.sp(dd.wi.weight), D, dsm, D)
         r.rmsnorm_bwd(dsm, 0, sv["hmid"], eng.mp(ff.layer_norm.weight), sv["rstd2"], dH, dH,
-                      eng.gp(ff.layer_norm.weight), M, D, 0.0, 0, None)
+                      eng.gp(ff.layer_norm.weight), M, D, 0.0, 0, rng, g_bf, p_t5, sv["sid_o"])
         # self-attention sub-layer
-        r.dropout_cast(dH, g_bf, M, D, p_t5, sv["sid_o"], rng)
         r.wgrad(g_bf, M, D, D, sv["ctx"], inner, inner, eng.gp(sa.o.weight))
         r.dgrad(g_bf, M, D, D, eng.sp(sa.o.weight), inner, dsm, inner)
         qkv = sv["qkv"]
@@ -400,7 +407,8 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
         r.wgrad(dqkv, M, 3 * inner, 3 * inner, sv["y1"], D, D, eng.gp(sa.q.weight))
         r.dgrad(dqkv, M, 3 * inner, 3 * inner, eng.sp(sa.q.weight), D, dsm, D)
         r.rmsnorm_bwd(dsm, 0, hid[bi], eng.mp(att.layer_norm.weight), sv["rstd1"], dH, dH,
-                      eng.gp(att.layer_norm.weight), M, D, 0.0, 0, None)
+                      eng.gp(att.layer_norm.weight), M, D, 0.0, 0, rng,
+                      g_bf if bi > 0 else None, p_t5, saved_t5[bi - 1]["sid_f"] if bi > 0 else 0)
         if bi > 0 and (nblk - bi) % blocks_per_seg == 0:
             hi = o[id(blocks[bi - 1].layer[0].SelfAttention.q.weight)]
             close_segment(bp, seg_lo, hi)

@@ -191,13 +191,18 @@ def test_rmsnorm_fwd_bwd(C, M):
     C.rmsnorm_fwd(x.detach(), w.detach(), yb, yf, rstd, M, D, 1e-6, 0.0, 0, None)
     assert rel_fro(yf, y.detach()) < 1e-5 and rel_fro(yb, y.detach()) < 4e-3
     dx, dw = torch.empty(M, D, device="cuda"), torch.zeros(D, device="cuda")
-    C.rmsnorm_bwd(dy, 1, x.detach(), w.detach(), rstd, dres, dx, dw, M, D, 0.0, 0, None)
+    C.rmsnorm_bwd(dy, 1, x.detach(), w.detach(), rstd, dres, dx, dw, M, D, 0.0, 0, None, None, 0.0, 0)
     assert rel_fro(dx, x.grad + dres) < 1e-5 and rel_fro(dw, w.grad) < 1e-5
     # bf16 upstream gradient, in-place residual accumulation (dx aliases dres)
     dyb = dy.to(BF)
     acc = dres.clone()
     dw.zero_()
-    C.rmsnorm_bwd(dyb, 0, x.detach(), w.detach(), rstd, acc, acc, dw, M, D, 0.0, 0, None)
+    gb = torch.empty(M, D, dtype=BF, device="cuda")
+    rng = rng_state()
+    C.rmsnorm_bwd(dyb, 0, x.detach(), w.detach(), rstd, acc, acc, dw, M, D, 0.0, 0, rng, gb, 0.1, 5)
+    gb2 = torch.empty_like(gb)
+    C.dropout_cast(acc, gb2, M, D, 0.1, 5, rng)          # fused masked copy == separate dropout_cast of dx
+    assert torch.equal(gb, gb2)
     x.grad = None
     w.grad = None
     y2 = w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6))
@@ -219,7 +224,12 @@ def test_layernorm_fwd_bwd(C, M):
     C.layernorm_fwd(z.detach(), g.detach(), b.detach(), yb, yf, mean, rstd, M, D, 1e-5)
     assert rel_fro(yf, y.detach()) < 1e-5 and rel_fro(yb, y.detach()) < 4e-3
     dz, dg, db = torch.empty(M, D, device="cuda"), torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
-    C.layernorm_bwd(dy, z.detach(), g.detach(), mean, rstd, dz, dg, db, M, D)
+    gb, gcs = torch.empty(M, D, dtype=BF, device="cuda"), torch.zeros(D, device="cuda")
+    rng = rng_state()
+    C.layernorm_bwd(dy, z.detach(), g.detach(), mean, rstd, dz, dg, db, M, D, gb, 0.1, 9, rng, gcs)
+    gb2 = torch.empty_like(gb)
+    C.dropout_cast(dz, gb2, M, D, 0.1, 9, rng)
+    assert torch.equal(gb, gb2) and rel_fro(gcs, gb2.float().sum(0)) < 2e-3
     assert rel_fro(dz, z.grad) < 1e-5 and rel_fro(dg, g.grad) < 1e-5 and rel_fro(db, b.grad) < 1e-5
 
 
