@@ -52,6 +52,11 @@ int vqa_plan_capture_graph(void* plan, void* stream);/* capture the recorded lau
 int vqa_plan_set_lane(void* plan, int lane);
 int vqa_plan_fork(void* plan);
 int vqa_plan_join(void* plan);
+/* Finer ordering than a full join: vqa_plan_mark returns an id (>= 0) for lane 1's current position;
+ * vqa_plan_wait makes lane 0 wait until lane 1 has passed that position (used before lane 0 overwrites a
+ * buffer an earlier lane-1 launch reads). */
+int vqa_plan_mark(void* plan);
+int vqa_plan_wait(void* plan, int mark);
 /* measurement aid: eager replay with a CUDA event between launches; ms_out[vqa_plan_size] device durations
  * (synchronises the stream).  op_info: kernel family and the algorithmic flops / HBM bytes of launch i. */
 int vqa_plan_profile(void* plan, void* stream, float* ms_out, int spin_us);
@@ -208,6 +213,9 @@ int vqa_logsoftmax_nll_bwd(void* plan, const float* logp, const long long* label
 /* ---- optimizer step (trainer/faster_rcnn_vqa_trainer.py:399-404) -------------------------------- */
 /* out[0] += sum x^2 */
 int vqa_sumsq_f32(void* plan, const float* x, long long n, float* out, void* stream);
+/* torch.nn.utils.clip_grad_norm_'s scaling (trainer/faster_rcnn_vqa_trainer.py:399-400) over a contiguous fp32
+ * gradient range: g *= max_norm / (sqrt(gnorm_sq) + 1e-6) when that factor is < 1, untouched otherwise. */
+int vqa_clip_scale_f32(void* plan, float* g, long long n, const float* gnorm_sq, float max_norm, void* stream);
 /* torch.optim.AdamW(amsgrad) on a contiguous fp32 range (torch/optim/adamw.py single-tensor math:
  * p *= 1-lr*wd; m = lerp(m,g,1-b1); v = b2*v + (1-b2)*g*g; vmax = max(vmax,v);
  * p -= (lr/bc1) * m / (sqrt(vmax)/sqrt(bc2) + eps)); scalar combinations are formed in double on the host.

@@ -28,7 +28,7 @@ struct OpNote {
 // explicit fork (lane 1 waits for lane 0's position) and join (lane 0 waits for lane 1) markers.  Independent
 // chains - the frozen backbone next to the T5 encoder, weight gradients next to the data-gradient chain - then
 // overlap on the GPU; in a captured graph they become parallel branches.
-enum : int { PLAN_LAUNCH = 0, PLAN_FORK = 1, PLAN_JOIN = 2 };
+enum : int { PLAN_LAUNCH = 0, PLAN_FORK = 1, PLAN_JOIN = 2, PLAN_MARK = 3, PLAN_WAIT = 4 };
 struct Plan {
   std::vector<std::function<int(cudaStream_t)>> ops;   // launches only (notes[i] describes ops[i])
   std::vector<OpNote> notes;
@@ -39,6 +39,7 @@ struct Plan {
   bool lane1_open = false;                              // lane 1 has work not yet joined
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<cudaEvent_t> marks;                       // lane-1 positions lane 0 may wait for (PLAN_MARK / PLAN_WAIT)
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
 };

@@ -103,6 +103,24 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
 }
 
+// clip_grad_norm_'s in-place scaling: g *= min(1, max_norm / (||g|| + 1e-6)).  When the norm is already below
+// max_norm the factor clamps to exactly 1 (torch multiplies by 1.0 there), so the pass is skipped.
+__global__ void __launch_bounds__(256)
+clip_scale_kernel(float* __restrict__ g, long long n, const float* __restrict__ gnorm_sq, float max_norm) {
+  pdl_grid_sync();
+  const float norm = __fsqrt_rn(gnorm_sq[0]);
+  const float clip = __fdiv_rn(max_norm, norm + 1e-6f);
+  if (!(clip < 1.f)) return;
+  const long long nvec = n >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float4 v = reinterpret_cast<float4*>(g)[i];
+    v.x *= clip; v.y *= clip; v.z *= clip; v.w *= clip;
+    reinterpret_cast<float4*>(g)[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) g[(nvec << 2) + threadIdx.x] *= clip;
+}
+
 __global__ void rng_advance_kernel(unsigned long long* rng) {
   pdl_grid_sync(); rng[1] += 1ull; }
 
@@ -122,6 +140,16 @@ int vqa_sumsq_f32(void* plan, const float* x, long long n, float* out, void* str
   return submit(plan, stream, [=](cudaStream_t s) {
     launch_pdl(sumsq_kernel, dim3(stream_grid((n >> 2) + 4, 256)), dim3(256), 0, s, x, n, out);
     return launch_status("sumsq");
+  });
+}
+
+int vqa_clip_scale_f32(void* plan, float* g, long long n, const float* gnorm_sq, float max_norm, void* stream) {
+  if (reinterpret_cast<uintptr_t>(g) & 15) { set_last_error("clip_scale: pointer must be 16-byte aligned"); return -1; }
+  if (gnorm_sq == nullptr) { set_last_error("clip_scale: needs the squared gradient norm"); return -1; }
+  note_op("clip_scale", 0.0, 8.0 * static_cast<double>(n));
+  return submit(plan, stream, [=](cudaStream_t s) {
+    launch_pdl(clip_scale_kernel, dim3(stream_grid((n >> 2) + 4, 256)), dim3(256), 0, s, g, n, gnorm_sq, max_norm);
+    return launch_status("clip_scale");
   });
 }
 

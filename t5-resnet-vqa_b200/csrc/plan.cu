@@ -16,6 +16,7 @@ int vqa_plan_destroy(void* plan) {
   if (p->graph) cudaGraphDestroy(p->graph);
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   if (p->ev_join) cudaEventDestroy(p->ev_join);
+  for (cudaEvent_t e : p->marks) if (e) cudaEventDestroy(e);
   if (p->side) cudaStreamDestroy(p->side);
   delete p;
   return 0;
@@ -46,6 +47,23 @@ int vqa_plan_join(void* plan) {
   return 0;
 }
 
+int vqa_plan_mark(void* plan) {
+  if (plan == nullptr) return -1;
+  Plan* p = static_cast<Plan*>(plan);
+  p->marks.push_back(nullptr);
+  const int id = static_cast<int>(p->marks.size()) - 1;
+  p->steps.push_back({PLAN_MARK, id});
+  return id;
+}
+
+int vqa_plan_wait(void* plan, int mark) {
+  if (plan == nullptr) return -1;
+  Plan* p = static_cast<Plan*>(plan);
+  if (mark < 0 || mark >= static_cast<int>(p->marks.size())) { set_last_error("plan_wait: unknown mark %d", mark); return -1; }
+  p->steps.push_back({PLAN_WAIT, mark});
+  return 0;
+}
+
 static int ensure_side(Plan* p) {
   if (p->side != nullptr) return 0;
   cudaError_t e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
@@ -58,6 +76,7 @@ static int ensure_side(Plan* p) {
 static int replay(Plan* p, cudaStream_t s) {
   bool forked = false;   // lane 1 has been ordered after lane 0 at least once in this replay
   bool open = false;     // lane 1 holds work lane 0 has not waited for
+  std::vector<char> marked(p->marks.size(), 0);   // marks recorded during THIS replay
   for (const Plan::Step& st : p->steps) {
     if (st.kind == PLAN_LAUNCH) {
       cudaStream_t target = s;
@@ -80,6 +99,17 @@ static int replay(Plan* p, cudaStream_t s) {
       cudaEventRecord(p->ev_fork, s);
       cudaStreamWaitEvent(p->side, p->ev_fork, 0);
       forked = true;
+    } else if (st.kind == PLAN_MARK) {
+      if (!forked) continue;   // lane 1 has done nothing yet: nothing to wait for
+      if (p->marks[st.op] == nullptr &&
+          cudaEventCreateWithFlags(&p->marks[st.op], cudaEventDisableTiming) != cudaSuccess) {
+        set_last_error("plan mark: cannot create event");
+        return -1;
+      }
+      cudaEventRecord(p->marks[st.op], p->side);
+      marked[st.op] = 1;
+    } else if (st.kind == PLAN_WAIT) {
+      if (marked[st.op]) cudaStreamWaitEvent(s, p->marks[st.op], 0);
     } else if (open) {  // PLAN_JOIN
       cudaEventRecord(p->ev_join, p->side);
       cudaStreamWaitEvent(s, p->ev_join, 0);

@@ -71,6 +71,19 @@ class _Rec:
         if self.plan is not None:
             L.check(self.lib.vqa_plan_join(self.plan), "plan_join")
 
+    def mark(self):
+        """Id of lane 1's current position (None when launches run immediately)."""
+        if self.plan is None:
+            return None
+        mid = self.lib.vqa_plan_mark(self.plan)
+        if mid < 0:
+            raise RuntimeError("vqa_plan_mark failed")
+        return mid
+
+    def wait(self, mid):
+        if self.plan is not None and mid is not None:
+            L.check(self.lib.vqa_plan_wait(self.plan, mid), "plan_wait")
+
     # ---- contractions ----
     def gemm(self, M, N, K, A, lda, a_mn, B, ldb, b_mn, out, ldo, out_fp32, bias=None, relu=0, relu_mask=None,
              ldm=0, drop_p=0.0, sid=0, rng=None, residual=None, ldr=0, res_fp32=1, alpha=1.0, accumulate=0,
@@ -202,6 +215,9 @@ class Engine:
         self.shadow_fresh = False
         self.proj_dirty = True
         self._ddp = None
+        self.fused_opt = None       # weakref to a VQAFusedAdamW that updates every parameter of this engine
+        self.pending_clip = None    # max_norm of a clip_grad_norm_ whose scaling the fused optimizer will apply
+        self.clip_sumsq = None      # device scalar: sum of squared gradients of the last clip_grad_norm_
 
     # ------------------------------------------------------------------------------------------
     # flat parameter layout
@@ -415,6 +431,7 @@ class Engine:
             st.glogp.copy_(glogp)
         elif st.glogp_used:
             st.glogp.zero_()
+        self.pending_clip = None
         if self._ddp is not None:
             self._ddp.backward(self, st)
         else:

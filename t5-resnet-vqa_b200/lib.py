@@ -64,6 +64,8 @@ SIGNATURES = {
     "vqa_plan_set_lane": (c_int, [_P, c_int]),
     "vqa_plan_fork": (c_int, [_P]),
     "vqa_plan_join": (c_int, [_P]),
+    "vqa_plan_mark": (c_int, [_P]),
+    "vqa_plan_wait": (c_int, [_P, c_int]),
     "vqa_plan_profile": (c_int, [_P, _P, _P, c_int]),
     "vqa_plan_op_info": (c_int, [_P, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_d),
                                  ctypes.POINTER(c_d)]),
@@ -97,6 +99,7 @@ SIGNATURES = {
     "vqa_logsoftmax_nll_fwd": (c_int, [_P, _P, c_ll, _P, _P, _P, c_int, c_int, _P]),
     "vqa_logsoftmax_nll_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_ll, c_int, c_int, _P]),
     "vqa_sumsq_f32": (c_int, [_P, _P, c_ll, _P, _P]),
+    "vqa_clip_scale_f32": (c_int, [_P, _P, c_ll, _P, c_f, _P]),
     "vqa_adamw_amsgrad": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_ll, c_d, c_d, c_d, c_d, c_d, c_d, c_d, _P, c_f,
                                   c_int, _P]),
     "vqa_rng_advance": (c_int, [_P, _P, _P]),

@@ -10,6 +10,8 @@ Parameters that live in an Engine's flat fp32 buffer are updated range-by-range:
 are merged into a single launch that also refreshes the bf16 shadow the GEMMs read.
 """
 import ctypes
+import os
+import weakref
 
 import torch
 
@@ -61,6 +63,7 @@ class VQAFusedAdamW(torch.optim.Optimizer):
                 cur = dict(group=gi, p0=pp, g0=gp, p_end=pp + 4 * n, g_end=gp + 4 * n, params=[(p, 0)],
                            dev=p.device)
                 ranges.append(cur)
+        covered = {}
         for r in ranges:
             n = (r["p_end"] - r["p0"]) // 4
             r["n"] = n
@@ -86,6 +89,7 @@ class VQAFusedAdamW(torch.optim.Optimizer):
             r["shadow"] = None
             if eng is not None:
                 r["shadow"] = eng.shadow.data_ptr() + (r["p0"] - eng.master.data_ptr()) // 2
+                covered[eng] = covered.get(eng, 0) + len(r["params"])
         # per-group step counters: every state entry of a group references the same tensor
         group_step = {}
         for r in ranges:
@@ -97,6 +101,10 @@ class VQAFusedAdamW(torch.optim.Optimizer):
             for p, _ in r["params"]:
                 self.state[p]["step"] = group_step[gi]
         self._ranges = ranges
+        # an engine all of whose parameters this optimizer updates may fold clip_grad_norm_'s scaling into the
+        # AdamW pass (see clip_grad_norm_ below)
+        for eng, k in covered.items():
+            eng.fused_opt = weakref.ref(self) if k == len(eng.params) else None
 
     def _signature(self):
         sig = []
@@ -140,20 +148,78 @@ class VQAFusedAdamW(torch.optim.Optimizer):
             t = steps[gi]
             b1, b2 = group["betas"]
             s = ctypes.c_void_p(torch.cuda.current_stream(r["dev"]).cuda_stream)
+            r_gnorm, r_max = gnorm_ptr, self.max_grad_norm
+            eng = r["engine"]
+            if eng is not None and eng.pending_clip is not None:   # clip_grad_norm_ deferred its scaling to us
+                r_gnorm, r_max = eng.clip_sumsq.data_ptr(), eng.pending_clip
             L.check(lib.vqa_adamw_amsgrad(
                 None, r["p0"], r["g0"], r["m"].data_ptr(), r["v"].data_ptr(),
                 r["vmax"].data_ptr() if r["vmax"] is not None else None, r["shadow"], r["n"],
                 float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                1.0 - b1 ** t, 1.0 - b2 ** t, gnorm_ptr,
-                float(self.max_grad_norm) if self.max_grad_norm is not None else 0.0,
+                1.0 - b1 ** t, 1.0 - b2 ** t, r_gnorm,
+                float(r_max) if r_max is not None else 0.0,
                 int(bool(group["amsgrad"])), s), "adamw")
             if r["engine"] is not None:
                 engines[r["engine"]] = engines.get(r["engine"], 0) + len(r["params"])
         for eng, covered in engines.items():
             eng.note_fused_update(covered)
+            eng.pending_clip = None
         return loss
 
 
+_torch_clip_grad_norm_ = torch.nn.utils.clip_grad_norm_
+
+
+def _engine_holding_all_grads(params):
+    """The Engine whose flat gradient buffer holds EVERY gradient in `params` (and nothing else), or None."""
+    eng, n = None, 0
+    for p in params:
+        g = p.grad
+        if g is None:
+            continue
+        if eng is None:
+            eng = engine_for_ptr(p.data_ptr()) if p.is_cuda else None
+            if eng is None:
+                return None
+        if g.dtype != torch.float32 or g.data_ptr() - eng.grad.data_ptr() != p.data_ptr() - eng.master.data_ptr():
+            return None
+        n += 1
+    return eng if eng is not None and n == len(eng.params) else None
+
+
+def clip_grad_norm_(parameters, max_norm, norm_type=2.0, error_if_nonfinite=False, foreach=None):
+    """torch.nn.utils.clip_grad_norm_ (called by trainer/faster_rcnn_vqa_trainer.py:399-400) for models whose
+    gradients live in an Engine's flat buffer: one sum-of-squares pass over the buffer instead of a multi-tensor
+    norm, and the scaling pass runs only when the norm exceeds max_norm.  When a VQAFusedAdamW instance updates
+    all of the engine's parameters the scaling is folded into its update pass (VQA_B200_DEFER_CLIP=0 keeps the
+    in-place scaling; `.grad` then holds the clipped values as with torch).  Everything else goes to torch."""
+    if isinstance(parameters, torch.Tensor):
+        parameters = [parameters]
+    params = list(parameters)
+    eng = None
+    if float(norm_type) == 2.0 and not error_if_nonfinite:
+        eng = _engine_holding_all_grads(params)
+    if eng is None:
+        return _torch_clip_grad_norm_(params, max_norm, norm_type, error_if_nonfinite, foreach)
+    lib = L.load()
+    dev = eng.device
+    if eng.clip_sumsq is None or eng.clip_sumsq.device != dev:
+        eng.clip_sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+    sq = eng.clip_sumsq
+    s = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    sq.zero_()
+    L.check(lib.vqa_sumsq_f32(None, eng.grad.data_ptr(), eng.total, sq.data_ptr(), s), "sumsq")
+    opt = eng.fused_opt() if eng.fused_opt is not None else None
+    if opt is not None and os.environ.get("VQA_B200_DEFER_CLIP", "1") != "0":
+        eng.pending_clip = float(max_norm)
+    else:
+        L.check(lib.vqa_clip_scale_f32(None, eng.grad.data_ptr(), eng.total, sq.data_ptr(), float(max_norm), s),
+                "clip_scale")
+    return sq.sqrt().reshape(())
+
+
 def register():
-    """Expose the optimizer where the reference trainer looks it up: getattr(torch.optim, "<type>")."""
+    """Expose the optimizer where the reference trainer looks it up: getattr(torch.optim, "<type>"), and route
+    torch.nn.utils.clip_grad_norm_ (looked up at call time by the trainer) through the flat-buffer fast path."""
     torch.optim.VQAFusedAdamW = VQAFusedAdamW
+    torch.nn.utils.clip_grad_norm_ = clip_grad_norm_

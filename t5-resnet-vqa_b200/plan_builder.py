@@ -275,7 +275,8 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
 
     o = eng.offs
     # scratch shared by all layers
-    g_bf = al(M, D)            # dropout-masked residual-branch gradient (bf16 GEMM operand)
+    g_pair = [al(M, D), al(M, D)]  # dropout-masked residual-branch gradient (bf16 GEMM operand), ping-pong
+    g_idx = [0]
     dpre = al(M, max(dff, D))  # gradient before ReLU
     dsm = al(M, D)             # small bf16 [M,768] gradients (dy of a norm, dctx)
     dqkv = al(M, 3 * D)
@@ -291,16 +292,55 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     dbias_pos = al(nH, Lt, Lt, dtype=f32)
     proj_dw = al(D, 9 * Cf, dtype=f32)
 
-    # ---- segment 0: head + SGA + projection ----
+    def next_g():
+        g_idx[0] ^= 1
+        return g_pair[g_idx[0]]
+
+    # Weight / bias gradients are leaves of the backward graph: they go to lane 1 and overlap the data-gradient
+    # chain on lane 0.  `side.leaf(reads, fn)` orders lane 1 after the producer of its operands and remembers a
+    # mark; `side.before_write(buf)` makes lane 0 wait for that mark before it overwrites a scratch buffer a leaf
+    # still reads (rarely a real stall: the scratch buffers are reused several launches later).
+    class _Side:
+        def __init__(self, enabled):
+            self.enabled, self.r, self.pending = enabled, None, {}
+
+        def bind(self, rec):
+            self.r, self.pending = rec, {}
+
+        def leaf(self, reads, fn):
+            if not self.enabled:
+                fn()
+                return
+            self.r.fork()
+            self.r.lane(1)
+            fn()
+            mid = self.r.mark()
+            self.r.lane(0)
+            for t in reads:
+                self.pending[t.data_ptr()] = mid
+
+        def before_write(self, *bufs):
+            for t in bufs:
+                mid = self.pending.pop(t.data_ptr(), None)
+                if mid is not None:
+                    self.r.wait(mid)
+
+    side = _Side(two_lanes)
+
+    # ---- segment 0: head + SGA ----
     bp = new_segment()
     r = eng.rec(bp)
+    side.bind(r)
     n_small = eng.total - eng.n_big
     r.memset_zero(eng.grad.data_ptr() + 4 * eng.n_big, 4 * n_small)
     r.memset_zero(dbias_pos, 4 * nH * Lt * Lt)
     r.logsoftmax_nll_bwd(st.logp, st.labels if has_labels else None, st.gloss, st.glogp, dlogits, Apad, B, A)
     st.glogp_used = True
-    r.colsum_bf16(dlogits, Apad, eng.gp(cls.bias), B, A)
-    r.wgrad(dlogits, B, A, Apad, pooled_b, D, D, eng.gp(cls.weight), bn=64)
+
+    def head_leaf():
+        r.colsum_bf16(dlogits, Apad, eng.gp(cls.bias), B, A)
+        r.wgrad(dlogits, B, A, Apad, pooled_b, D, D, eng.gp(cls.weight), bn=64)
+    side.leaf([dlogits], head_leaf)
     r.dgrad(dlogits, B, A, Apad, eng.sp(cls.weight), D, dpooled, D, out_fp32=1, bn=64)
     dOut = dY[0]
     r.pooler_bwd(out_f32, eng.mp(pl.weight), pool_w, dpooled, dOut, eng.gp(pl.weight), eng.gp(pl.bias), B, Lt, D)
@@ -313,28 +353,40 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
         Myl = B * Ly
         # norm3 / FFN
         # LayerNorm backward also emits the dropout-masked bf16 branch gradient and its column sums (bias grad)
+        g_bf = next_g()
+        side.before_write(g_bf)
         r.layernorm_bwd(dOut, sv["z3"], eng.mp(sga.norm3.norm.weight), sv["mean3"], sv["rstd3"], dZ,
                         eng.gp(sga.norm3.norm.weight), eng.gp(sga.norm3.norm.bias), M, D,
                         g_bf, p_sga, sv["sid_r3"], rng, eng.gp(mlp.fc2.bias))
-        r.wgrad(g_bf, M, D, D, sv["hm"], D, D, eng.gp(mlp.fc2.weight))
+        side.leaf([g_bf], lambda: r.wgrad(g_bf, M, D, D, sv["hm"], D, D, eng.gp(mlp.fc2.weight)))
+        side.before_write(dpre)
         r.dgrad(g_bf, M, D, D, eng.sp(mlp.fc2.weight), D, dpre, D, relu_mask=sv["hm"], ldm=D, drop_p=p_sga,
                 sid=sv["sid_h"], rng=rng)
-        r.colsum_bf16(dpre, D, eng.gp(mlp.fc1.bias), M, D)
-        r.wgrad(dpre, M, D, D, sv["x2b"], D, D, eng.gp(mlp.fc1.weight))
+
+        def fc1_leaf():
+            r.colsum_bf16(dpre, D, eng.gp(mlp.fc1.bias), M, D)
+            r.wgrad(dpre, M, D, D, sv["x2b"], D, D, eng.gp(mlp.fc1.weight))
+        side.leaf([dpre], fc1_leaf)
         r.dgrad(dpre, M, D, D, eng.sp(mlp.fc1.weight), D, dX, D, out_fp32=1, residual=dZ, ldr=D, res_fp32=1)
         # norm2 / mhatt2
+        g_bf = next_g()
+        side.before_write(g_bf)
         r.layernorm_bwd(dX, sv["z2"], eng.mp(sga.norm2.norm.weight), sv["mean2"], sv["rstd2"], dZ,
                         eng.gp(sga.norm2.norm.weight), eng.gp(sga.norm2.norm.bias), M, D,
                         g_bf, p_sga, sv["sid_r2"], rng, eng.gp(m2.linear_merge.bias))
-        r.wgrad(g_bf, M, D, D, sv["ctx2"], D, D, eng.gp(m2.linear_merge.weight))
+        side.leaf([g_bf], lambda: r.wgrad(g_bf, M, D, D, sv["ctx2"], D, D, eng.gp(m2.linear_merge.weight)))
         r.dgrad(g_bf, M, D, D, eng.sp(m2.linear_merge.weight), D, dsm, D)
         vk = sv["vk2"]
+        side.before_write(dqkv, dvk)
         r.attn_bwd(B, Hs, Lt, Ly, hd, sv["q2"], D, vk.data_ptr() + 2 * D, 2 * D, vk, 2 * D, sv["probs2"], dsm, D,
                    dqkv, D, dvk.data_ptr() + 2 * D, 2 * D, dvk, 2 * D, None, scale, p_sga, sv["sid_p2"], rng)
-        r.colsum_bf16(dqkv, D, eng.gp(m2.linear_q.bias), M, D)
-        r.colsum_bf16(dvk, 2 * D, eng.gp(m2.linear_v.bias), Myl, 2 * D)
-        r.wgrad(dqkv, M, D, D, sv["x1b"], D, D, eng.gp(m2.linear_q.weight))
-        r.wgrad(dvk, Myl, 2 * D, 2 * D, sv["y"], D, D, eng.gp(m2.linear_v.weight))
+
+        def att2_leaf():
+            r.colsum_bf16(dqkv, D, eng.gp(m2.linear_q.bias), M, D)
+            r.colsum_bf16(dvk, 2 * D, eng.gp(m2.linear_v.bias), Myl, 2 * D)
+            r.wgrad(dqkv, M, D, D, sv["x1b"], D, D, eng.gp(m2.linear_q.weight))
+            r.wgrad(dvk, Myl, 2 * D, 2 * D, sv["y"], D, D, eng.gp(m2.linear_v.weight))
+        side.leaf([dqkv, dvk], att2_leaf)
         r.dgrad(dqkv, M, D, D, eng.sp(m2.linear_q.weight), D, dX, D, out_fp32=1, residual=dZ, ldr=D, res_fp32=1)
         if li > 0:
             dPrev = dY[1] if dOut is dY[0] else dY[0]
@@ -343,69 +395,85 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
             dPrev = None
             r.dgrad(dvk, Myl, 2 * D, 2 * D, eng.sp(m2.linear_v.weight), D, dy0, D)
         # norm1 / mhatt1
+        g_bf = next_g()
+        side.before_write(g_bf)
         r.layernorm_bwd(dX, sv["z1"], eng.mp(sga.norm1.norm.weight), sv["mean1"], sv["rstd1"], dZ,
                         eng.gp(sga.norm1.norm.weight), eng.gp(sga.norm1.norm.bias), M, D,
                         g_bf, p_sga, sv["sid_r1"], rng, eng.gp(m1.linear_merge.bias))
-        r.wgrad(g_bf, M, D, D, sv["ctx1"], D, D, eng.gp(m1.linear_merge.weight))
+        side.leaf([g_bf], lambda: r.wgrad(g_bf, M, D, D, sv["ctx1"], D, D, eng.gp(m1.linear_merge.weight)))
         r.dgrad(g_bf, M, D, D, eng.sp(m1.linear_merge.weight), D, dsm, D)
         q1 = sv["qkv1"]
+        side.before_write(dqkv)
         r.attn_bwd(B, Hs, Lt, Lt, hd, q1.data_ptr() + 4 * D, 3 * D, q1.data_ptr() + 2 * D, 3 * D, q1, 3 * D,
                    sv["probs1"], dsm, D, dqkv.data_ptr() + 4 * D, 3 * D, dqkv.data_ptr() + 2 * D, 3 * D, dqkv, 3 * D,
                    None, scale, p_sga, sv["sid_p1"], rng)
-        r.colsum_bf16(dqkv, 3 * D, eng.gp(m1.linear_v.bias), M, 3 * D)
-        r.wgrad(dqkv, M, 3 * D, 3 * D, text_bf16, D, D, eng.gp(m1.linear_v.weight))
+
+        def att1_leaf():
+            r.colsum_bf16(dqkv, 3 * D, eng.gp(m1.linear_v.bias), M, 3 * D)
+            r.wgrad(dqkv, M, 3 * D, 3 * D, text_bf16, D, D, eng.gp(m1.linear_v.weight))
+        side.leaf([dqkv], att1_leaf)
         # x is the T5 output for every layer: its gradient accumulates over the three layers
         r.dgrad(dqkv, M, 3 * D, 3 * D, eng.sp(m1.linear_v.weight), D, dText, D, out_fp32=1, residual=dZ, ldr=D,
                 res_fp32=1, accumulate=0 if first_text else 1)
         first_text = False
         dOut = dPrev
+    close_segment(bp, 0, o[id(proj.weight)])
 
-    # projection: bias grad + wgrad of the equivalent 3x3 conv, mapped back to the ConvTranspose2d layout
-    r.colsum_bf16(dy0, D, eng.gp(proj.bias), My, D)
-    wg_bn = 256 if Cf % 256 == 0 else (128 if Cf % 128 == 0 else 64)
-    n_kb = (My + 63) // 64
-    tiles = ((D + 127) // 128) * (9 * Cf // wg_bn)
-    split = 1
-    if tiles < 148 and n_kb >= 8:
-        split = min(4, max(1, 296 // max(tiles, 1)), n_kb // 4)
-    if split > 1:
-        r.memset_zero(proj_dw, 4 * D * 9 * Cf)
-    r.conv_wgrad(B, Hf, Wf, Cf, D, dy0, feat, proj_dw, wg_bn, split)
-    r.convT_wgrad_unprep(proj_dw, eng.gp(proj.weight), Cf, D)
-    blk_last = blocks[-1].layer[0].SelfAttention.q.weight
-    close_segment(bp, 0, o[id(blk_last)])
-
-    # ---- T5 encoder backward, a few blocks per segment ----
+    # ---- T5 encoder backward, a few blocks per segment; the projection's gradients ride on lane 1 ----
     bp = new_segment()
     r = eng.rec(bp)
+    side.bind(r)
+
+    def proj_leaf():
+        # bias grad + wgrad of the equivalent 3x3 conv, mapped back to the ConvTranspose2d layout
+        r.colsum_bf16(dy0, D, eng.gp(proj.bias), My, D)
+        wg_bn = 256 if Cf % 256 == 0 else (128 if Cf % 128 == 0 else 64)
+        n_kb = (My + 63) // 64
+        tiles = ((D + 127) // 128) * (9 * Cf // wg_bn)
+        split = 1
+        if tiles < 148 and n_kb >= 8:
+            split = min(4, max(1, 296 // max(tiles, 1)), n_kb // 4)
+        if split > 1:
+            r.memset_zero(proj_dw, 4 * D * 9 * Cf)
+        r.conv_wgrad(B, Hf, Wf, Cf, D, dy0, feat, proj_dw, wg_bn, split)
+        r.convT_wgrad_unprep(proj_dw, eng.gp(proj.weight), Cf, D)
+    side.leaf([dy0], proj_leaf)
     # every RMSNorm backward also writes the dropout-masked bf16 gradient the NEXT residual branch consumes
+    g_bf = next_g()
     r.rmsnorm_bwd(dText, 1, hid[nblk], eng.mp(t5.final_layer_norm.weight), rstd_f, None, dH,
                   eng.gp(t5.final_layer_norm.weight), M, D, p_t5, sid_final, rng,
                   g_bf, p_t5, saved_t5[nblk - 1]["sid_f"])
     blocks_per_seg = 3
-    seg_lo = o[id(blk_last)]
+    seg_lo = o[id(proj.weight)]
     for bi in reversed(range(nblk)):
         blk, sv = blocks[bi], saved_t5[bi]
         att, ff = blk.layer[0], blk.layer[1]
         sa, dd = att.SelfAttention, ff.DenseReluDense
         # FFN sub-layer
-        r.wgrad(g_bf, M, D, D, sv["h"], dff, dff, eng.gp(dd.wo.weight))
+        side.leaf([g_bf], lambda: r.wgrad(g_bf, M, D, D, sv["h"], dff, dff, eng.gp(dd.wo.weight)))
+        side.before_write(dpre)
         r.dgrad(g_bf, M, D, D, eng.sp(dd.wo.weight), dff, dpre, dff, relu_mask=sv["h"], ldm=dff, drop_p=p_t5,
                 sid=sv["sid_h"], rng=rng)
-        r.wgrad(dpre, M, dff, dff, sv["y2"], D, D, eng.gp(dd.wi.weight))
+        side.leaf([dpre], lambda: r.wgrad(dpre, M, dff, dff, sv["y2"], D, D, eng.gp(dd.wi.weight)))
         r.dgrad(dpre, M, dff, dff, eng.sp(dd.wi.weight), D, dsm, D)
+        g_bf = next_g()
+        side.before_write(g_bf)
         r.rmsnorm_bwd(dsm, 0, sv["hmid"], eng.mp(ff.layer_norm.weight), sv["rstd2"], dH, dH,
                       eng.gp(ff.layer_norm.weight), M, D, 0.0, 0, rng, g_bf, p_t5, sv["sid_o"])
         # self-attention sub-layer
-        r.wgrad(g_bf, M, D, D, sv["ctx"], inner, inner, eng.gp(sa.o.weight))
+        side.leaf([g_bf], lambda: r.wgrad(g_bf, M, D, D, sv["ctx"], inner, inner, eng.gp(sa.o.weight)))
         r.dgrad(g_bf, M, D, D, eng.sp(sa.o.weight), inner, dsm, inner)
         qkv = sv["qkv"]
+        side.before_write(dqkv)
         r.attn_bwd(B, nH, Lt, Lt, dkv, qkv, 3 * inner, qkv.data_ptr() + 2 * inner, 3 * inner,
                    qkv.data_ptr() + 4 * inner, 3 * inner, sv["probs"], dsm, inner,
                    dqkv, 3 * inner, dqkv.data_ptr() + 2 * inner, 3 * inner, dqkv.data_ptr() + 4 * inner, 3 * inner,
                    dbias_pos, 1.0, p_t5, sv["sid_p"], rng)
-        r.wgrad(dqkv, M, 3 * inner, 3 * inner, sv["y1"], D, D, eng.gp(sa.q.weight))
+        side.leaf([dqkv], lambda: r.wgrad(dqkv, M, 3 * inner, 3 * inner, sv["y1"], D, D, eng.gp(sa.q.weight)))
         r.dgrad(dqkv, M, 3 * inner, 3 * inner, eng.sp(sa.q.weight), D, dsm, D)
+        if bi > 0:
+            g_bf = next_g()
+            side.before_write(g_bf)
         r.rmsnorm_bwd(dsm, 0, hid[bi], eng.mp(att.layer_norm.weight), sv["rstd1"], dH, dH,
                       eng.gp(att.layer_norm.weight), M, D, 0.0, 0, rng,
                       g_bf if bi > 0 else None, p_t5, saved_t5[bi - 1]["sid_f"] if bi > 0 else 0)
@@ -415,6 +483,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
             seg_lo = hi
             bp = new_segment()
             r = eng.rec(bp)
+            side.bind(r)
     r.t5_bias_grad(dbias_pos, bucket, eng.gp(relw), nH, Lt, cfg["num_buckets"])
     r.embedding_bwd(st.ids, dH, eng.gp(t5.embed_tokens.weight), M, D, vocab, p_t5, sid_embed, rng)
     close_segment(bp, seg_lo, eng.total)
