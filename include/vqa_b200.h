@@ -168,6 +168,9 @@ typedef struct {
   const long long* key_mask;            /* int64 [B,Lk], 0 = masked key, or NULL (hf:323-325) */
   float scale;                          /* 1.0 (T5) or 1/sqrt(hd) (SGA) */
   float drop_p; uint32_t sid; const uint64_t* rng;
+  float* stats;                         /* fp32 [B,H,Lq,2] row max and 1/row-sum of the softmax.  Non-NULL with Lq, Lk <= 32
+                                           selects the tcgen05 flash kernel (probs is then not written); NULL or longer
+                                           sequences run the SIMT kernel, which saves probs instead */
 } vqa_attn_fwd_args;
 int vqa_attention_fwd(void* plan, const vqa_attn_fwd_args* a, void* stream);
 typedef struct {
@@ -177,6 +180,9 @@ typedef struct {
   void* dq; long long lddq; void* dk; long long lddk; void* dv; long long lddv;   /* bf16 */
   float* dbias;                         /* fp32 [H,Lq,Lk] accumulated atomically, or NULL */
   float scale; float drop_p; uint32_t sid; const uint64_t* rng;
+  const float* stats;                   /* forward's stats: backward recomputes the probabilities (probs unused) */
+  const float* bias;                    /* forward's bias / key_mask, needed for that recomputation */
+  const long long* key_mask;
 } vqa_attn_bwd_args;
 int vqa_attention_bwd(void* plan, const vqa_attn_bwd_args* a, void* stream);
 

@@ -14,6 +14,13 @@
 
 using namespace vqa;
 
+namespace vqa {
+// attention_tc.cu: tcgen05 flash kernels for Lq, Lk <= 32
+bool attention_tc_supported(int Lq, int Lk, int hd);
+int attention_tc_fwd(void* plan, const vqa_attn_fwd_args* x, void* stream);
+int attention_tc_bwd(void* plan, const vqa_attn_bwd_args* x, void* stream);
+}  // namespace vqa
+
 namespace {
 
 constexpr int kThreads = 128;
@@ -322,6 +329,7 @@ extern "C" {
 
 int vqa_attention_fwd(void* plan, const vqa_attn_fwd_args* x, void* stream) {
   if (check_common(x->Lq, x->Lk, x->hd, x->ldq, x->ldk, x->ldv, x->ldo, "attention_fwd")) return -1;
+  if (x->stats != nullptr && attention_tc_supported(x->Lq, x->Lk, x->hd)) return attention_tc_fwd(plan, x, stream);
   FwdArgs a;
   a.B = x->B; a.H = x->H; a.Lq = x->Lq; a.Lk = x->Lk;
   a.q = static_cast<const __nv_bfloat16*>(x->q); a.k = static_cast<const __nv_bfloat16*>(x->k);
@@ -346,6 +354,8 @@ int vqa_attention_fwd(void* plan, const vqa_attn_fwd_args* x, void* stream) {
 int vqa_attention_bwd(void* plan, const vqa_attn_bwd_args* x, void* stream) {
   if (check_common(x->Lq, x->Lk, x->hd, x->ldq, x->ldk, x->ldv, x->ldo, "attention_bwd")) return -1;
   if ((x->lddq | x->lddk | x->lddv) & 7) { set_last_error("attention_bwd: gradient strides must be multiples of 8"); return -1; }
+  if (x->stats != nullptr && attention_tc_supported(x->Lq, x->Lk, x->hd)) return attention_tc_bwd(plan, x, stream);
+  if (x->probs == nullptr) { set_last_error("attention_bwd: the SIMT kernel needs the saved probabilities"); return -1; }
   BwdArgs a;
   a.B = x->B; a.H = x->H; a.Lq = x->Lq; a.Lk = x->Lk;
   a.q = static_cast<const __nv_bfloat16*>(x->q); a.k = static_cast<const __nv_bfloat16*>(x->k);

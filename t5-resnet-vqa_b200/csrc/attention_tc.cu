@@ -1,0 +1,563 @@
+// Flash-style tcgen05 attention for short sequences (Lq, Lk <= 32): T5 self-attention (hf:308-334: no 1/sqrt(d),
+// relative-position bias, key-padding mask) and the SGA self / guided attention over the 32 text tokens
+// (model/multi_head_vision_text_attn.py:73-86: 1/sqrt(96) scale), forward and backward.
+//
+// One (batch, head) problem is only 32 x 32 x hd, far below one MMA, so a CTA packs FOUR (b, h) pairs into the
+// 128 rows of one tcgen05.mma: the packed Q [128 x hd] times the packed K^T [hd x 128] gives a 128 x 128 score tile
+// in TMEM whose four diagonal 32 x 32 blocks are the four problems (the off-diagonal blocks are never read; tensor
+// FLOPs are free at this size, launches and bytes are not).  Thread t owns TMEM lane t = one query row: it pulls its
+// 32 scores with one tcgen05.ld, does bias + mask + softmax + dropout entirely in registers (no shuffles), and writes
+// its probabilities as bf16 into a block-diagonal P tile in shared memory (canonical 128B-swizzled K-major layout,
+// off-diagonal blocks zero), which is the A operand of the second MMA  O = P V  (V is read MN-major, straight from
+// the TMA tile).  Scores / probabilities never touch HBM: forward saves only the row max and 1/row-sum, backward
+// recomputes S = Q K^T and P with one more MMA, then  dP = dO V^T,  dS = P (dP - rowsum(P dP)),
+// dV = Pd^T dO,  dQ = scale dS K,  dK = scale dS^T Q  as three more MMAs over the same shared-memory tiles
+// (transposes are free: the MN-major descriptor bit).
+// Operands arrive by TMA (2-D boxes of 64 columns x 32 rows per pair and 64-column chunk, 128B swizzle).
+#include "../../include/vqa_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+#include "rng.cuh"
+#include "tmap.cuh"
+
+using namespace vqa;
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kPairs = 4;                 // (batch, head) pairs per CTA
+constexpr int kSlot = 32;                 // query rows / keys per pair
+constexpr int kTile = 128 * 128;          // bytes of one 64-column chunk: 128 rows x 128 B
+constexpr int kBox = kSlot * 128;         // bytes one TMA box delivers (32 rows x 64 bf16)
+constexpr float kMaskedScore = -3.4028234663852886e38f;  // torch.finfo(float32).min (hf additive mask)
+
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t philox_u16(const Philox8& r, uint32_t e) {
+  const uint32_t lo = (e & 2u) ? r.w[1] : r.w[0];
+  const uint32_t hi = (e & 2u) ? r.w[3] : r.w[2];
+  const uint32_t w = (e & 4u) ? hi : lo;
+  return (w >> ((e & 1u) * 16u)) & 0xFFFFu;
+}
+
+// Bit j = probability j of the row starting at flat index `base` survives dropout.  Same stream convention as the
+// SIMT kernel (attention.cu: philox group = flat index / 8, 16-bit lane = flat index % 8).
+__device__ __forceinline__ uint32_t keep_bits(const DropCtx& dc, unsigned long long base, int Lk) {
+  if (!dc.on) return 0xFFFFFFFFu;
+  uint32_t keep = 0;
+  if ((Lk & 7) == 0) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g * 8 < Lk) {
+        const Philox8 r = philox8(dc.seed, dc.offset, dc.sid, (base >> 3) + g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) keep |= (r.u16(e) >= dc.thresh ? 1u : 0u) << (g * 8 + e);
+      }
+    }
+  } else {
+    unsigned long long cur = ~0ull;
+    Philox8 r;
+    r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0;
+#pragma unroll 1
+    for (int j = 0; j < Lk; ++j) {
+      const unsigned long long idx = base + j;
+      if ((idx >> 3) != cur) { cur = idx >> 3; r = philox8(dc.seed, dc.offset, dc.sid, cur); }
+      keep |= (philox_u16(r, static_cast<uint32_t>(idx & 7)) >= dc.thresh ? 1u : 0u) << j;
+    }
+  }
+  return keep;
+}
+
+// Write 32 fp32 values as bf16 into row `row` of a block-diagonal [128 x 128] K-major tile (two 64-column chunks of
+// 128 rows x 128 B, 128B swizzle): pair `g` owns columns 32g .. 32g+31.
+__device__ __forceinline__ void store_diag_row(uint8_t* tile, int row, int g, const float (&v)[32]) {
+  uint8_t* rowp = tile + (g >> 1) * kTile + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint4 u;
+    u.x = pack_bf16x2(v[8 * k + 0], v[8 * k + 1]);
+    u.y = pack_bf16x2(v[8 * k + 2], v[8 * k + 3]);
+    u.z = pack_bf16x2(v[8 * k + 4], v[8 * k + 5]);
+    u.w = pack_bf16x2(v[8 * k + 6], v[8 * k + 7]);
+    const int unit = ((g & 1) * 4 + k) ^ (row & 7);
+    *reinterpret_cast<uint4*>(rowp + unit * 16) = u;
+  }
+}
+
+// One TMEM row of NC fp32 columns -> bf16 -> global (16-byte stores)
+template <int NC>
+__device__ __forceinline__ void store_tmem_row(uint32_t taddr, __nv_bfloat16* dst, bool ok) {
+#pragma unroll
+  for (int c = 0; c < NC / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + c * 32, r);
+    tmem_ld_wait();
+    if (ok) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(r[8 * k + 0]), __uint_as_float(r[8 * k + 1]));
+        u.y = pack_bf16x2(__uint_as_float(r[8 * k + 2]), __uint_as_float(r[8 * k + 3]));
+        u.z = pack_bf16x2(__uint_as_float(r[8 * k + 4]), __uint_as_float(r[8 * k + 5]));
+        u.w = pack_bf16x2(__uint_as_float(r[8 * k + 6]), __uint_as_float(r[8 * k + 7]));
+        reinterpret_cast<uint4*>(dst + c * 32)[k] = u;
+      }
+    }
+  }
+}
+
+struct RowCtx {
+  int b, h, i;
+  bool pair_ok, row_ok;
+  long long prow;        // (b*H + h)*Lq + i
+  uint32_t in_range;     // bit j: key j < Lk
+  uint32_t visible;      // bit j: key j not masked by key_mask
+};
+
+__device__ __forceinline__ RowCtx row_ctx(int B, int H, int Lq, int Lk, const long long* key_mask) {
+  RowCtx c;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int npairs = B * H;
+  const int pr = blockIdx.x * kPairs + warp;
+  c.pair_ok = pr < npairs;
+  const int prc = c.pair_ok ? pr : npairs - 1;
+  c.b = prc / H;
+  c.h = prc - c.b * H;
+  c.i = lane;
+  c.row_ok = c.pair_ok && lane < Lq;
+  c.prow = (static_cast<long long>(c.b) * H + c.h) * Lq + lane;
+  c.in_range = Lk >= 32 ? 0xFFFFFFFFu : ((1u << Lk) - 1u);
+  bool vis = lane < Lk;
+  if (vis && key_mask != nullptr) vis = key_mask[static_cast<long long>(c.b) * Lk + lane] != 0;
+  c.visible = __ballot_sync(0xffffffffu, vis);
+  return c;
+}
+
+// scores of one row: acc * scale + bias, masked keys -> finfo.min, keys >= Lk left untouched (never used)
+__device__ __forceinline__ void finish_scores(float (&s)[32], const uint32_t (&acc)[32], const RowCtx& c, float scale,
+                                              const float* bias, int Lq, int Lk) {
+  const float* brow = bias != nullptr ? bias + (static_cast<long long>(c.h) * Lq + (c.i < Lq ? c.i : 0)) * Lk : nullptr;
+  const bool vec = brow != nullptr && (Lk & 3) == 0 && (reinterpret_cast<uintptr_t>(brow) & 15) == 0;
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4) {
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (brow != nullptr && q4 * 4 < Lk) {
+      if (vec) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(brow) + q4);
+        bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (q4 * 4 + e < Lk) bv[e] = __ldg(brow + q4 * 4 + e);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = q4 * 4 + e;
+      float v = __uint_as_float(acc[j]) * scale + bv[e];
+      if (!((c.visible >> j) & 1u)) v = kMaskedScore;
+      s[j] = v;
+    }
+  }
+}
+
+struct FwdP {
+  int B, H, Lq, Lk;
+  __nv_bfloat16* out; long long ldo;
+  float* stats;
+  const float* bias;
+  const long long* key_mask;
+  float scale, drop_p;
+  uint32_t sid;
+  const unsigned long long* rng;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kThreads)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const FwdP a) {
+  constexpr int CH = (HD + 63) / 64;   // 64-column chunks per operand row
+  constexpr int KS = HD / 16;          // UMMA k-steps over the head dim
+  constexpr uint32_t kCols = 256;      // TMEM: S [0,128), O [128, 128 + HD)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base, sK = sQ + CH * kTile, sV = sK + CH * kTile, sP = sV + CH * kTile;
+  const uint32_t bar_tma = sP + 2 * kTile, bar_mma = bar_tma + 8, slot = bar_mma + 8;
+  uint8_t* Pg = gen + 3 * CH * kTile;
+  const uint32_t* slot_ptr = reinterpret_cast<const uint32_t*>(gen + (3 * CH + 2) * kTile + 16);
+  const int t = threadIdx.x, warp = t >> 5;
+
+  pdl_launch_dependents();
+  if (t == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(bar_tma, 1);
+    mbar_init(bar_mma, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(slot, kCols);
+    tmem_relinquish();
+  }
+  for (int i = t; i < 2 * kTile / 16; i += kThreads) reinterpret_cast<uint4*>(Pg)[i] = make_uint4(0u, 0u, 0u, 0u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot_ptr;
+  pdl_wait();
+
+  const int npairs = a.B * a.H;
+  if (t == 0) {
+    mbar_expect_tx(bar_tma, 3u * CH * kPairs * kBox);
+    for (int g = 0; g < kPairs; ++g) {
+      int pr = blockIdx.x * kPairs + g;
+      if (pr >= npairs) pr = npairs - 1;      // duplicate the last pair: finite data, results discarded
+      const int b = pr / a.H, h = pr - b * a.H;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        tma_load_2d(sQ + c * kTile + g * kBox, &tmQ, bar_tma, h * HD + c * 64, b * a.Lq);
+        tma_load_2d(sK + c * kTile + g * kBox, &tmK, bar_tma, h * HD + c * 64, b * a.Lk);
+        tma_load_2d(sV + c * kTile + g * kBox, &tmV, bar_tma, h * HD + c * 64, b * a.Lk);
+      }
+    }
+    mbar_wait(bar_tma, 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, 128, false, false);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const uint32_t off = (ks >> 2) * kTile + (ks & 3) * 32;
+      umma_bf16(tmem, umma_smem_desc(sQ + off, 16u, 1024u), umma_smem_desc(sK + off, 16u, 1024u), idesc, ks ? 1u : 0u);
+    }
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+
+  const RowCtx rc = row_ctx(a.B, a.H, a.Lq, a.Lk, a.key_mask);
+  const DropCtx dc = drop_ctx(a.drop_p, a.sid, a.rng);
+  const uint32_t keep = keep_bits(dc, static_cast<unsigned long long>(rc.prow) * a.Lk, a.Lk);
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+  float p[32];
+  {
+    uint32_t acc[32];
+    tmem_ld_32x32(tmem + lane_base + warp * 32, acc);
+    tmem_ld_wait();
+    finish_scores(p, acc, rc, a.scale, a.bias, a.Lq, a.Lk);
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if ((rc.in_range >> j) & 1u) mx = fmaxf(mx, p[j]);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float e = ((rc.in_range >> j) & 1u) ? __expf(p[j] - mx) : 0.f;
+    p[j] = e;
+    sum += e;
+  }
+  const float inv = 1.f / sum;
+  if (rc.row_ok && a.stats != nullptr) {
+    *reinterpret_cast<float2*>(a.stats + 2 * rc.prow) = make_float2(mx, inv);
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) p[j] = ((keep >> j) & 1u) ? p[j] * inv * dc.scale : 0.f;
+  store_diag_row(Pg, t, warp, p);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (t == 0) {
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, HD, false, true);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint64_t da = umma_smem_desc(sP + (ks >> 2) * kTile + (ks & 3) * 32, 16u, 1024u);
+      const uint64_t db = umma_smem_desc(sV + ks * 2048, kTile, 1024u);
+      umma_bf16(tmem + 128, da, db, idesc, ks ? 1u : 0u);
+    }
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 1);
+  tc_fence_after();
+  __nv_bfloat16* op = a.out + (static_cast<long long>(rc.b) * a.Lq + rc.i) * a.ldo + rc.h * HD;
+  store_tmem_row<HD>(tmem + lane_base + 128, op, rc.row_ok);
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, kCols);
+  }
+}
+
+struct BwdP {
+  int B, H, Lq, Lk;
+  const float* stats;
+  const float* bias;
+  const long long* key_mask;
+  __nv_bfloat16 *dq, *dk, *dv;
+  long long lddq, lddk, lddv;
+  float* dbias;
+  float scale, drop_p;
+  uint32_t sid;
+  const unsigned long long* rng;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kThreads)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const BwdP a) {
+  constexpr int CH = (HD + 63) / 64;
+  constexpr int KS = HD / 16;
+  // TMEM: S [0,128), dP [128,256); once both are in registers their columns are recycled for the outputs
+  constexpr uint32_t kCols = (3 * HD <= 256) ? 256 : 512;
+  constexpr uint32_t cDV = (3 * HD <= 256) ? 0 : 256;
+  constexpr uint32_t cDQ = (3 * HD <= 256) ? HD : 256 + HD;
+  constexpr uint32_t cDK = (3 * HD <= 256) ? 2 * HD : 0;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base, sK = sQ + CH * kTile, sV = sK + CH * kTile, sdO = sV + CH * kTile;
+  const uint32_t sPd = sdO + CH * kTile, sdS = sPd + 2 * kTile;
+  const uint32_t bar_tma = sdS + 2 * kTile, bar_mma = bar_tma + 8, slot = bar_mma + 8;
+  uint8_t* Pdg = gen + 4 * CH * kTile;
+  uint8_t* dSg = Pdg + 2 * kTile;
+  const uint32_t* slot_ptr = reinterpret_cast<const uint32_t*>(gen + (4 * CH + 4) * kTile + 16);
+  const int t = threadIdx.x, warp = t >> 5;
+
+  pdl_launch_dependents();
+  if (t == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    mbar_init(bar_tma, 1);
+    mbar_init(bar_mma, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(slot, kCols);
+    tmem_relinquish();
+  }
+  for (int i = t; i < 4 * kTile / 16; i += kThreads) reinterpret_cast<uint4*>(Pdg)[i] = make_uint4(0u, 0u, 0u, 0u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot_ptr;
+  pdl_wait();
+
+  const int npairs = a.B * a.H;
+  if (t == 0) {
+    mbar_expect_tx(bar_tma, 4u * CH * kPairs * kBox);
+    for (int g = 0; g < kPairs; ++g) {
+      int pr = blockIdx.x * kPairs + g;
+      if (pr >= npairs) pr = npairs - 1;
+      const int b = pr / a.H, h = pr - b * a.H;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        tma_load_2d(sQ + c * kTile + g * kBox, &tmQ, bar_tma, h * HD + c * 64, b * a.Lq);
+        tma_load_2d(sdO + c * kTile + g * kBox, &tmdO, bar_tma, h * HD + c * 64, b * a.Lq);
+        tma_load_2d(sK + c * kTile + g * kBox, &tmK, bar_tma, h * HD + c * 64, b * a.Lk);
+        tma_load_2d(sV + c * kTile + g * kBox, &tmV, bar_tma, h * HD + c * 64, b * a.Lk);
+      }
+    }
+    mbar_wait(bar_tma, 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, 128, false, false);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {     // S = Q K^T
+      const uint32_t off = (ks >> 2) * kTile + (ks & 3) * 32;
+      umma_bf16(tmem, umma_smem_desc(sQ + off, 16u, 1024u), umma_smem_desc(sK + off, 16u, 1024u), idesc, ks ? 1u : 0u);
+    }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {     // dP = dO V^T
+      const uint32_t off = (ks >> 2) * kTile + (ks & 3) * 32;
+      umma_bf16(tmem + 128, umma_smem_desc(sdO + off, 16u, 1024u), umma_smem_desc(sV + off, 16u, 1024u), idesc,
+                ks ? 1u : 0u);
+    }
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+
+  const RowCtx rc = row_ctx(a.B, a.H, a.Lq, a.Lk, a.key_mask);
+  const DropCtx dc = drop_ctx(a.drop_p, a.sid, a.rng);
+  const uint32_t keep = keep_bits(dc, static_cast<unsigned long long>(rc.prow) * a.Lk, a.Lk);
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  float mx = 0.f, inv = 0.f;
+  if (rc.row_ok) {
+    const float2 st = *reinterpret_cast<const float2*>(a.stats + 2 * rc.prow);
+    mx = st.x; inv = st.y;
+  }
+
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+  float p[32], ds[32];
+  {
+    uint32_t acc[32];
+    tmem_ld_32x32(tmem + lane_base + warp * 32, acc);
+    tmem_ld_wait();
+    finish_scores(p, acc, rc, a.scale, a.bias, a.Lq, a.Lk);
+    tmem_ld_32x32(tmem + lane_base + 128 + warp * 32, acc);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ds[j] = __uint_as_float(acc[j]);
+  }
+  // rows that do not exist (i >= Lq, pair beyond B*H) get P = 0 so they add nothing to dK / dV
+  float rowdot = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const bool live = rc.row_ok && ((rc.in_range >> j) & 1u);
+    const float pj = live ? __expf(p[j] - mx) * inv : 0.f;
+    const float m = ((keep >> j) & 1u) ? dc.scale : 0.f;
+    const float dp = live ? ds[j] * m : 0.f;
+    rowdot = fmaf(pj, dp, rowdot);
+    p[j] = pj;
+    ds[j] = dp;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) ds[j] = p[j] * (ds[j] - rowdot);
+  if (a.dbias != nullptr && rc.row_ok) {
+    float* dbrow = a.dbias + (static_cast<long long>(rc.h) * a.Lq + rc.i) * a.Lk;
+    if ((a.Lk & 3) == 0 && (reinterpret_cast<uintptr_t>(dbrow) & 15) == 0) {
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4)
+        if (q4 * 4 < a.Lk)
+          atomicAdd(reinterpret_cast<float4*>(dbrow) + q4,
+                    make_float4(ds[4 * q4], ds[4 * q4 + 1], ds[4 * q4 + 2], ds[4 * q4 + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < a.Lk) atomicAdd(dbrow + j, ds[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    p[j] = ((keep >> j) & 1u) ? p[j] * dc.scale : 0.f;   // dropped probabilities (operand of dV)
+    ds[j] *= a.scale;                                     // both dQ and dK carry the score scale
+  }
+  store_diag_row(Pdg, t, warp, p);
+  store_diag_row(dSg, t, warp, ds);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (t == 0) {
+    tc_fence_after();
+    const uint32_t id_tt = umma_idesc_bf16(128, HD, true, true);
+    const uint32_t id_nt = umma_idesc_bf16(128, HD, false, true);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {      // dV[key, d] = sum_q Pd[q, key] dO[q, d]
+      umma_bf16(tmem + cDV, umma_smem_desc(sPd + ks * 2048, kTile, 1024u), umma_smem_desc(sdO + ks * 2048, kTile, 1024u),
+                id_tt, ks ? 1u : 0u);
+    }
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {      // dQ[q, d] = sum_key dS[q, key] K[key, d]
+      umma_bf16(tmem + cDQ, umma_smem_desc(sdS + (ks >> 2) * kTile + (ks & 3) * 32, 16u, 1024u),
+                umma_smem_desc(sK + ks * 2048, kTile, 1024u), id_nt, ks ? 1u : 0u);
+    }
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {      // dK[key, d] = sum_q dS[q, key] Q[q, d]
+      umma_bf16(tmem + cDK, umma_smem_desc(sdS + ks * 2048, kTile, 1024u), umma_smem_desc(sQ + ks * 2048, kTile, 1024u),
+                id_tt, ks ? 1u : 0u);
+    }
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 1);
+  tc_fence_after();
+  {
+    __nv_bfloat16* qp = a.dq + (static_cast<long long>(rc.b) * a.Lq + rc.i) * a.lddq + rc.h * HD;
+    store_tmem_row<HD>(tmem + lane_base + cDQ, qp, rc.row_ok);
+    const bool key_ok = rc.pair_ok && rc.i < a.Lk;
+    __nv_bfloat16* kp = a.dk + (static_cast<long long>(rc.b) * a.Lk + rc.i) * a.lddk + rc.h * HD;
+    store_tmem_row<HD>(tmem + lane_base + cDK, kp, key_ok);
+    __nv_bfloat16* vp = a.dv + (static_cast<long long>(rc.b) * a.Lk + rc.i) * a.lddv + rc.h * HD;
+    store_tmem_row<HD>(tmem + lane_base + cDV, vp, key_ok);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, kCols);
+  }
+}
+
+template <int HD> constexpr size_t fwd_smem_bytes() { return (3 * ((HD + 63) / 64) + 2) * kTile + 64 + 1024; }
+template <int HD> constexpr size_t bwd_smem_bytes() { return (4 * ((HD + 63) / 64) + 4) * kTile + 64 + 1024; }
+
+template <typename K>
+int raise_smem(K kern, size_t bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) { set_last_error("%s: %s", what, cudaGetErrorString(e)); return static_cast<int>(e); }
+  return 0;
+}
+
+int operand_map(CUtensorMap* tm, const void* base, long long rows, int H, int hd, long long ld, const char* what) {
+  if (reinterpret_cast<uintptr_t>(base) & 15) { set_last_error("%s: operand pointers must be 16-byte aligned", what); return -1; }
+  return make_tmap_2d(tm, base, static_cast<uint64_t>(rows), static_cast<uint64_t>(H) * hd, static_cast<uint64_t>(ld), 64, kSlot);
+}
+
+}  // namespace
+
+namespace vqa {
+
+bool attention_tc_supported(int Lq, int Lk, int hd) {
+  return Lq >= 1 && Lq <= kSlot && Lk >= 1 && Lk <= kSlot && (hd == 64 || hd == 96);
+}
+
+int attention_tc_fwd(void* plan, const vqa_attn_fwd_args* x, void* stream) {
+  CUtensorMap tq, tk, tv;
+  if (operand_map(&tq, x->q, static_cast<long long>(x->B) * x->Lq, x->H, x->hd, x->ldq, "attention_fwd")) return -1;
+  if (operand_map(&tk, x->k, static_cast<long long>(x->B) * x->Lk, x->H, x->hd, x->ldk, "attention_fwd")) return -1;
+  if (operand_map(&tv, x->v, static_cast<long long>(x->B) * x->Lk, x->H, x->hd, x->ldv, "attention_fwd")) return -1;
+  FwdP a;
+  a.B = x->B; a.H = x->H; a.Lq = x->Lq; a.Lk = x->Lk;
+  a.out = static_cast<__nv_bfloat16*>(x->out); a.ldo = x->ldo;
+  a.stats = x->stats; a.bias = x->bias; a.key_mask = x->key_mask;
+  a.scale = x->scale; a.drop_p = x->drop_p; a.sid = x->sid;
+  a.rng = reinterpret_cast<const unsigned long long*>(x->rng);
+  const int hd = x->hd;
+  static bool attr64 = false, attr96 = false;
+  if (hd == 64 && !attr64) { if (raise_smem(attn_tc_fwd_kernel<64>, fwd_smem_bytes<64>(), "attention_fwd")) return -1; attr64 = true; }
+  if (hd == 96 && !attr96) { if (raise_smem(attn_tc_fwd_kernel<96>, fwd_smem_bytes<96>(), "attention_fwd")) return -1; attr96 = true; }
+  const int grid = (a.B * a.H + kPairs - 1) / kPairs;
+  const double fl = 4.0 * a.B * a.H * a.Lq * a.Lk * hd;
+  note_op("attention_fwd", fl, 0.0);
+  return submit(plan, stream, [=](cudaStream_t s) {
+    if (hd == 64) launch_pdl(attn_tc_fwd_kernel<64>, dim3(grid), dim3(kThreads), fwd_smem_bytes<64>(), s, tq, tk, tv, a);
+    else launch_pdl(attn_tc_fwd_kernel<96>, dim3(grid), dim3(kThreads), fwd_smem_bytes<96>(), s, tq, tk, tv, a);
+    return launch_status("attention_fwd");
+  });
+}
+
+int attention_tc_bwd(void* plan, const vqa_attn_bwd_args* x, void* stream) {
+  CUtensorMap tq, tk, tv, tdo;
+  if (operand_map(&tq, x->q, static_cast<long long>(x->B) * x->Lq, x->H, x->hd, x->ldq, "attention_bwd")) return -1;
+  if (operand_map(&tk, x->k, static_cast<long long>(x->B) * x->Lk, x->H, x->hd, x->ldk, "attention_bwd")) return -1;
+  if (operand_map(&tv, x->v, static_cast<long long>(x->B) * x->Lk, x->H, x->hd, x->ldv, "attention_bwd")) return -1;
+  if (operand_map(&tdo, x->dout, static_cast<long long>(x->B) * x->Lq, x->H, x->hd, x->ldo, "attention_bwd")) return -1;
+  BwdP a;
+  a.B = x->B; a.H = x->H; a.Lq = x->Lq; a.Lk = x->Lk;
+  a.stats = x->stats; a.bias = x->bias; a.key_mask = x->key_mask;
+  a.dq = static_cast<__nv_bfloat16*>(x->dq); a.dk = static_cast<__nv_bfloat16*>(x->dk);
+  a.dv = static_cast<__nv_bfloat16*>(x->dv);
+  a.lddq = x->lddq; a.lddk = x->lddk; a.lddv = x->lddv;
+  a.dbias = x->dbias; a.scale = x->scale; a.drop_p = x->drop_p; a.sid = x->sid;
+  a.rng = reinterpret_cast<const unsigned long long*>(x->rng);
+  const int hd = x->hd;
+  static bool attr64 = false, attr96 = false;
+  if (hd == 64 && !attr64) { if (raise_smem(attn_tc_bwd_kernel<64>, bwd_smem_bytes<64>(), "attention_bwd")) return -1; attr64 = true; }
+  if (hd == 96 && !attr96) { if (raise_smem(attn_tc_bwd_kernel<96>, bwd_smem_bytes<96>(), "attention_bwd")) return -1; attr96 = true; }
+  const int grid = (a.B * a.H + kPairs - 1) / kPairs;
+  const double fl = 10.0 * a.B * a.H * a.Lq * a.Lk * hd;
+  note_op("attention_bwd", fl, 0.0);
+  return submit(plan, stream, [=](cudaStream_t s) {
+    if (hd == 64) launch_pdl(attn_tc_bwd_kernel<64>, dim3(grid), dim3(kThreads), bwd_smem_bytes<64>(), s, tq, tk, tv, tdo, a);
+    else launch_pdl(attn_tc_bwd_kernel<96>, dim3(grid), dim3(kThreads), bwd_smem_bytes<96>(), s, tq, tk, tv, tdo, a);
+    return launch_status("attention_bwd");
+  });
+}
+
+}  // namespace vqa

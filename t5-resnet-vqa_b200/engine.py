@@ -136,16 +136,17 @@ class _Rec:
         L.check(self.lib.vqa_conv2d_wgrad_bf16(self.plan, ctypes.byref(a), self._s()), "conv2d_wgrad")
 
     def attn_fwd(self, B, H, Lq, Lk, hd, q, ldq, k, ldk, v, ldv, out, ldo, probs, bias, key_mask, scale, drop_p,
-                 sid, rng):
+                 sid, rng, stats=None):
         a = L.AttnFwdArgs()
         a.B, a.H, a.Lq, a.Lk, a.hd = B, H, Lq, Lk, hd
         a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = L.ptr(q), ldq, L.ptr(k), ldk, L.ptr(v), ldv
         a.out, a.ldo, a.probs, a.bias, a.key_mask = L.ptr(out), ldo, L.ptr(probs), L.ptr(bias), L.ptr(key_mask)
         a.scale, a.drop_p, a.sid, a.rng = scale, float(drop_p), sid, L.ptr(rng) if drop_p > 0 else None
+        a.stats = L.ptr(stats)
         L.check(self.lib.vqa_attention_fwd(self.plan, ctypes.byref(a), self._s()), "attention_fwd")
 
     def attn_bwd(self, B, H, Lq, Lk, hd, q, ldq, k, ldk, v, ldv, probs, dout, ldo, dq, lddq, dk, lddk, dv, lddv,
-                 dbias, scale, drop_p, sid, rng):
+                 dbias, scale, drop_p, sid, rng, stats=None, bias=None, key_mask=None):
         a = L.AttnBwdArgs()
         a.B, a.H, a.Lq, a.Lk, a.hd = B, H, Lq, Lk, hd
         a.q, a.ldq, a.k, a.ldk, a.v, a.ldv = L.ptr(q), ldq, L.ptr(k), ldk, L.ptr(v), ldv
@@ -153,6 +154,7 @@ class _Rec:
         a.dq, a.lddq, a.dk, a.lddk, a.dv, a.lddv = L.ptr(dq), lddq, L.ptr(dk), lddk, L.ptr(dv), lddv
         a.dbias, a.scale, a.drop_p, a.sid = L.ptr(dbias), scale, float(drop_p), sid
         a.rng = L.ptr(rng) if drop_p > 0 else None
+        a.stats, a.bias, a.key_mask = L.ptr(stats), L.ptr(bias), L.ptr(key_mask)
         L.check(self.lib.vqa_attention_bwd(self.plan, ctypes.byref(a), self._s()), "attention_bwd")
 
     # ---- everything else: positional passthrough ----
@@ -210,6 +212,7 @@ class Engine:
         self.run_id = 0
         self.use_graphs = _env_flag("VQA_B200_GRAPHS", True)
         self.use_lanes = _env_flag("VQA_B200_LANES", True)
+        self.use_tc_attention = _env_flag("VQA_B200_TC_ATTENTION", True)
         self.vision_sig = None
         self.param_sig = None
         self.shadow_fresh = False

@@ -39,7 +39,7 @@ class AttnFwdArgs(ctypes.Structure):
     _fields_ = [("B", c_int), ("H", c_int), ("Lq", c_int), ("Lk", c_int), ("hd", c_int),
                 ("q", c_vp), ("ldq", c_ll), ("k", c_vp), ("ldk", c_ll), ("v", c_vp), ("ldv", c_ll),
                 ("out", c_vp), ("ldo", c_ll), ("probs", c_vp), ("bias", c_vp), ("key_mask", c_vp),
-                ("scale", c_f), ("drop_p", c_f), ("sid", c_u32), ("rng", c_vp)]
+                ("scale", c_f), ("drop_p", c_f), ("sid", c_u32), ("rng", c_vp), ("stats", c_vp)]
 
 
 class AttnBwdArgs(ctypes.Structure):
@@ -47,7 +47,8 @@ class AttnBwdArgs(ctypes.Structure):
                 ("q", c_vp), ("ldq", c_ll), ("k", c_vp), ("ldk", c_ll), ("v", c_vp), ("ldv", c_ll),
                 ("probs", c_vp), ("dout", c_vp), ("ldo", c_ll),
                 ("dq", c_vp), ("lddq", c_ll), ("dk", c_vp), ("lddk", c_ll), ("dv", c_vp), ("lddv", c_ll),
-                ("dbias", c_vp), ("scale", c_f), ("drop_p", c_f), ("sid", c_u32), ("rng", c_vp)]
+                ("dbias", c_vp), ("scale", c_f), ("drop_p", c_f), ("sid", c_u32), ("rng", c_vp),
+                ("stats", c_vp), ("bias", c_vp), ("key_mask", c_vp)]
 
 
 # every symbol include/vqa_b200.h declares, with its argument types (tests check the library exports all)

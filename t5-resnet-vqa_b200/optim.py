@@ -106,6 +106,14 @@ class VQAFusedAdamW(torch.optim.Optimizer):
         for eng, k in covered.items():
             eng.fused_opt = weakref.ref(self) if k == len(eng.params) else None
 
+    def state_dict(self):
+        """torch layout.  The per-group step counter is one tensor shared by the group's parameters here; torch's
+        AdamW advances `step` once per parameter, so a checkpoint must carry an independent copy for each."""
+        sd = super().state_dict()
+        sd["state"] = {k: {**v, "step": v["step"].clone()} if "step" in v else dict(v)
+                       for k, v in sd["state"].items()}
+        return sd
+
     def _signature(self):
         sig = []
         for group in self.param_groups:

@@ -60,6 +60,13 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
         sid_counter[0] += 1
         return sid_counter[0]
 
+    def attn_save(nheads, Lq, Lk):
+        """What attention saves for backward: (probs, stats).  Up to 32 x 32 tokens the tcgen05 flash kernels run
+        and keep only the softmax row statistics; longer key sequences use the SIMT kernel and its fp32 probs."""
+        if Lq <= 32 and Lk <= 32 and eng.use_tc_attention:
+            return None, al(B * nheads * Lq, 2, dtype=f32)
+        return al(B * nheads * Lq * Lk, dtype=f32), None
+
     # ---- static inputs / outputs ----
     st.ids = al(B, Lt, dtype=i64, zero=True)
     st.mask = al(B, Lt, dtype=i64, zero=True)
@@ -168,7 +175,8 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     for bi, blk in enumerate(blocks):
         att, ff = blk.layer[0], blk.layer[1]
         sa, dd = att.SelfAttention, ff.DenseReluDense
-        sv = dict(y1=al(M, D), rstd1=al(M, dtype=f32), qkv=al(M, 3 * inner), probs=al(B * nH * Lt * Lt, dtype=f32),
+        t5_probs, t5_stats = attn_save(nH, Lt, Lt)
+        sv = dict(y1=al(M, D), rstd1=al(M, dtype=f32), qkv=al(M, 3 * inner), probs=t5_probs, stats=t5_stats,
                   ctx=al(M, inner), hmid=al(M, D, dtype=f32), y2=al(M, D), rstd2=al(M, dtype=f32), h=al(M, dff),
                   sid_p=new_sid(), sid_o=new_sid(), sid_h=new_sid(), sid_f=new_sid())
         r.rmsnorm_fwd(hid[bi], eng.mp(att.layer_norm.weight), sv["y1"], None, sv["rstd1"], M, D, eps_t5, 0.0, 0, None)
@@ -177,7 +185,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
         qkv = sv["qkv"]
         r.attn_fwd(B, nH, Lt, Lt, dkv, qkv, 3 * inner, qkv.data_ptr() + 2 * inner, 3 * inner,
                    qkv.data_ptr() + 4 * inner, 3 * inner, sv["ctx"], inner, sv["probs"], pos_bias, st.mask, 1.0,
-                   p_t5, sv["sid_p"], rng)
+                   p_t5, sv["sid_p"], rng, stats=sv["stats"])
         r.linear(sv["ctx"], M, inner, inner, eng.sp(sa.o.weight), D, sv["hmid"], D, out_fp32=1,
                  drop_p=p_t5, sid=sv["sid_o"], rng=rng, residual=hid[bi], ldr=D, res_fp32=1)
         r.rmsnorm_fwd(sv["hmid"], eng.mp(ff.layer_norm.weight), sv["y2"], None, sv["rstd2"], M, D, eps_t5, 0.0, 0, None)
@@ -203,10 +211,12 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     for li, sga in enumerate(sgas):
         Myl = B * Ly
         m1, m2, mlp = sga.mhatt1, sga.mhatt2, sga.ffn.mlp
-        sv = dict(y=y_bf16, Ly=Ly,
-                  qkv1=al(M, 3 * D), probs1=al(B * Hs * Lt * Lt, dtype=f32), ctx1=al(M, D), z1=al(M, D, dtype=f32),
+        probs1, stats1 = attn_save(Hs, Lt, Lt)
+        probs2, stats2 = attn_save(Hs, Lt, Ly)
+        sv = dict(y=y_bf16, Ly=Ly, stats1=stats1, stats2=stats2,
+                  qkv1=al(M, 3 * D), probs1=probs1, ctx1=al(M, D), z1=al(M, D, dtype=f32),
                   mean1=al(M, dtype=f32), rstd1=al(M, dtype=f32), x1f=al(M, D, dtype=f32), x1b=al(M, D),
-                  q2=al(M, D), vk2=al(Myl, 2 * D), probs2=al(B * Hs * Lt * Ly, dtype=f32), ctx2=al(M, D),
+                  q2=al(M, D), vk2=al(Myl, 2 * D), probs2=probs2, ctx2=al(M, D),
                   z2=al(M, D, dtype=f32), mean2=al(M, dtype=f32), rstd2=al(M, dtype=f32),
                   x2f=al(M, D, dtype=f32), x2b=al(M, D), hm=al(M, D), z3=al(M, D, dtype=f32),
                   mean3=al(M, dtype=f32), rstd3=al(M, dtype=f32), of=al(M, D, dtype=f32), ob=al(M, D),
@@ -217,7 +227,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
                  bias=eng.mp(m1.linear_v.bias))
         q1 = sv["qkv1"]
         r.attn_fwd(B, Hs, Lt, Lt, hd, q1.data_ptr() + 4 * D, 3 * D, q1.data_ptr() + 2 * D, 3 * D, q1, 3 * D,
-                   sv["ctx1"], D, sv["probs1"], None, None, scale, p_sga, sv["sid_p1"], rng)
+                   sv["ctx1"], D, sv["probs1"], None, None, scale, p_sga, sv["sid_p1"], rng, stats=sv["stats1"])
         r.linear(sv["ctx1"], M, D, D, eng.sp(m1.linear_merge.weight), D, sv["z1"], D, out_fp32=1,
                  bias=eng.mp(m1.linear_merge.bias), drop_p=p_sga, sid=sv["sid_r1"], rng=rng, residual=text_f32,
                  ldr=D, res_fp32=1)
@@ -231,7 +241,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
                  bias=eng.mp(m2.linear_v.bias))
         vk = sv["vk2"]
         r.attn_fwd(B, Hs, Lt, Ly, hd, sv["q2"], D, vk.data_ptr() + 2 * D, 2 * D, vk, 2 * D, sv["ctx2"], D,
-                   sv["probs2"], None, None, scale, p_sga, sv["sid_p2"], rng)
+                   sv["probs2"], None, None, scale, p_sga, sv["sid_p2"], rng, stats=sv["stats2"])
         r.linear(sv["ctx2"], M, D, D, eng.sp(m2.linear_merge.weight), D, sv["z2"], D, out_fp32=1,
                  bias=eng.mp(m2.linear_merge.bias), drop_p=p_sga, sid=sv["sid_r2"], rng=rng, residual=sv["x1f"],
                  ldr=D, res_fp32=1)
@@ -379,7 +389,8 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
         vk = sv["vk2"]
         side.before_write(dqkv, dvk)
         r.attn_bwd(B, Hs, Lt, Ly, hd, sv["q2"], D, vk.data_ptr() + 2 * D, 2 * D, vk, 2 * D, sv["probs2"], dsm, D,
-                   dqkv, D, dvk.data_ptr() + 2 * D, 2 * D, dvk, 2 * D, None, scale, p_sga, sv["sid_p2"], rng)
+                   dqkv, D, dvk.data_ptr() + 2 * D, 2 * D, dvk, 2 * D, None, scale, p_sga, sv["sid_p2"], rng,
+                   stats=sv["stats2"])
 
         def att2_leaf():
             r.colsum_bf16(dqkv, D, eng.gp(m2.linear_q.bias), M, D)
@@ -406,7 +417,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
         side.before_write(dqkv)
         r.attn_bwd(B, Hs, Lt, Lt, hd, q1.data_ptr() + 4 * D, 3 * D, q1.data_ptr() + 2 * D, 3 * D, q1, 3 * D,
                    sv["probs1"], dsm, D, dqkv.data_ptr() + 4 * D, 3 * D, dqkv.data_ptr() + 2 * D, 3 * D, dqkv, 3 * D,
-                   None, scale, p_sga, sv["sid_p1"], rng)
+                   None, scale, p_sga, sv["sid_p1"], rng, stats=sv["stats1"])
 
         def att1_leaf():
             r.colsum_bf16(dqkv, 3 * D, eng.gp(m1.linear_v.bias), M, 3 * D)
@@ -468,7 +479,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
         r.attn_bwd(B, nH, Lt, Lt, dkv, qkv, 3 * inner, qkv.data_ptr() + 2 * inner, 3 * inner,
                    qkv.data_ptr() + 4 * inner, 3 * inner, sv["probs"], dsm, inner,
                    dqkv, 3 * inner, dqkv.data_ptr() + 2 * inner, 3 * inner, dqkv.data_ptr() + 4 * inner, 3 * inner,
-                   dbias_pos, 1.0, p_t5, sv["sid_p"], rng)
+                   dbias_pos, 1.0, p_t5, sv["sid_p"], rng, stats=sv["stats"], bias=pos_bias, key_mask=st.mask)
         side.leaf([dqkv], lambda: r.wgrad(dqkv, M, 3 * inner, 3 * inner, sv["y1"], D, D, eng.gp(sa.q.weight)))
         r.dgrad(dqkv, M, 3 * inner, 3 * inner, eng.sp(sa.q.weight), D, dsm, D)
         if bi > 0:

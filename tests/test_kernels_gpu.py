@@ -267,10 +267,14 @@ def test_embedding_and_bias(C, pkg):
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,H,Lq,Lk,hd,t5", [(4, 12, 32, 32, 64, True), (3, 12, 16, 16, 64, True),
-                                             (4, 8, 32, 32, 96, False), (4, 8, 32, 49, 96, False),
-                                             (2, 8, 16, 64, 96, False), (2, 8, 32, 196, 96, False)])
-def test_attention_fwd_bwd(C, B, H, Lq, Lk, hd, t5):
+@pytest.mark.parametrize("B,H,Lq,Lk,hd,t5,tc", [
+    (4, 12, 32, 32, 64, True, False), (3, 12, 16, 16, 64, True, False), (4, 8, 32, 32, 96, False, False),
+    (4, 8, 32, 49, 96, False, False), (2, 8, 16, 64, 96, False, False), (2, 8, 32, 196, 96, False, False),
+    # tcgen05 flash kernels (Lq, Lk <= 32): full groups, ragged last group, short sequences, ragged Lk
+    (4, 12, 32, 32, 64, True, True), (3, 12, 16, 16, 64, True, True), (64, 12, 32, 32, 64, True, True),
+    (4, 8, 32, 32, 96, False, True), (3, 7, 32, 32, 96, False, True), (5, 6, 20, 27, 64, True, True),
+    (2, 8, 16, 16, 96, False, True)])
+def test_attention_fwd_bwd(C, B, H, Lq, Lk, hd, t5, tc):
     D = H * hd
     q = rnd(B * Lq, D, seed=1, scale=1.0 if not t5 else 0.4, dtype=BF)
     k = rnd(B * Lk, D, seed=2, scale=1.0 if not t5 else 0.4, dtype=BF)
@@ -293,17 +297,47 @@ def test_attention_fwd_bwd(C, B, H, Lq, Lk, hd, t5):
     o = torch.matmul(p, vh).transpose(1, 2).reshape(B * Lq, D)
     o.backward(dO.float())
     out = torch.zeros(B * Lq, D, dtype=BF, device="cuda")
-    probs = torch.zeros(B * H * Lq * Lk, dtype=F32, device="cuda")
-    C.attn_fwd(B, H, Lq, Lk, hd, q, D, k, D, v, D, out, D, probs, bias.detach() if t5 else None, mask, scale, 0.0, 0, None)
+    probs = None if tc else torch.zeros(B * H * Lq * Lk, dtype=F32, device="cuda")
+    stats = torch.zeros(B * H * Lq, 2, dtype=F32, device="cuda") if tc else None
+    bdet = bias.detach() if t5 else None
+    C.attn_fwd(B, H, Lq, Lk, hd, q, D, k, D, v, D, out, D, probs, bdet, mask, scale, 0.0, 0, None, stats=stats)
     assert rel_fro(out, o.detach()) < 6e-3
-    assert rel_fro(probs.view(B, H, Lq, Lk), p.detach()) < 2e-3
+    if tc:
+        sv = stats.view(B, H, Lq, 2)
+        assert rel_fro(sv[..., 0], s.detach().max(-1).values) < 1e-5
+        assert rel_fro(1.0 / sv[..., 1], (s.detach() - s.detach().max(-1, keepdim=True).values).exp().sum(-1)) < 1e-4
+    else:
+        assert rel_fro(probs.view(B, H, Lq, Lk), p.detach()) < 2e-3
     dq, dk, dv = [torch.zeros_like(t) for t in (q, k, v)]
     dbias = torch.zeros(H, Lq, Lk, device="cuda") if t5 else None
-    C.attn_bwd(B, H, Lq, Lk, hd, q, D, k, D, v, D, probs, dO, D, dq, D, dk, D, dv, D, dbias, scale, 0.0, 0, None)
+    C.attn_bwd(B, H, Lq, Lk, hd, q, D, k, D, v, D, probs, dO, D, dq, D, dk, D, dv, D, dbias, scale, 0.0, 0, None,
+               stats=stats, bias=bdet, key_mask=mask)
     assert rel_fro(dq, qf.grad) < 1.5e-2 and rel_fro(dk, kf.grad) < 1.5e-2 and rel_fro(dv, vf.grad) < 1.5e-2
     assert cosine(dq, qf.grad) > 0.9999 and cosine(dk, kf.grad) > 0.9999
     if t5:
         assert rel_fro(dbias, bias.grad) < 1.5e-2
+
+
+@pytest.mark.parametrize("H,hd,Lk", [(12, 64, 32), (8, 96, 32), (6, 64, 27)])
+def test_attention_tcgen05_dropout_matches_simt(C, H, hd, Lk):
+    """Both kernels draw the dropout mask of probability (b,h,i,j) from the same Philox stream, so with dropout on
+    the tcgen05 path must reproduce the SIMT path (forward and every gradient) up to bf16 rounding of P."""
+    B, Lq, D = 5, 32, H * hd
+    q, k = rnd(B * Lq, D, seed=1, scale=0.5, dtype=BF), rnd(B * Lk, D, seed=2, scale=0.5, dtype=BF)
+    v, dO = rnd(B * Lk, D, seed=3, dtype=BF), rnd(B * Lq, D, seed=4, dtype=BF)
+    rng = rng_state()
+    res = []
+    for tc in (False, True):
+        out = torch.zeros(B * Lq, D, dtype=BF, device="cuda")
+        probs = None if tc else torch.zeros(B * H * Lq * Lk, dtype=F32, device="cuda")
+        stats = torch.zeros(B * H * Lq, 2, dtype=F32, device="cuda") if tc else None
+        C.attn_fwd(B, H, Lq, Lk, hd, q, D, k, D, v, D, out, D, probs, None, None, 0.125, 0.1, 3, rng, stats=stats)
+        dq, dk, dv = [torch.zeros_like(t) for t in (q, k, v)]
+        C.attn_bwd(B, H, Lq, Lk, hd, q, D, k, D, v, D, probs, dO, D, dq, D, dk, D, dv, D, None, 0.125, 0.1, 3, rng,
+                   stats=stats)
+        res.append((out, dq, dk, dv))
+    for a, b in zip(*res):
+        assert rel_fro(b, a) < 1.2e-2 and cosine(a, b) > 0.9999
 
 
 # ------------------------------------------------------------------------------------------------

@@ -202,48 +202,67 @@ def test_train_mode_dropout_and_fused_optimizer_step(pkg, cuda):
             assert float((p.detach() - ref[k].detach()).abs().max()) < 2e-6, k
 
 
-def test_clip_grad_norm_fast_path(pkg, cuda, monkeypatch):
+def test_clip_grad_norm_fast_path(pkg, cuda):
     """torch.nn.utils.clip_grad_norm_ (the trainer's call, trainer/faster_rcnn_vqa_trainer.py:399-400) is routed
-    through the flat-buffer kernels: same norm and same clipped gradients as torch's implementation; with the fused
-    optimizer attached the scaling is folded into AdamW and gives the same parameters as the in-place path."""
+    through the flat-buffer kernels: same norm and same clipped gradients as torch's implementation; once the fused
+    optimizer is attached the scaling is folded into its AdamW pass, which must equal torch.optim.AdamW stepping
+    from the same state on the clipped gradients."""
+    import copy
     from oracle import vqa_oracle as O
     from t5_resnet_vqa_b200 import optim as vo
     assert torch.nn.utils.clip_grad_norm_ is vo.clip_grad_norm_
     sd = O.random_state_dict("resnet18", 170, seed=0)
     batch = O.synthetic_batch(2, 16, 64, 64, 170, seed=1)
+    m = build(pkg, "resnet18", sd, cuda)          # eval(): dropout off
+    opt = torch.optim.VQAFusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.1, amsgrad=True)
+    MAXN = 0.05
 
-    def two_steps(defer):
-        monkeypatch.setenv("VQA_B200_DEFER_CLIP", "1" if defer else "0")
-        m = build(pkg, "resnet18", sd, cuda)          # eval(): dropout off, deterministic
-        opt = torch.optim.VQAFusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.1, amsgrad=True)
-        norms = []
-        for step in range(2):
-            opt.zero_grad()
-            _, loss = run(m, batch, cuda)
-            loss.backward()
-            grads = [p.grad.detach().clone() for p in m.parameters() if p.grad is not None]
-            holders = [torch.zeros_like(g).requires_grad_(True) for g in grads]
-            for h, g in zip(holders, grads):
-                h.grad = g
-            want = vo._torch_clip_grad_norm_(holders, 0.05)            # clips the clones in place
-            got = torch.nn.utils.clip_grad_norm_(m.parameters(), 0.05)
-            assert got.dim() == 0 and abs(float(got) / float(want) - 1) < 1e-5
-            now = [p.grad for p in m.parameters() if p.grad is not None]
-            if m._engine.pending_clip is None:                         # in-place path: .grad holds clipped values
-                assert float(want) > 0.05
-                for a, b in zip(now, grads):
-                    assert float((a - b).abs().max()) <= 1e-6 * max(1.0, float(b.abs().max()))
-            else:                                                      # deferred: the optimizer applies the factor
-                assert defer and step == 1
-            opt.step()
-            norms.append(float(got))
-        return {k: p.detach().clone() for k, p in m.named_parameters()}, norms
+    def fwd_bwd():
+        opt.zero_grad()
+        _, loss = run(m, batch, cuda)
+        loss.backward()
+        return {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
 
-    p_inplace, n0 = two_steps(False)
-    p_defer, n1 = two_steps(True)
-    assert abs(n0[1] / n1[1] - 1) < 1e-5
-    for k in p_inplace:
-        assert float((p_inplace[k] - p_defer[k]).abs().max()) < 2e-6, k
+    def torch_clip(grads):
+        holders = [torch.zeros_like(g).requires_grad_(True) for g in grads.values()]
+        for h, g in zip(holders, grads.values()):
+            h.grad = g.clone()
+        total = vo._torch_clip_grad_norm_(holders, MAXN)
+        return total, {k: h.grad for k, h in zip(grads, holders)}
+
+    # step 1: no fused optimizer attached yet -> in-place scaling, .grad holds the clipped values like torch
+    g = fwd_bwd()
+    want, clipped = torch_clip(g)
+    got = torch.nn.utils.clip_grad_norm_(m.parameters(), MAXN)
+    assert got.dim() == 0 and abs(float(got) / float(want) - 1) < 1e-5 and float(want) > MAXN
+    assert m._engine.pending_clip is None
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            assert float((p.grad - clipped[k]).abs().max()) <= 1e-6 * max(1.0, float(clipped[k].abs().max())), k
+    opt.step()
+
+    # step 2: the optimizer now covers the whole engine -> deferred; gradients stay unscaled until step()
+    g = fwd_bwd()
+    before = {k: p.detach().clone() for k, p in m.named_parameters()}
+    state = copy.deepcopy(opt.state_dict())
+    want, clipped = torch_clip(g)
+    got = torch.nn.utils.clip_grad_norm_(m.parameters(), MAXN)
+    assert abs(float(got) / float(want) - 1) < 1e-5
+    assert m._engine.pending_clip == MAXN
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            assert torch.equal(p.grad, g[k])
+    opt.step()
+    assert m._engine.pending_clip is None
+    ref = [before[k].clone().requires_grad_(True) for k, _ in m.named_parameters()]
+    ropt = torch.optim.AdamW(ref, lr=1e-3, weight_decay=0.1, amsgrad=True)
+    ropt.load_state_dict(state)
+    for r, (k, _) in zip(ref, m.named_parameters()):
+        if k in clipped:
+            r.grad = clipped[k]
+    ropt.step()
+    for r, (k, p) in zip(ref, m.named_parameters()):
+        assert float((p.detach() - r.detach()).abs().max()) < 2e-6, k
     # tensors outside an engine still go to torch
     w = torch.randn(10, 10, device=cuda, requires_grad=True)
     w.grad = torch.ones_like(w)
