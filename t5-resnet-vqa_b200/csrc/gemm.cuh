@@ -44,6 +44,7 @@ struct GemmParams {
   int a_mn, b_mn;  // 1 = operand is MN-major in global memory (contraction index is the row index)
   int a_mode, b_mode;
   int stage_tx_bytes;  // bytes the TMA loads of one pipeline stage deliver (A box + B boxes)
+  int res_tx_bytes;    // bytes of one bf16 residual panel load (rows of the tile x 128 B)
 
   // pixel-box geometry (LOAD_CONV for A; LOAD_PIXELS_MN for A and/or B)
   int bx_w, bx_h, bx_n;        // box extent in output pixels (w, h, images); product = rows per box
@@ -78,7 +79,8 @@ struct GemmParams {
 
 // Launch. tmA / tmB are host-encoded CUtensorMaps (copied into kernel parameter space).
 // bn in {64, 128, 256}; split_k >= 1.  Returns cudaError_t as int.
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn,
-                int split_k, cudaStream_t stream);
+// tmOut: store map of the output (box = 128 rows / pixel box x 128 bytes); tmRes: same geometry over the bf16 residual.
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
+                const GemmParams& p, int bn, int split_k, cudaStream_t stream);
 
 }  // namespace vqa

@@ -2,8 +2,8 @@
 #include "gemm_kernel.cuh"
 
 namespace vqa {
-int launch_gemm_bn128(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int tiles_m, int tiles_n,
-                     int splits, cudaStream_t stream) {
-  return launch_bn<128, 5>(tmA, tmB, p, tiles_m, tiles_n, splits, stream);
+int launch_gemm_bn128(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
+                     const GemmParams& p, int tiles_m, int tiles_n, int splits, cudaStream_t stream) {
+  return launch_bn<128, 4>(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, splits, stream);
 }
 }  // namespace vqa

@@ -1,16 +1,23 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a:  D[M,N] = epilogue( A[M,K] * B[N,K]^T ), bf16 in, fp32 accumulate.
 //
-// Persistent kernel, one CTA per SM, 320 threads, static round-robin tile scheduler over 128 x BN output tiles
+// Persistent kernel, one CTA per SM, 352 threads, static round-robin tile scheduler over 128 x BN output tiles
 // (n-tile fastest so CTAs running side by side share the A tile in L2; split-K slices are extra tiles):
 //   warp 0      TMA producer   (one elected lane; STAGES-deep ring of 128x64 A and BNx64 B tiles, runs ahead
 //                               across tile boundaries)
 //   warp 1      TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma into one of TWO accumulator
 //                               stages of BN columns, so tile i+1 is multiplied while tile i is drained)
-//   warps 2..9  epilogue       (8 warps; warp w owns TMEM lanes 32*(w%4).. and every other 32-column chunk:
-//                               tcgen05.ld 32 lanes x 32 columns -> per-warp shared-memory transpose -> each
-//                               lane handles 8 consecutive columns of a row, so residual / mask loads and the
-//                               output stores are coalesced 128-bit accesses with 4 independent rows in flight
-//                               -> bias / ReLU / dropout / residual -> global, or fp32 red.add for split-K)
+//   warps 2..9  epilogue       (8 warps; warp w owns TMEM lanes 32*(w%4).. and every other 32-column chunk.  A thread
+//                               owns ONE output row: tcgen05.ld gives it 32 consecutive fp32 columns, which it runs
+//                               through bias / ReLU / ReLU-mask / dropout / residual in registers, packs, and writes
+//                               into a 128-byte-swizzled staging panel in shared memory; one elected thread per
+//                               panel then issues a TMA tensor store (or fp32 reduce-add for split-K / accumulate),
+//                               double-buffered so stores drain while the next panel is computed.  TMA clips ragged
+//                               M / N edges and maps convolution pixel boxes back to NHWC, so the epilogue has no
+//                               per-row address arithmetic at all.)
+//   warp 10     residual producer (bf16 residual tiles of the ResNet block tails, TMA-loaded panel by panel into a
+//                               two-slot ring so the HBM latency of the epilogue's reads is covered by bytes in flight,
+//                               not by registers; fp32 residuals / ReLU masks of the token GEMMs are L2-resident and
+//                               are read directly, one full 128-byte line per thread)
 // Operands may be K-major or MN-major in global memory (instruction-descriptor transpose bits), so
 // forward (X W^T), dgrad (dY W) and wgrad (dY^T X) all run on this kernel without any transposed copy.
 // A may also be an implicit-GEMM convolution operand: NHWC activations read through a 4-D tensor map,
@@ -32,10 +39,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 32 * (2 + kEpiWarps);
+constexpr int kThreads = 32 * (3 + kEpiWarps);   // producer, MMA, 8 epilogue, residual producer
 constexpr int kChunkBytes = BK * 128;   // one 64-wide MN-major chunk: 64 k-rows x 128 B
-constexpr int kStgStride = 36;          // floats per staged row (32 + 4 pad: conflict-free v4 both ways)
-constexpr int kStgFloats = 32 * kStgStride;
+constexpr int kPanelBytes = BM * 128;   // staging panel: 128 rows x 128 B (32 fp32 or 64 bf16 columns)
 
 template <int BN, int STAGES>
 struct Cfg {
@@ -43,14 +49,14 @@ struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_OFF = STAGES * STAGE_BYTES;
-  static constexpr int STG_BYTES = kEpiWarps * kStgFloats * 4;
+  // four panels: fp32 output -> two double-buffered panels per column-half group; bf16 output -> a double-buffered
+  // output panel [0, 2) and the two-slot bf16 residual ring [2, 4)
+  static constexpr int STG_BYTES = 4 * kPanelBytes;
   static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
-  static constexpr int NBARS = 2 * STAGES + 4;  // full[], empty[], tmem_full[2], tmem_empty[2]
+  static constexpr int NBARS = 2 * STAGES + 8;  // full[], empty[], tmem_full[2], tmem_empty[2], res_full[2], res_empty[2]
   static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * BN;      // two accumulator stages (128, 256 or 512 columns)
 };
-
-__device__ __forceinline__ float bf16_bits_to_float(uint32_t lo16) { return __uint_as_float(lo16 << 16); }
 
 struct TileCoord {
   int m0;             // first output row (linear outputs)
@@ -89,60 +95,10 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int t, cons
   return tc;
 }
 
-// Linear output row of tile row `row` (pixel boxes for convolutions) and whether it exists.
-__device__ __forceinline__ long long output_row(const GemmParams& p, const TileCoord& tc, int row, bool* ok) {
-  if (p.out_pixels) {
-    const int t1 = fast_div(row, p.fd_bx_w);
-    const int wi = row - t1 * p.bx_w;
-    const int ni = fast_div(t1, p.fd_bx_h);
-    const int hi = t1 - ni * p.bx_h;
-    const int ow = tc.pw0 + wi, oh = tc.ph0 + hi, on = tc.pn0 + ni;
-    *ok = (ni < p.bx_n) && ow < p.Wo && oh < p.Ho && on < p.Nimg;
-    return (static_cast<long long>(on) * p.Ho + oh) * p.Wo + ow;
-  }
-  *ok = (tc.m0 + row) < p.M;
-  return tc.m0 + row;
-}
-
-// Scalar, fully run-time epilogue for one row x 8 columns (ragged N tail / unaligned tensors).  Out of line
-// on purpose: it is cold, and inlining it four times made the epilogue warps instruction-fetch bound.
-__device__ __noinline__ void epilogue_slow_row(const GemmParams& p, const float* sp, long long orow, int n,
-                                               bool add_bias, bool add_res, unsigned long long seed,
-                                               unsigned long long offset, uint32_t thresh, float keep_scale) {
-  const Philox8 rnd = (p.drop_p > 0.f)
-                          ? philox8(seed, offset, p.drop_sid, (static_cast<unsigned long long>(orow) * p.N + n) >> 3)
-                          : Philox8();
-  for (int i = 0; i < 8; ++i) {
-    if (n + i >= p.N) break;
-    float v = sp[i] * p.alpha;
-    if (add_bias) v += __ldg(p.bias + n + i);
-    float rs = 0.f;
-    if (add_res) {
-      rs = p.res_fp32 ? reinterpret_cast<const float*>(p.residual)[orow * p.ldr + n + i]
-                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[orow * p.ldr + n + i]);
-    }
-    if (p.res_first) v += rs;
-    if (p.relu) v = fmaxf(v, 0.f);
-    if (p.relu_mask != nullptr && !(__bfloat162float(p.relu_mask[orow * p.ldm + n + i]) > 0.f)) v = 0.f;
-    if (p.drop_p > 0.f) v = (rnd.u16(i) < thresh) ? 0.f : v * keep_scale;
-    if (!p.res_first) v += rs;
-    if (p.out_fp32) {
-      float* op = reinterpret_cast<float*>(p.out) + orow * p.ldo + n + i;
-      if (p.atomic_out) atomicAdd(op, v);
-      else *op = v;
-    } else {
-      reinterpret_cast<__nv_bfloat16*>(p.out)[orow * p.ldo + n + i] = __float2bfloat16_rn(v);
-    }
-  }
-}
-
 }  // namespace
 
-// EPI: compile-time epilogue variant (bit 0 fp32 output, bits 1-2 residual: 0 none / 1 bf16 / 2 fp32, bit 3
-// ReLU-mask, bit 4 dropout, bit 5 fp32 red.add output); EPI_GENERIC keeps every switch at run time.  The
-// specialised variants exist because the fully general epilogue is ~70 KB of SASS and its eight warps
-// were instruction-fetch bound (ncu: stall_no_inst on most epilogue instructions).
-constexpr int EPI_GENERIC = 0xFF;
+// EPI: compile-time epilogue variant (bit 0 fp32 output, bits 1-2 residual: 0 none / 1 bf16 through the TMA ring /
+// 2 fp32 read directly, bit 3 ReLU-mask, bit 4 dropout, bit 5 fp32 reduce-add output).
 __host__ __device__ constexpr int epi_code(bool out_fp32, int res, bool mask, bool drop, bool atomic) {
   return (out_fp32 ? 1 : 0) | (res << 1) | (mask ? 8 : 0) | (drop ? 16 : 0) | (atomic ? 32 : 0);
 }
@@ -150,9 +106,16 @@ __host__ __device__ constexpr int epi_code(bool out_fp32, int res, bool mask, bo
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                     const __grid_constant__ GemmParams p, const FastDiv fd_tiles_m, const FastDiv fd_tiles_n,
                     const int splits) {
   using C = Cfg<BN, STAGES>;
+  constexpr bool kOutF32 = (EPI & 1) != 0;
+  constexpr int kRes = (EPI >> 1) & 3;
+  constexpr bool kMask = (EPI & 8) != 0;
+  constexpr bool kDrop = (EPI & 16) != 0;
+  constexpr bool kAtomic = (EPI & 32) != 0;
+  static_assert(!(kRes == 1 && kOutF32), "a bf16 residual (TMA ring) is only combined with bf16 output");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -161,6 +124,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  auto res_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 4 + a); };
+  auto res_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 6 + a); };
   const uint32_t tmem_slot = bar_base + 8u * C::NBARS;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + C::BAR_OFF + 8 * C::NBARS);
 
@@ -173,6 +138,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    if (kRes == 1) tma_prefetch_desc(&tmRes);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -180,6 +147,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
       mbar_init(tmem_empty_bar(a), kEpiWarps);
+      mbar_init(res_full_bar(a), 1);
+      mbar_init(res_empty_bar(a), kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -288,257 +257,228 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
+  } else if (warp == 2 + kEpiWarps) {
+    // ================================ bf16 residual producer =================================
+    if (kRes == 1 && lane == 0) {
+      const uint32_t ring = smem_base + C::STG_OFF + 2 * kPanelBytes;
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN);
+        if (tc.kb_begin != 0) continue;             // the residual is added by the first k-slice only
+        for (int pn = 0; pn < BN / 64; ++pn) {
+          const int n = tc.n0 + pn * 64;
+          if (n >= p.N) break;
+          mbar_wait(res_empty_bar(slot), phase ^ 1u);
+          mbar_expect_tx(res_full_bar(slot), static_cast<uint32_t>(p.res_tx_bytes));
+          if (p.out_pixels) tma_load_4d(ring + slot * kPanelBytes, &tmRes, res_full_bar(slot), n, tc.pw0, tc.ph0, tc.pn0);
+          else tma_load_2d(ring + slot * kPanelBytes, &tmRes, res_full_bar(slot), n, tc.m0);
+          if (++slot == 2) { slot = 0; phase ^= 1u; }
+        }
+      }
+    }
   } else {
     // ===================================== epilogue ==========================================
     const int ew = warp - 2;             // 0..7
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int half = ew >> 2;            // which alternating 32-column chunks this warp drains
-    float* stg = reinterpret_cast<float*>(smem_gen + C::STG_OFF) + ew * kStgFloats;
-    const int cg = lane & 3;             // 8-column group inside the 32-column chunk
-    const int rsub = lane >> 2;          // row inside an 8-row slab
+    const int row = q * 32 + lane;       // tile row owned by this thread
+    const int sw = row & 7;              // 128B-swizzle phase of that row
+    uint8_t* stg_gen = smem_gen + C::STG_OFF;
+    const uint32_t stg = smem_base + C::STG_OFF;
+    const uint32_t row_off = static_cast<uint32_t>((row >> 3) * 1024 + sw * 128);
+    // fp32 output: each column-half group (4 warps) owns two panels; bf16 output: all 8 warps share two panels
+    const int panel0 = kOutF32 ? 2 * half : 0;
+    const bool issuer = (q == 0 && lane == 0 && (kOutF32 || half == 0));
+    const uint32_t bar_id = kOutF32 ? 1u + half : 1u;
+    const uint32_t bar_threads = kOutF32 ? 128u : 256u;
 
-    constexpr bool G = (EPI == EPI_GENERIC);
-    const bool f_out_fp32 = G ? (p.out_fp32 != 0) : ((EPI & 1) != 0);
-    const bool f_has_res = G ? (p.residual != nullptr) : (((EPI >> 1) & 3) != 0);
-    const bool f_res_fp32 = G ? (p.res_fp32 != 0) : (((EPI >> 1) & 3) == 2);
-    const bool f_mask = G ? (p.relu_mask != nullptr) : ((EPI & 8) != 0);
-    const bool f_drop = G ? (p.drop_p > 0.f) : ((EPI & 16) != 0);
-    const bool f_atomic = G ? (p.atomic_out != 0) : ((EPI & 32) != 0);
     unsigned long long seed = 0, offset = 0;
     uint32_t thresh = 0;
     float keep_scale = 1.f;
-    if (f_drop) {
+    if (kDrop) {
       seed = p.rng[0]; offset = p.rng[1];
       thresh = drop_threshold(p.drop_p);
       keep_scale = 1.f / (1.f - p.drop_p);
     }
-    const bool out_vec = f_out_fp32 ? ((p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
-                                    : ((p.ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
-    const bool res_vec = !f_has_res ? false
-                         : (f_res_fp32 ? ((p.ldr & 3) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)
-                                       : ((p.ldr & 7) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0));
-    const bool msk_vec = f_mask && (p.ldm & 7) == 0 &&
-                         (reinterpret_cast<uintptr_t>(p.relu_mask) & 15) == 0;
-
-    // Prefetch registers: residual (bf16: first uint4; fp32: both) and ReLU-mask vectors of the NEXT chunk this
-    // lane will finish.  They are issued one whole chunk ahead (across tile boundaries), so the HBM latency
-    // of the epilogue's reads hides behind the TMEM drain, the math and the stores of the current chunk.
-    struct Rows { long long row[4]; bool ok[4]; bool add_bias, add_res; int n0, num_kb; };
-    uint4 pf_res[4][2];
-    uint4 pf_msk[4];
-    auto rows_of = [&](int t, Rows& r) {
-      const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN);
-      const bool first_split = (tc.kb_begin == 0);
-      r.add_bias = p.bias != nullptr && first_split;
-      r.add_res = f_has_res && first_split;
-      r.n0 = tc.n0;
-      r.num_kb = tc.num_kb;
-#pragma unroll
-      for (int it = 0; it < 4; ++it) r.row[it] = output_row(p, tc, q * 32 + it * 8 + rsub, &r.ok[it]);
-    };
-    auto fast_ok = [&](int n) {
-      return (n + 8) <= p.N && out_vec && (!f_has_res || res_vec) && (!f_mask || msk_vec);
-    };
-    auto prefetch = [&](const Rows& r, int c) {
-      const int n = r.n0 + c * 32 + cg * 8;
-      if (!(f_has_res || f_mask) || !fast_ok(n)) return;
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        if (!r.ok[it]) continue;
-        if (r.add_res) {
-          if (f_res_fp32) {
-            const uint4* rp = reinterpret_cast<const uint4*>(
-                reinterpret_cast<const float*>(p.residual) + r.row[it] * p.ldr + n);
-            pf_res[it][0] = __ldg(rp);
-            pf_res[it][1] = __ldg(rp + 1);
-          } else {
-            pf_res[it][0] = __ldg(reinterpret_cast<const uint4*>(
-                reinterpret_cast<const __nv_bfloat16*>(p.residual) + r.row[it] * p.ldr + n));
-          }
-        }
-        if (f_mask) pf_msk[it] = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + r.row[it] * p.ldm + n));
-      }
-    };
-
-    // One tile ahead, pull the residual / mask lines this lane will read into L2 (fire-and-forget, no
-    // registers): the register prefetch above then hits L2 instead of HBM, i.e. ~3x shorter latency for the
-    // same bytes in flight (the epilogue-bound 1x1 convolutions were capped at ~2.2 TB/s by Little's law).
-    auto l2_prefetch_tile = [&](const Rows& r) {
-      if (!(f_has_res || f_mask)) return;
-#pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
-        const int n = r.n0 + c * 32 + cg * 8;
-        if (!fast_ok(n)) continue;
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          if (!r.ok[it]) continue;
-          if (r.add_res) {
-            const char* a = f_res_fp32
-                ? reinterpret_cast<const char*>(reinterpret_cast<const float*>(p.residual) + r.row[it] * p.ldr + n)
-                : reinterpret_cast<const char*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + r.row[it] * p.ldr + n);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-          }
-          if (f_mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.relu_mask + r.row[it] * p.ldm + n));
-        }
-      }
-    };
 
     int acc = 0;
     uint32_t acc_phase = 0;
-    Rows cur;
-    int t = blockIdx.x;
-    if (t < total_tiles) {
-      rows_of(t, cur);
-      prefetch(cur, half);
-    }
-    for (; t < total_tiles; t += gridDim.x) {
-      mbar_wait(tmem_full_bar(acc), acc_phase);
-      tc_fence_after();
+    int buf = 0;                          // staging double buffer
+    int rslot = 0;                        // residual ring position
+    uint32_t rphase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN);
+      const bool first_split = (tc.kb_begin == 0);
+      const bool add_bias = p.bias != nullptr && first_split;
+      const bool add_res = kRes != 0 && first_split;
+      const long long grow = static_cast<long long>(tc.m0) + row;     // global row (linear outputs)
+      const bool row_ok = grow < p.M;
       const uint32_t t_tile = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
-      Rows nxt = cur;
+      bool waited = false;
 
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
-        const int nc0 = cur.n0 + c * 32;
+        const int n = tc.n0 + c * 32;
         const bool last_chunk = (c + 2 >= BN / 32);
-        uint32_t accr[32];
-        if (cur.num_kb > 0) {
-          tmem_ld_32x32(t_tile + static_cast<uint32_t>(c * 32), accr);
-          tmem_ld_wait();
-        } else {
+        // uniform over the barrier group: fp32 panels are one chunk wide, bf16 panels two (one per column half)
+        const bool active = kOutF32 ? (n < p.N) : ((n & ~63) < p.N);
+        float v[32];
+        // ---- directly read operands of this chunk are requested before the accumulator is waited for ----
+        uint4 rres[8];
+        uint4 rmsk[4];
+        if (kRes == 2 && active && add_res && row_ok) {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) + grow * p.ldr + n);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) accr[i] = 0u;
+          for (int k = 0; k < 8; ++k) rres[k] = __ldg(rp + k);
+        }
+        if (kMask && active && row_ok) {
+          const uint4* mp = reinterpret_cast<const uint4*>(p.relu_mask + grow * p.ldm + n);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rmsk[k] = __ldg(mp + k);
+        }
+        if (!waited) {
+          mbar_wait(tmem_full_bar(acc), acc_phase);
+          tc_fence_after();
+          waited = true;
+        }
+        if (active) {
+          uint32_t accr[32];
+          if (tc.num_kb > 0) {
+            tmem_ld_32x32(t_tile + static_cast<uint32_t>(c * 32), accr);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) accr[i] = 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(accr[i]) * p.alpha;
         }
         if (last_chunk) {
           // all of this warp's TMEM reads of the tile are done: hand the accumulator stage back
           tc_fence_before();
+          __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
-          if (t + static_cast<int>(gridDim.x) < total_tiles) {
-            rows_of(t + gridDim.x, nxt);
-            l2_prefetch_tile(nxt);
-          }
         }
-        const int n = nc0 + cg * 8;
-        const bool active = nc0 < p.N;            // warp-uniform
         if (active) {
-          // ---- transpose through shared memory: lane (= tile row) writes its 32 columns ----
+          if (add_bias) {
+            if (n + 32 <= p.N) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stg + lane * kStgStride + 4 * j) =
-                make_uint4(accr[4 * j], accr[4 * j + 1], accr[4 * j + 2], accr[4 * j + 3]);
-        }
-        __syncwarp();
-        const bool fast = active && n < p.N && fast_ok(n);
-        float v[4][8];
-        if (fast) {
-          float bias8[8];
-          if (cur.add_bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + 1);
-            bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
-            bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) bias8[i] = 0.f;
-          }
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            if (!cur.ok[it]) continue;
-            {
-              const float* sp = stg + (it * 8 + rsub) * kStgStride + cg * 8;
-              const float4 a0 = *reinterpret_cast<const float4*>(sp);
-              const float4 a1 = *reinterpret_cast<const float4*>(sp + 4);
-              v[it][0] = a0.x; v[it][1] = a0.y; v[it][2] = a0.z; v[it][3] = a0.w;
-              v[it][4] = a1.x; v[it][5] = a1.y; v[it][6] = a1.z; v[it][7] = a1.w;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[it][i] = v[it][i] * p.alpha + bias8[i];
-            float rs[8];
-            if (cur.add_res) {
-              if (f_res_fp32) {
-                rs[0] = __uint_as_float(pf_res[it][0].x); rs[1] = __uint_as_float(pf_res[it][0].y);
-                rs[2] = __uint_as_float(pf_res[it][0].z); rs[3] = __uint_as_float(pf_res[it][0].w);
-                rs[4] = __uint_as_float(pf_res[it][1].x); rs[5] = __uint_as_float(pf_res[it][1].y);
-                rs[6] = __uint_as_float(pf_res[it][1].z); rs[7] = __uint_as_float(pf_res[it][1].w);
-              } else {
-                const uint32_t rw[4] = {pf_res[it][0].x, pf_res[it][0].y, pf_res[it][0].z, pf_res[it][0].w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) rs[i] = bf16_bits_to_float((rw[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu);
+              for (int k = 0; k < 8; ++k) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + k);
+                v[4 * k] += b4.x; v[4 * k + 1] += b4.y; v[4 * k + 2] += b4.z; v[4 * k + 3] += b4.w;
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) rs[i] = 0.f;
+              for (int i = 0; i < 32; ++i)
+                if (n + i < p.N) v[i] += __ldg(p.bias + n + i);
             }
+          }
+          if (kRes == 1 && add_res) {
+            // bf16 residual panel (64 columns) from the TMA ring; this warp's chunk is one 64-byte half of the row
+            mbar_wait(res_full_bar(rslot), rphase);
+            const uint8_t* rrow = stg_gen + (2 + rslot) * kPanelBytes + row_off;
+            float rs[32];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rrow + ((((c & 1) * 4 + k) ^ sw) << 4));
+              float f8[8];
+              unpack_bf16x8(u, f8);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) rs[8 * k + i] = f8[i];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(res_empty_bar(rslot));
+            if (++rslot == 2) { rslot = 0; rphase ^= 1u; }
             if (p.res_first) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[it][i] += rs[i];
-            }
-            if (p.relu) {
+              for (int i = 0; i < 32; ++i) v[i] += rs[i];
+              if (p.relu) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[it][i] = fmaxf(v[it][i], 0.f);
-            }
-            if (f_mask) {
-              const uint32_t mw[4] = {pf_msk[it].x, pf_msk[it].y, pf_msk[it].z, pf_msk[it].w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float mf = bf16_bits_to_float((mw[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu);
-                if (!(mf > 0.f)) v[it][i] = 0.f;
-              }
-            }
-            if (f_drop) {
-              const unsigned long long idx = static_cast<unsigned long long>(cur.row[it]) * p.N + n;
-              const Philox8 rnd = philox8(seed, offset, p.drop_sid, idx >> 3);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[it][i] = (rnd.u16(i) < thresh) ? 0.f : v[it][i] * keep_scale;
-            }
-            if (!p.res_first) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[it][i] += rs[i];
-            }
-          }
-        }
-        // the prefetch registers are consumed: issue the next chunk's loads before this chunk's stores
-        if (!last_chunk) prefetch(cur, c + 2);
-        else if (t + static_cast<int>(gridDim.x) < total_tiles) prefetch(nxt, half);
-
-        if (fast) {
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            if (!cur.ok[it]) continue;
-            const long long orow = cur.row[it];
-            if (f_out_fp32) {
-              float* op = reinterpret_cast<float*>(p.out) + orow * p.ldo + n;
-              if (f_atomic) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) atomicAdd(op + i, v[it][i]);
-              } else {
-                reinterpret_cast<float4*>(op)[0] = make_float4(v[it][0], v[it][1], v[it][2], v[it][3]);
-                reinterpret_cast<float4*>(op)[1] = make_float4(v[it][4], v[it][5], v[it][6], v[it][7]);
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
               }
             } else {
-              uint4 pk;
-              __nv_bfloat162 t2;
-              t2 = __floats2bfloat162_rn(v[it][0], v[it][1]); pk.x = *reinterpret_cast<uint32_t*>(&t2);
-              t2 = __floats2bfloat162_rn(v[it][2], v[it][3]); pk.y = *reinterpret_cast<uint32_t*>(&t2);
-              t2 = __floats2bfloat162_rn(v[it][4], v[it][5]); pk.z = *reinterpret_cast<uint32_t*>(&t2);
-              t2 = __floats2bfloat162_rn(v[it][6], v[it][7]); pk.w = *reinterpret_cast<uint32_t*>(&t2);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n) = pk;
+              if (p.relu) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += rs[i];
+            }
+          } else {
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
             }
           }
-        } else if (active && n < p.N) {
-          // ragged column tail or unaligned tensors: scalar path, out of line (rare: N = 170 classifier)
+          if (kMask) {
+            if (row_ok) {
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            if (!cur.ok[it]) continue;
-            epilogue_slow_row(p, stg + (it * 8 + rsub) * kStgStride + cg * 8, cur.row[it], n, cur.add_bias,
-                              cur.add_res, seed, offset, thresh, keep_scale);
+              for (int k = 0; k < 4; ++k) {
+                float f8[8];
+                unpack_bf16x8(rmsk[k], f8);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (!(f8[i] > 0.f)) v[8 * k + i] = 0.f;
+              }
+            }
           }
+          if (kDrop) {
+            const unsigned long long idx = static_cast<unsigned long long>(grow) * p.N + n;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const Philox8 rnd = philox8(seed, offset, p.drop_sid, (idx >> 3) + k);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[8 * k + i] = (rnd.u16(i) < thresh) ? 0.f : v[8 * k + i] * keep_scale;
+            }
+          }
+          if (kRes == 2 && add_res && row_ok) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              v[4 * k] += __uint_as_float(rres[k].x); v[4 * k + 1] += __uint_as_float(rres[k].y);
+              v[4 * k + 2] += __uint_as_float(rres[k].z); v[4 * k + 3] += __uint_as_float(rres[k].w);
+            }
+          }
+          // ---- stage the row into the swizzled panel ----
+          if (kOutF32) {
+            uint8_t* prow = stg_gen + (panel0 + buf) * kPanelBytes + row_off;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<float4*>(prow + ((k ^ sw) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          } else {
+            uint8_t* prow = stg_gen + (panel0 + buf) * kPanelBytes + row_off;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint4 u;
+              u.x = pack_bf16x2(v[8 * k + 0], v[8 * k + 1]);
+              u.y = pack_bf16x2(v[8 * k + 2], v[8 * k + 3]);
+              u.z = pack_bf16x2(v[8 * k + 4], v[8 * k + 5]);
+              u.w = pack_bf16x2(v[8 * k + 6], v[8 * k + 7]);
+              *reinterpret_cast<uint4*>(prow + ((((c & 1) * 4 + k) ^ sw) << 4)) = u;
+            }
+          }
+          fence_proxy_async_smem();
+          // the previous store from the OTHER buffer must have finished reading before anyone refills it
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(bar_id, bar_threads);
+          if (issuer) {
+            const uint32_t src = stg + (panel0 + buf) * kPanelBytes;
+            const int pn = kOutF32 ? n : (n & ~63);
+            if (p.out_pixels) {
+              tma_store_4d(&tmOut, src, pn, tc.pw0, tc.ph0, tc.pn0);
+            } else if (kAtomic) {
+              tma_reduce_add_2d(&tmOut, src, pn, tc.m0);
+            } else {
+              tma_store_2d(&tmOut, src, pn, tc.m0);
+            }
+            tma_store_commit();
+          }
+          buf ^= 1;
         }
-        __syncwarp();  // staging buffer is rewritten by the next chunk
       }
-      cur = nxt;
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (issuer) tma_store_wait_all<0>();
   }
 
   // ---- teardown --------------------------------------------------------------------------------
@@ -563,8 +503,8 @@ inline int sm_count() {
 }
 
 template <int BN, int STAGES, int EPI>
-int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int tiles_m, int tiles_n,
-                int splits, cudaStream_t stream) {
+int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
+                const GemmParams& p, int tiles_m, int tiles_n, int splits, cudaStream_t stream) {
   using C = Cfg<BN, STAGES>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;  // per-process; all devices share the same kernel image attributes
@@ -577,20 +517,20 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
   }
   const int total = tiles_m * tiles_n * splits;
   const int grid = total < sm_count() ? total : sm_count();
-  launch_pdl(gemm_tcgen05_kernel<BN, STAGES, EPI>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, tmA, tmB, p,
-             make_fastdiv(tiles_m), make_fastdiv(tiles_n), splits);
+  launch_pdl(gemm_tcgen05_kernel<BN, STAGES, EPI>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, tmA, tmB, tmOut,
+             tmRes, p, make_fastdiv(tiles_m), make_fastdiv(tiles_n), splits);
   return static_cast<int>(cudaGetLastError());
 }
 
 // one translation unit per tile width instantiates these variants (compile time)
 template <int BN, int STAGES>
-int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int tiles_m, int tiles_n,
-              int splits, cudaStream_t stream) {
+int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
+              const GemmParams& p, int tiles_m, int tiles_n, int splits, cudaStream_t stream) {
   const int res = p.residual == nullptr ? 0 : (p.res_fp32 ? 2 : 1);
   const int code = epi_code(p.out_fp32 != 0, res, p.relu_mask != nullptr, p.drop_p > 0.f, p.atomic_out != 0);
 #define VQA_EPI_CASE(o, r, m, d, a)                                                                   \
   case epi_code(o, r, m, d, a):                                                                       \
-    return launch_impl<BN, STAGES, epi_code(o, r, m, d, a)>(tmA, tmB, p, tiles_m, tiles_n, splits, stream);
+    return launch_impl<BN, STAGES, epi_code(o, r, m, d, a)>(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, splits, stream);
   switch (code) {
     VQA_EPI_CASE(false, 0, false, false, false)  // bf16 out                      (qkv, convs, plain dgrad)
     VQA_EPI_CASE(false, 1, false, false, false)  // bf16 out + bf16 residual      (ResNet block tails)
@@ -599,11 +539,12 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& 
     VQA_EPI_CASE(false, 0, true, true, false)    // bf16 out + ReLU mask + dropout (training)
     VQA_EPI_CASE(true, 2, false, false, false)   // fp32 out + fp32 residual      (residual streams)
     VQA_EPI_CASE(true, 2, false, true, false)    //   ... + dropout
-    VQA_EPI_CASE(true, 2, false, false, true)    //   ... accumulated with red.add
+    VQA_EPI_CASE(true, 2, false, false, true)    //   ... accumulated with reduce-add
     VQA_EPI_CASE(true, 0, false, false, false)   // fp32 out                      (wgrad, logits)
-    VQA_EPI_CASE(true, 0, false, false, true)    // fp32 red.add                  (split-K)
+    VQA_EPI_CASE(true, 0, false, true, false)    // fp32 out + dropout
+    VQA_EPI_CASE(true, 0, false, false, true)    // fp32 reduce-add               (split-K, accumulate)
     default:
-      return launch_impl<BN, STAGES, EPI_GENERIC>(tmA, tmB, p, tiles_m, tiles_n, splits, stream);
+      return -2;   // combination not instantiated (gemm_op_run reports it)
   }
 #undef VQA_EPI_CASE
 }

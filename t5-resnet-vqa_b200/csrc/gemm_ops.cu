@@ -47,6 +47,71 @@ void choose_box(int Wo, int Ho, int Nimg, int rows, bool exact, int* bw, int* bh
   }
 }
 
+// Epilogue-side tensor maps and argument checks shared by the three builders.  Linear outputs: [M, N] with row
+// stride ldo; convolution outputs: NHWC through the same pixel boxes the A operand was loaded with.
+int finish_output_maps(GemmOp* op, bool pixels, int Nimg, int Ho, int Wo) {
+  GemmParams& p = op->p;
+  const int esize = p.out_fp32 ? 4 : 2;
+  const uint32_t panel_cols = p.out_fp32 ? 32u : 64u;
+  if (reinterpret_cast<uintptr_t>(p.out) & 15) { set_last_error("gemm: output pointer must be 16-byte aligned"); return -1; }
+  if ((p.ldo * esize) & 15) { set_last_error("gemm: output row stride must be a multiple of 16 bytes"); return -1; }
+  if (p.residual != nullptr) {
+    if (p.N % 32) { set_last_error("gemm: a residual needs N %% 32 == 0"); return -1; }
+    if (p.res_fp32) {
+      if (pixels) { set_last_error("conv: fp32 residuals are not supported (bf16 NHWC only)"); return -1; }
+      if ((reinterpret_cast<uintptr_t>(p.residual) & 15) || (p.ldr & 3)) { set_last_error("gemm: fp32 residual must be 16-byte aligned with ldr %% 4 == 0"); return -1; }
+    } else {
+      if (p.out_fp32) { set_last_error("gemm: a bf16 residual is only supported with bf16 output"); return -1; }
+      if ((reinterpret_cast<uintptr_t>(p.residual) & 15) || (p.ldr & 7)) { set_last_error("gemm: bf16 residual must be 16-byte aligned with ldr %% 8 == 0"); return -1; }
+    }
+  }
+  if (p.relu_mask != nullptr) {
+    if (pixels || (p.N % 32) || (p.ldm & 7) || (reinterpret_cast<uintptr_t>(p.relu_mask) & 15)) {
+      set_last_error("gemm: a ReLU mask needs a linear output, N %% 32 == 0, ldm %% 8 == 0 and 16-byte alignment");
+      return -1;
+    }
+  }
+  if (p.drop_p > 0.f && (pixels || (p.N % 8))) { set_last_error("gemm: dropout needs a linear output with N %% 8 == 0"); return -1; }
+  if (p.atomic_out && pixels) { set_last_error("conv: accumulate is not supported"); return -1; }
+  int r;
+  if (!pixels) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(p.M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(p.ldo) * esize};
+    const uint32_t box[2] = {panel_cols, 128};
+    r = p.out_fp32 ? make_tmap_f32(&op->tmOut, p.out, 2, dims, strides, box, nullptr)
+                   : make_tmap_bf16(&op->tmOut, p.out, 2, dims, strides, box, nullptr);
+    if (r) return r;
+    p.res_tx_bytes = 128 * 128;
+    if (p.residual != nullptr && !p.res_fp32) {
+      const uint64_t rstrides[1] = {static_cast<uint64_t>(p.ldr) * 2};
+      r = make_tmap_bf16(&op->tmRes, p.residual, 2, dims, rstrides, box, nullptr);
+      if (r) return r;
+    } else {
+      op->tmRes = op->tmOut;
+    }
+  } else {
+    const uint64_t dims[4] = {static_cast<uint64_t>(p.N), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho),
+                              static_cast<uint64_t>(Nimg)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(p.ldo) * esize, static_cast<uint64_t>(Wo) * p.ldo * esize,
+                                 static_cast<uint64_t>(Ho) * Wo * p.ldo * esize};
+    const uint32_t box[4] = {panel_cols, static_cast<uint32_t>(p.bx_w), static_cast<uint32_t>(p.bx_h),
+                             static_cast<uint32_t>(p.bx_n)};
+    r = p.out_fp32 ? make_tmap_f32(&op->tmOut, p.out, 4, dims, strides, box, nullptr)
+                   : make_tmap_bf16(&op->tmOut, p.out, 4, dims, strides, box, nullptr);
+    if (r) return r;
+    p.res_tx_bytes = p.bx_w * p.bx_h * p.bx_n * 128;
+    if (p.residual != nullptr) {
+      const uint64_t rstrides[3] = {static_cast<uint64_t>(p.ldr) * 2, static_cast<uint64_t>(Wo) * p.ldr * 2,
+                                    static_cast<uint64_t>(Ho) * Wo * p.ldr * 2};
+      r = make_tmap_bf16(&op->tmRes, p.residual, 4, dims, rstrides, box, nullptr);
+      if (r) return r;
+    } else {
+      op->tmRes = op->tmOut;
+    }
+  }
+  return 0;
+}
+
 }  // namespace
 
 int gemm_op_init(GemmOp* op, int M, int N, int K, const void* A, long long lda, int a_mn,
@@ -72,6 +137,8 @@ int gemm_op_init(GemmOp* op, int M, int N, int K, const void* A, long long lda, 
   if (r) return r;
   if (!b_mn) r = make_tmap_2d(&op->tmB, B, N, K, ldb, 64, bn);
   else       r = make_tmap_2d(&op->tmB, B, K, N, ldb, 64, 64);
+  if (r) return r;
+  r = finish_output_maps(op, false, 0, 0, 0);
   if (r) return r;
   op->bn = bn; op->split_k = split_k < 1 ? 1 : split_k;
   op->valid = true;
@@ -133,6 +200,8 @@ int conv_op_init(GemmOp* op, const ConvGeom& g, const void* x, const void* w, vo
   }
   r = make_tmap_2d(&op->tmB, w, g.Cout, Ktot, Ktot, 64, bn);
   if (r) return r;
+  r = finish_output_maps(op, true, g.Nimg, g.Ho, g.Wo);
+  if (r) return r;
   op->bn = bn; op->split_k = 1;
   op->valid = true;
   return 0;
@@ -182,6 +251,10 @@ int conv_wgrad_op_init(GemmOp* op, const ConvGeom& g, const void* dy, const void
     int r = make_tmap_bf16(&op->tmB, x, 4, dims, strides, box, nullptr);
     if (r) return r;
   }
+  {
+    int r = finish_output_maps(op, false, 0, 0, 0);
+    if (r) return r;
+  }
   op->bn = bn; op->split_k = split_k < 1 ? 1 : split_k;
   op->valid = true;
   return 0;
@@ -198,8 +271,9 @@ int gemm_op_run(const GemmOp* op, cudaStream_t stream) {
   p.fd_tiles_w = make_fastdiv(p.tiles_w); p.fd_tiles_h = make_fastdiv(p.tiles_h);
   p.fd_bx_w = make_fastdiv(p.bx_w); p.fd_bx_h = make_fastdiv(p.bx_h);
   p.dbg_a_lbo = g_dbg[0]; p.dbg_a_sbo = g_dbg[1]; p.dbg_b_lbo = g_dbg[2]; p.dbg_b_sbo = g_dbg[3];
-  int r = launch_gemm(op->tmA, op->tmB, p, op->bn, op->split_k, stream);
-  if (r) set_last_error("gemm launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
+  int r = launch_gemm(op->tmA, op->tmB, op->tmOut, op->tmRes, p, op->bn, op->split_k, stream);
+  if (r == -2) set_last_error("gemm: this epilogue combination (output type / residual / mask / dropout / accumulate) is not built");
+  else if (r) set_last_error("gemm launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
   return r;
 }
 

@@ -21,7 +21,7 @@ struct Epilogue {
 };
 
 struct GemmOp {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmOut, tmRes;
   GemmParams p;
   int bn = 128;
   int split_k = 1;
