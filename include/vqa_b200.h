@@ -38,6 +38,9 @@ const char* vqa_last_error(void);
 int vqa_version(void);
 /* bring-up aid: override the MN-major UMMA descriptor strides (bytes); zeros restore defaults */
 int vqa_debug_set_umma(int a_lbo, int a_sbo, int b_lbo, int b_sbo);
+/* bring-up aid: GEMM / conv launches issued after this call stamp clock64() of CTA 0's phases into buf (device
+ * memory, 11 warps x 16 slots); NULL switches it off.  Immediate-mode launches only. */
+int vqa_debug_gemm_timing(long long* buf);
 
 /* ---- launch plans ------------------------------------------------------------------------------ */
 void* vqa_plan_create(void);
@@ -185,6 +188,9 @@ typedef struct {
   const long long* key_mask;
 } vqa_attn_bwd_args;
 int vqa_attention_bwd(void* plan, const vqa_attn_bwd_args* a, void* stream);
+/* bring-up aid: tcgen05 attention ops created after this call stamp clock64() of CTA 0's phases into buf
+ * (device memory, 4 warps x 16 slots); NULL switches it off */
+int vqa_debug_attn_timing(long long* buf);
 
 /* ---- SGA pieces ---------------------------------------------------------------------------------- */
 /* nn.LayerNorm(768) (model/multi_head_vision_text_attn.py:120-126) over z = x + dropout(sublayer),

@@ -19,6 +19,7 @@ namespace vqa {
 bool attention_tc_supported(int Lq, int Lk, int hd);
 int attention_tc_fwd(void* plan, const vqa_attn_fwd_args* x, void* stream);
 int attention_tc_bwd(void* plan, const vqa_attn_bwd_args* x, void* stream);
+void attention_tc_debug(long long* buf);
 }  // namespace vqa
 
 namespace {
@@ -326,6 +327,11 @@ int ensure_smem(size_t bytes, const char* what) {
 }  // namespace
 
 extern "C" {
+
+int vqa_debug_attn_timing(long long* buf) {
+  attention_tc_debug(buf);
+  return 0;
+}
 
 int vqa_attention_fwd(void* plan, const vqa_attn_fwd_args* x, void* stream) {
   if (check_common(x->Lq, x->Lk, x->hd, x->ldq, x->ldk, x->ldv, x->ldo, "attention_fwd")) return -1;

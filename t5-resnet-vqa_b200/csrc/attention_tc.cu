@@ -31,6 +31,10 @@ constexpr int kTile = 128 * 128;          // bytes of one 64-column chunk: 128 r
 constexpr int kBox = kSlot * 128;         // bytes one TMA box delivers (32 rows x 64 bf16)
 constexpr float kMaskedScore = -3.4028234663852886e38f;  // torch.finfo(float32).min (hf additive mask)
 
+#define VQA_STAMP(k) do { if (a.dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) a.dbg[(threadIdx.x >> 5) * 16 + (k)] = clock64(); } while (0)
+
+long long* g_attn_dbg = nullptr;
+
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -172,6 +176,7 @@ struct FwdP {
   float scale, drop_p;
   uint32_t sid;
   const unsigned long long* rng;
+  long long* dbg;   // bring-up: clock64 stamps of CTA 0 (vqa_debug_attn_timing), else null
 };
 
 template <int HD>
@@ -190,6 +195,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t* slot_ptr = reinterpret_cast<const uint32_t*>(gen + (3 * CH + 2) * kTile + 16);
   const int t = threadIdx.x, warp = t >> 5;
 
+  VQA_STAMP(0);
   pdl_launch_dependents();
   if (t == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -207,7 +213,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot_ptr;
+  VQA_STAMP(1);
   pdl_wait();
+  VQA_STAMP(2);
 
   const int npairs = a.B * a.H;
   if (t == 0) {
@@ -225,6 +233,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     mbar_wait(bar_tma, 0);
     tc_fence_after();
+    VQA_STAMP(3);
     const uint32_t idesc = umma_idesc_bf16(128, 128, false, false);
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
@@ -240,8 +249,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t keep = keep_bits(dc, static_cast<unsigned long long>(rc.prow) * a.Lk, a.Lk);
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
 
+  VQA_STAMP(4);
   mbar_wait(bar_mma, 0);
   tc_fence_after();
+  VQA_STAMP(5);
   float p[32];
   {
     uint32_t acc[32];
@@ -267,9 +278,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
   for (int j = 0; j < 32; ++j) p[j] = ((keep >> j) & 1u) ? p[j] * inv * dc.scale : 0.f;
   store_diag_row(Pg, t, warp, p);
+  VQA_STAMP(6);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  VQA_STAMP(7);
   if (t == 0) {
     tc_fence_after();
     const uint32_t idesc = umma_idesc_bf16(128, HD, false, true);
@@ -284,9 +297,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncwarp();
   mbar_wait(bar_mma, 1);
   tc_fence_after();
+  VQA_STAMP(8);
   __nv_bfloat16* op = a.out + (static_cast<long long>(rc.b) * a.Lq + rc.i) * a.ldo + rc.h * HD;
   store_tmem_row<HD>(tmem + lane_base + 128, op, rc.row_ok);
 
+  VQA_STAMP(9);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -306,6 +321,7 @@ struct BwdP {
   float scale, drop_p;
   uint32_t sid;
   const unsigned long long* rng;
+  long long* dbg;
 };
 
 template <int HD>
@@ -330,6 +346,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t* slot_ptr = reinterpret_cast<const uint32_t*>(gen + (4 * CH + 4) * kTile + 16);
   const int t = threadIdx.x, warp = t >> 5;
 
+  VQA_STAMP(0);
   pdl_launch_dependents();
   if (t == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
@@ -347,7 +364,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot_ptr;
+  VQA_STAMP(1);
   pdl_wait();
+  VQA_STAMP(2);
 
   const int npairs = a.B * a.H;
   if (t == 0) {
@@ -366,6 +385,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     mbar_wait(bar_tma, 0);
     tc_fence_after();
+    VQA_STAMP(3);
     const uint32_t idesc = umma_idesc_bf16(128, 128, false, false);
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {     // S = Q K^T
@@ -392,8 +412,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mx = st.x; inv = st.y;
   }
 
+  VQA_STAMP(4);
   mbar_wait(bar_mma, 0);
   tc_fence_after();
+  VQA_STAMP(5);
   float p[32], ds[32];
   {
     uint32_t acc[32];
@@ -440,9 +462,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   store_diag_row(Pdg, t, warp, p);
   store_diag_row(dSg, t, warp, ds);
+  VQA_STAMP(6);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  VQA_STAMP(7);
   if (t == 0) {
     tc_fence_after();
     const uint32_t id_tt = umma_idesc_bf16(128, HD, true, true);
@@ -467,6 +491,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncwarp();
   mbar_wait(bar_mma, 1);
   tc_fence_after();
+  VQA_STAMP(8);
   {
     __nv_bfloat16* qp = a.dq + (static_cast<long long>(rc.b) * a.Lq + rc.i) * a.lddq + rc.h * HD;
     store_tmem_row<HD>(tmem + lane_base + cDQ, qp, rc.row_ok);
@@ -476,6 +501,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __nv_bfloat16* vp = a.dv + (static_cast<long long>(rc.b) * a.Lk + rc.i) * a.lddv + rc.h * HD;
     store_tmem_row<HD>(tmem + lane_base + cDV, vp, key_ok);
   }
+  VQA_STAMP(9);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -503,6 +529,8 @@ int operand_map(CUtensorMap* tm, const void* base, long long rows, int H, int hd
 
 namespace vqa {
 
+void attention_tc_debug(long long* buf) { g_attn_dbg = buf; }
+
 bool attention_tc_supported(int Lq, int Lk, int hd) {
   return Lq >= 1 && Lq <= kSlot && Lk >= 1 && Lk <= kSlot && (hd == 64 || hd == 96);
 }
@@ -518,6 +546,7 @@ int attention_tc_fwd(void* plan, const vqa_attn_fwd_args* x, void* stream) {
   a.stats = x->stats; a.bias = x->bias; a.key_mask = x->key_mask;
   a.scale = x->scale; a.drop_p = x->drop_p; a.sid = x->sid;
   a.rng = reinterpret_cast<const unsigned long long*>(x->rng);
+  a.dbg = g_attn_dbg;
   const int hd = x->hd;
   static bool attr64 = false, attr96 = false;
   if (hd == 64 && !attr64) { if (raise_smem(attn_tc_fwd_kernel<64>, fwd_smem_bytes<64>(), "attention_fwd")) return -1; attr64 = true; }
@@ -546,6 +575,7 @@ int attention_tc_bwd(void* plan, const vqa_attn_bwd_args* x, void* stream) {
   a.lddq = x->lddq; a.lddk = x->lddk; a.lddv = x->lddv;
   a.dbias = x->dbias; a.scale = x->scale; a.drop_p = x->drop_p; a.sid = x->sid;
   a.rng = reinterpret_cast<const unsigned long long*>(x->rng);
+  a.dbg = g_attn_dbg;
   const int hd = x->hd;
   static bool attr64 = false, attr96 = false;
   if (hd == 64 && !attr64) { if (raise_smem(attn_tc_bwd_kernel<64>, bwd_smem_bytes<64>(), "attention_bwd")) return -1; attr64 = true; }

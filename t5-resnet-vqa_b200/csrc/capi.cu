@@ -16,6 +16,11 @@ int vqa_debug_set_umma(int a_lbo, int a_sbo, int b_lbo, int b_sbo) {
   return 0;
 }
 
+int vqa_debug_gemm_timing(long long* buf) {
+  gemm_debug_set_clock(buf);
+  return 0;
+}
+
 int vqa_gemm_bf16(void* plan, const vqa_gemm_args* a, void* stream) {
   Epilogue e;
   e.bias = a->bias; e.relu = a->relu;

@@ -32,6 +32,8 @@
 #include "ptx.cuh"
 #include "rng.cuh"
 
+#define VQA_GSTAMP(k) do { if (p.dbg_clk != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) p.dbg_clk[(threadIdx.x >> 5) * 16 + (k)] = clock64(); } while (0)
+
 namespace vqa {
 
 namespace {
@@ -134,6 +136,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int total_tiles = static_cast<int>(fd_tiles_m.d * fd_tiles_n.d) * splits;
 
   // ---- one-time setup (overlaps the previous kernel's tail under programmatic dependent launch) ----
+  VQA_GSTAMP(0);
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -160,7 +163,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  VQA_GSTAMP(1);
   pdl_wait();   // nothing above touches global memory; everything below may
+  VQA_GSTAMP(2);
 
   if (warp == 0) {
     // ===================================== TMA producer ======================================
@@ -242,6 +247,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int i = 0; i < tc.num_kb; ++i) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (i == 0 && t == static_cast<int>(blockIdx.x)) VQA_GSTAMP(3);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + C::A_BYTES;
 #pragma unroll
@@ -254,6 +260,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tmem_full_bar(acc));  // accumulator complete (fires immediately when num_kb == 0)
+        if (t == static_cast<int>(blockIdx.x)) VQA_GSTAMP(4);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -341,6 +348,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(tmem_full_bar(acc), acc_phase);
           tc_fence_after();
           waited = true;
+          if (t == static_cast<int>(blockIdx.x)) VQA_GSTAMP(5);
         }
         if (active) {
           uint32_t accr[32];
@@ -478,12 +486,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    VQA_GSTAMP(6);
     if (issuer) tma_store_wait_all<0>();
+    VQA_GSTAMP(7);
   }
 
   // ---- teardown --------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+  VQA_GSTAMP(8);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);

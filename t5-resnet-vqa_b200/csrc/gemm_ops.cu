@@ -261,6 +261,8 @@ int conv_wgrad_op_init(GemmOp* op, const ConvGeom& g, const void* dy, const void
 }
 
 static int g_dbg[4] = {0, 0, 0, 0};
+static long long* g_dbg_clk = nullptr;
+void gemm_debug_set_clock(long long* buf) { g_dbg_clk = buf; }
 void gemm_debug_set_umma(int a_lbo, int a_sbo, int b_lbo, int b_sbo) {
   g_dbg[0] = a_lbo; g_dbg[1] = a_sbo; g_dbg[2] = b_lbo; g_dbg[3] = b_sbo;
 }
@@ -270,6 +272,7 @@ int gemm_op_run(const GemmOp* op, cudaStream_t stream) {
   GemmParams p = op->p;
   p.fd_tiles_w = make_fastdiv(p.tiles_w); p.fd_tiles_h = make_fastdiv(p.tiles_h);
   p.fd_bx_w = make_fastdiv(p.bx_w); p.fd_bx_h = make_fastdiv(p.bx_h);
+  p.dbg_clk = g_dbg_clk;
   p.dbg_a_lbo = g_dbg[0]; p.dbg_a_sbo = g_dbg[1]; p.dbg_b_lbo = g_dbg[2]; p.dbg_b_sbo = g_dbg[3];
   int r = launch_gemm(op->tmA, op->tmB, op->tmOut, op->tmRes, p, op->bn, op->split_k, stream);
   if (r == -2) set_last_error("gemm: this epilogue combination (output type / residual / mask / dropout / accumulate) is not built");

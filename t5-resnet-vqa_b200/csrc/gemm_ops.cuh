@@ -56,5 +56,7 @@ int gemm_op_run(const GemmOp* op, cudaStream_t stream);
 
 // bring-up only: override MN-major descriptor strides (bytes); zeros restore the defaults
 void gemm_debug_set_umma(int a_lbo, int a_sbo, int b_lbo, int b_sbo);
+// bring-up only: GEMM launches issued after this call stamp clock64() of CTA 0's phases into buf (11 warps x 16)
+void gemm_debug_set_clock(long long* buf);
 
 }  // namespace vqa

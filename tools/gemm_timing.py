@@ -1,0 +1,32 @@
+"""Phase timing (clock64 of CTA 0) of the tcgen05 GEMM kernel on the step's shapes.  Diagnostic only."""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import t5_resnet_vqa_b200 as pkg
+from util import Caller
+C = Caller(pkg); lib = pkg.lib.load()
+BF = torch.bfloat16; dev = "cuda"
+names = ["start", "setup done", "pdl_wait done", "first stage full (mma)", "tile0 mma committed", "tile0 acc ready (epi)", "epi loop done", "stores drained", "teardown sync"]
+shapes = [("fwd", 2048, 768, 768, 128, 0), ("fwd", 2048, 768, 768, 128, 1), ("fwd", 2048, 2304, 768, 256, 0), ("fwd", 2048, 768, 3072, 128, 1),
+          ("wgrad", 768, 768, 2048, 64, 1), ("wgrad", 3072, 768, 2048, 128, 1)]
+for kind, M, N, K, bn, fp32 in shapes:
+    A = torch.randn(M, K, device=dev).to(BF); B = torch.randn(N, K, device=dev).to(BF)
+    At, Bt = A.t().contiguous(), B.t().contiguous()
+    out = torch.empty(M, N, device=dev, dtype=torch.float32 if fp32 else BF)
+    res = torch.randn(M, N, device=dev) if (fp32 and kind == "fwd") else None
+    buf = torch.zeros(11 * 16, dtype=torch.int64, device=dev)
+    for it in range(3):
+        if it == 2:
+            lib.vqa_debug_gemm_timing(buf.data_ptr())
+        if kind == "fwd":
+            C.gemm(M, N, K, A, K, 0, B, K, 0, out, N, fp32, bn=bn, residual=res, ldr=N, res_fp32=1)
+        else:
+            C.gemm(M, N, K, At, M, 1, Bt, N, 1, out, N, fp32, bn=bn)
+        torch.cuda.synchronize()
+    lib.vqa_debug_gemm_timing(None)
+    t = buf.cpu().view(11, 16)
+    t0 = int(t[0, 0])
+    print("%s M%d N%d K%d bn%d fp32=%d   cycles since start: producer(w0) mma(w1) epi(w2) epi(w9)" % (kind, M, N, K, bn, fp32))
+    for i, n in enumerate(names):
+        print("   %-26s" % n + "".join("%9s" % (str(int(t[w, i]) - t0) if int(t[w, i]) else "-") for w in (0, 1, 2, 9)))
