@@ -88,6 +88,7 @@ typedef struct {
   int accumulate; /* 1: fp32 out += result (red.add) instead of a plain store */
   int bn;        /* output tile width: 64, 128 or 256 */
   int split_k;   /* >1: fp32 out must be zeroed by the caller; partial sums are red.add'ed */
+  int cta_pair;  /* 1: CTA pairs (cta_group::2): 256-row MMA, B tile split across two SMs; bn must be 128 or 256 */
 } vqa_gemm_args;
 int vqa_gemm_bf16(void* plan, const vqa_gemm_args* a, void* stream);
 
@@ -103,6 +104,7 @@ typedef struct {
   const void* x; const void* w; void* out; int out_fp32;
   const float* bias; const void* residual; int relu;
   int bn;
+  int cta_pair;
 } vqa_conv_args;
 int vqa_conv2d_bf16(void* plan, const vqa_conv_args* a, void* stream);
 
@@ -113,6 +115,7 @@ typedef struct {
   int N, H, W, Cin, Cout, R, S, pad;
   const void* dy; const void* x; float* dw;
   int bn, split_k;
+  int cta_pair;
 } vqa_conv_wgrad_args;
 int vqa_conv2d_wgrad_bf16(void* plan, const vqa_conv_wgrad_args* a, void* stream);
 

@@ -31,7 +31,7 @@ int vqa_gemm_bf16(void* plan, const vqa_gemm_args* a, void* stream) {
   e.alpha = a->alpha; e.accumulate = a->accumulate;
   GemmOp op;
   int r = gemm_op_init(&op, a->M, a->N, a->K, a->A, a->lda, a->a_mn, a->B, a->ldb, a->b_mn, a->out,
-                       a->ldo, a->out_fp32, e, a->bn, a->split_k);
+                       a->ldo, a->out_fp32, e, a->bn, a->split_k, a->cta_pair ? 2 : 1);
   if (r) return r;
   note_op("gemm", 2.0 * a->M * a->N * a->K, 0.0);
   return submit(plan, stream, [op](cudaStream_t s) { return gemm_op_run(&op, s); });
@@ -44,7 +44,7 @@ int vqa_conv2d_bf16(void* plan, const vqa_conv_args* a, void* stream) {
   Epilogue e;
   e.bias = a->bias; e.relu = a->relu; e.residual = a->residual; e.ldr = a->Cout; e.res_fp32 = 0; e.res_first = 1;
   GemmOp op;
-  int r = conv_op_init(&op, g, a->x, a->w, a->out, a->out_fp32, e, a->bn);
+  int r = conv_op_init(&op, g, a->x, a->w, a->out, a->out_fp32, e, a->bn, a->cta_pair ? 2 : 1);
   if (r) return r;
   // algorithmic MACs of the convolution (the stem's zero-padded taps/channels are not counted)
   note_op("conv", 2.0 * a->N * a->Ho * a->Wo * a->Cout * a->R * a->S * (a->stem7 ? 3 : a->Cin), 0.0);
@@ -56,7 +56,7 @@ int vqa_conv2d_wgrad_bf16(void* plan, const vqa_conv_wgrad_args* a, void* stream
   g.Nimg = a->N; g.H = a->H; g.W = a->W; g.Cin = a->Cin; g.Cout = a->Cout; g.R = a->R; g.S = a->S;
   g.stride = 1; g.pad = a->pad; g.Ho = a->H; g.Wo = a->W; g.stem7 = 0;
   GemmOp op;
-  int r = conv_wgrad_op_init(&op, g, a->dy, a->x, a->dw, a->bn, a->split_k);
+  int r = conv_wgrad_op_init(&op, g, a->dy, a->x, a->dw, a->bn, a->split_k, a->cta_pair ? 2 : 1);
   if (r) return r;
   note_op("conv_wgrad", 2.0 * a->N * a->H * a->W * a->Cout * a->R * a->S * a->Cin, 0.0);
   return submit(plan, stream, [op](cudaStream_t s) { return gemm_op_run(&op, s); });

@@ -5,14 +5,14 @@
 namespace vqa {
 
 int launch_gemm_bn64(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const GemmParams&, int, int, int,
-                     cudaStream_t);
+                     int, cudaStream_t);
 int launch_gemm_bn128(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const GemmParams&, int, int, int,
-                     cudaStream_t);
+                     int, cudaStream_t);
 int launch_gemm_bn256(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const GemmParams&, int, int, int,
-                     cudaStream_t);
+                     int, cudaStream_t);
 
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
-                const GemmParams& p, int bn, int split_k, cudaStream_t stream) {
+                const GemmParams& p, int bn, int split_k, int ctas, cudaStream_t stream) {
   int tiles_m;
   if (p.a_mode == LOAD_CONV) {
     tiles_m = p.tiles_w * p.tiles_h * ((p.Nimg + p.bx_n - 1) / p.bx_n);
@@ -24,9 +24,9 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   const int tiles_n = (p.N + bn - 1) / bn;
   if (tiles_m <= 0 || tiles_n <= 0) return 0;
   switch (bn) {
-    case 64:  return launch_gemm_bn64(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, split_k, stream);
-    case 128: return launch_gemm_bn128(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, split_k, stream);
-    case 256: return launch_gemm_bn256(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, split_k, stream);
+    case 64:  return launch_gemm_bn64(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, split_k, ctas, stream);
+    case 128: return launch_gemm_bn128(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, split_k, ctas, stream);
+    case 256: return launch_gemm_bn256(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, split_k, ctas, stream);
     default:  return static_cast<int>(cudaErrorInvalidValue);
   }
 }

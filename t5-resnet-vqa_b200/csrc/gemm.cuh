@@ -74,6 +74,7 @@ struct GemmParams {
   int res_fp32;
   int res_first;              // 1: add the residual before ReLU (ResNet block), else after dropout
   float alpha;                 // scale applied to the accumulator before everything else
+  int split_producer;          // 1: B tiles are issued by a second thread (see gemm_kernel.cuh)
   long long* dbg_clk;          // bring-up: clock64 stamps of CTA 0 (vqa_debug_gemm_timing), else null
   int dbg_a_lbo, dbg_a_sbo, dbg_b_lbo, dbg_b_sbo;  // bring-up overrides of the MN-major descriptor strides (0 = default)
 };
@@ -82,6 +83,7 @@ struct GemmParams {
 // bn in {64, 128, 256}; split_k >= 1.  Returns cudaError_t as int.
 // tmOut: store map of the output (box = 128 rows / pixel box x 128 bytes); tmRes: same geometry over the bf16 residual.
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
-                const GemmParams& p, int bn, int split_k, cudaStream_t stream);
+                const GemmParams& p, int bn, int split_k, int ctas, cudaStream_t stream);
+// ctas = 2: CTA pairs (cta_group::2, 256-row MMA, the B tile split between the two CTAs); bn must be 128 or 256
 
 }  // namespace vqa

@@ -3,7 +3,8 @@
 
 namespace vqa {
 int launch_gemm_bn256(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
-                     const GemmParams& p, int tiles_m, int tiles_n, int splits, cudaStream_t stream) {
-  return launch_bn<256, 3>(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, splits, stream);
+                     const GemmParams& p, int tiles_m, int tiles_n, int splits, int ctas, cudaStream_t stream) {
+  if (ctas == 2) return launch_bn<256, 4, 2>(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, splits, stream);
+  return launch_bn<256, 3, 1>(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, splits, stream);
 }
 }  // namespace vqa

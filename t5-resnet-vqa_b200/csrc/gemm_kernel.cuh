@@ -32,7 +32,7 @@
 #include "ptx.cuh"
 #include "rng.cuh"
 
-#define VQA_GSTAMP(k) do { if (p.dbg_clk != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) p.dbg_clk[(threadIdx.x >> 5) * 16 + (k)] = clock64(); } while (0)
+#define VQA_GSTAMP(k) do { if (p.dbg_clk != nullptr && blockIdx.x < 2 && (threadIdx.x & 31) == 0) p.dbg_clk[(blockIdx.x * 11 + (threadIdx.x >> 5)) * 16 + (k)] = clock64(); } while (0)
 
 namespace vqa {
 
@@ -41,14 +41,14 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 32 * (3 + kEpiWarps);   // producer, MMA, 8 epilogue, residual producer
+constexpr int kThreads = 32 * (4 + kEpiWarps);   // A producer, MMA, 8 epilogue, residual producer, B producer
 constexpr int kChunkBytes = BK * 128;   // one 64-wide MN-major chunk: 64 k-rows x 128 B
 constexpr int kPanelBytes = BM * 128;   // staging panel: 128 rows x 128 B (32 fp32 or 64 bf16 columns)
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CTAS>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CTAS) * BK * 2;   // a CTA pair splits the B tile between its two CTAs
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_OFF = STAGES * STAGE_BYTES;
   // four panels: fp32 output -> two double-buffered panels per column-half group; bf16 output -> a double-buffered
@@ -67,13 +67,15 @@ struct TileCoord {
   int kb_begin, num_kb;
 };
 
+// fd_tiles_m counts the m-tiles of a scheduling unit (a CTA, or a CTA pair covering `ctas` consecutive m-tiles)
 __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int t, const FastDiv& fd_tiles_m,
-                                                const FastDiv& fd_tiles_n, int splits, int bn) {
+                                                const FastDiv& fd_tiles_n, int splits, int bn, int ctas = 1,
+                                                int rank = 0) {
   TileCoord tc;
   const int rest = fast_div(t, fd_tiles_n);
   const int nt = t - rest * static_cast<int>(fd_tiles_n.d);
   const int z = fast_div(rest, fd_tiles_m);
-  const int mt = rest - z * static_cast<int>(fd_tiles_m.d);
+  const int mt = (rest - z * static_cast<int>(fd_tiles_m.d)) * ctas + rank;
   tc.n0 = nt * bn;
   tc.m0 = mt * BM;
   tc.pw0 = tc.ph0 = tc.pn0 = 0;
@@ -105,13 +107,14 @@ __host__ __device__ constexpr int epi_code(bool out_fp32, int res, bool mask, bo
   return (out_fp32 ? 1 : 0) | (res << 1) | (mask ? 8 : 0) | (drop ? 16 : 0) | (atomic ? 32 : 0);
 }
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                     const __grid_constant__ GemmParams p, const FastDiv fd_tiles_m, const FastDiv fd_tiles_n,
                     const int splits) {
-  using C = Cfg<BN, STAGES>;
+  using C = Cfg<BN, STAGES, CTAS>;
+  static_assert(CTAS == 1 || BN >= 128, "a CTA pair needs at least 64 B-tile rows per CTA");
   constexpr bool kOutF32 = (EPI & 1) != 0;
   constexpr int kRes = (EPI >> 1) & 3;
   constexpr bool kMask = (EPI & 8) != 0;
@@ -134,6 +137,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = static_cast<int>(fd_tiles_m.d * fd_tiles_n.d) * splits;
+  // scheduling unit: one CTA, or a CTA pair (cluster of 2) that owns two consecutive m-tiles of one n-tile
+  const int rank = CTAS == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = rank == 0;
+  const int unit = static_cast<int>(blockIdx.x) / CTAS;
+  const int nunits = static_cast<int>(gridDim.x) / CTAS;
 
   // ---- one-time setup (overlaps the previous kernel's tail under programmatic dependent launch) ----
   VQA_GSTAMP(0);
@@ -144,43 +152,62 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmOut);
     if (kRes == 1) tma_prefetch_desc(&tmRes);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), 1);        // the leader's expect_tx arrival (+ the bytes of every producer)
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), kEpiWarps);
+      mbar_init(tmem_empty_bar(a), kEpiWarps * CTAS);   // the leader waits for both CTAs' epilogues
       mbar_init(res_full_bar(a), 1);
       mbar_init(res_empty_bar(a), kEpiWarps);
     }
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_pair(tmem_slot, C::TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // the peer's barriers must be initialised before anyone signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   VQA_GSTAMP(1);
   pdl_wait();   // nothing above touches global memory; everything below may
   VQA_GSTAMP(2);
 
-  if (warp == 0) {
-    // ===================================== TMA producer ======================================
-    if (lane == 0) {
+  if (warp == 0 || warp == 3 + kEpiWarps) {
+    // ===================================== TMA producers =====================================
+    const bool do_a = warp == 0;
+    // Operands that need several TMA instructions per k-block (MN-major chunks, convolution taps) are issued by two
+    // threads, A from warp 0 and B from the last warp, so their issue latencies overlap; a plain K-major pair
+    // (one box each) is issued by warp 0 alone (measured: tools/gemm_bench.py).
+    const bool split = p.split_producer != 0;
+    const bool do_b = split ? (warp != 0) : (warp == 0);
+    if (lane == 0 && (do_a || do_b)) {
+      auto load2 = [](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+        if (CTAS == 2) tma_load_2d_pair(dst, m, bar, c0, c1);
+        else tma_load_2d(dst, m, bar, c0, c1);
+      };
+      auto load4 = [](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+        if (CTAS == 2) tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3);
+        else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+      };
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN);
+      for (int t = unit; t < total_tiles; t += nunits) {
+        const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN, CTAS, rank);
         for (int i = 0; i < tc.num_kb; ++i) {
           const int kb = tc.kb_begin + i;
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (i < 7 && t == unit && do_a) VQA_GSTAMP(9 + i);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + C::A_BYTES;
-          const uint32_t fb = full_bar(stage);
-          mbar_expect_tx(fb, static_cast<uint32_t>(p.stage_tx_bytes));
+          // pair: both CTAs' loads are credited to the LEADER's full barrier (the leader issues the MMA)
+          const uint32_t fb = CTAS == 2 ? mapa_shared(full_bar(stage), 0) : full_bar(stage);
+          // one arrival per stage (the leader's A producer); the peer's bytes are simply counted by the same barrier
+          if (leader && do_a) mbar_expect_tx(full_bar(stage), static_cast<uint32_t>(p.stage_tx_bytes) * CTAS);
+          const int nb0 = tc.n0 + rank * (BN / CTAS);   // first B-tile row / column staged by this CTA
           // pixel box visited by this k-block when the contraction runs over pixels
           int kw0 = 0, kh0 = 0, kn0 = 0;
           if (p.a_mode == LOAD_PIXELS_MN || p.b_mode == LOAD_PIXELS_MN) {
@@ -190,40 +217,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             kw0 = tw * p.bx_w; kh0 = th * p.bx_h; kn0 = tn * p.bx_n;
           }
           // ---- A ----
-          if (p.a_mode == LOAD_2D) {
+          if (!do_a) {
+          } else if (p.a_mode == LOAD_2D) {
             if (!p.a_mn) {
-              tma_load_2d(sa, &tmA, fb, kb * BK, tc.m0);
+              load2(sa, &tmA, fb, kb * BK, tc.m0);
             } else {
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j)
-                tma_load_2d(sa + j * kChunkBytes, &tmA, fb, tc.m0 + 64 * j, kb * BK);
+                load2(sa + j * kChunkBytes, &tmA, fb, tc.m0 + 64 * j, kb * BK);
             }
           } else if (p.a_mode == LOAD_CONV) {
             const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
             const int r = tap / p.taps_s, s = tap - r * p.taps_s;
-            tma_load_4d(sa, &tmA, fb, cc * 64, tc.pw0 * p.stride_w - p.pad_w + s * p.dil_w,
-                        tc.ph0 * p.stride_h - p.pad_h + r, tc.pn0);
+            load4(sa, &tmA, fb, cc * 64, tc.pw0 * p.stride_w - p.pad_w + s * p.dil_w,
+                  tc.ph0 * p.stride_h - p.pad_h + r, tc.pn0);
           } else {  // LOAD_PIXELS_MN
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
-              tma_load_4d(sa + j * kChunkBytes, &tmA, fb, tc.m0 + 64 * j, kw0, kh0, kn0);
+              load4(sa + j * kChunkBytes, &tmA, fb, tc.m0 + 64 * j, kw0, kh0, kn0);
           }
           // ---- B ----
-          if (p.b_mode == LOAD_2D) {
+          if (!do_b) {
+          } else if (p.b_mode == LOAD_2D) {
             if (!p.b_mn) {
-              tma_load_2d(sb, &tmB, fb, kb * BK, tc.n0);
+              load2(sb, &tmB, fb, kb * BK, nb0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j)
-                tma_load_2d(sb + j * kChunkBytes, &tmB, fb, tc.n0 + 64 * j, kb * BK);
+              for (int j = 0; j < BN / CTAS / 64; ++j)
+                load2(sb + j * kChunkBytes, &tmB, fb, nb0 + 64 * j, kb * BK);
             }
           } else {  // LOAD_PIXELS_MN: column n -> (tap, input channel)
-            const int tap = tc.n0 / p.b_tap_cin, ci0 = tc.n0 - tap * p.b_tap_cin;
+            const int tap = nb0 / p.b_tap_cin, ci0 = nb0 - tap * p.b_tap_cin;
             const int r = tap / p.b_taps_s, s = tap - r * p.b_taps_s;
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_4d(sb + j * kChunkBytes, &tmB, fb, ci0 + 64 * j, kw0 + s - p.pad_w,
-                          kh0 + r - p.pad_h, kn0);
+            for (int j = 0; j < BN / CTAS / 64; ++j)
+              load4(sb + j * kChunkBytes, &tmB, fb, ci0 + 64 * j, kw0 + s - p.pad_w,
+                    kh0 + r - p.pad_h, kn0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -231,36 +260,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ========================================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn != 0, p.b_mn != 0);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc_bf16(BM * CTAS, BN, p.a_mn != 0, p.b_mn != 0);
       const uint32_t a_lbo = p.a_mn ? kChunkBytes : 16u, b_lbo = p.b_mn ? kChunkBytes : 16u;
       const uint32_t a_kstep = p.a_mn ? 16u * 128u : 32u, b_kstep = p.b_mn ? 16u * 128u : 32u;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN);
+      for (int t = unit; t < total_tiles; t += nunits) {
+        const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN, CTAS, rank);
         mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         for (int i = 0; i < tc.num_kb; ++i) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          if (i == 0 && t == static_cast<int>(blockIdx.x)) VQA_GSTAMP(3);
+          if (i == 0 && t == unit) VQA_GSTAMP(3);
+          if (i >= 1 && i < 7 && t == unit) VQA_GSTAMP(8 + i);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + C::A_BYTES;
 #pragma unroll
           for (int ks = 0; ks < BK / 16; ++ks) {
             const uint64_t da = umma_smem_desc(sa + ks * a_kstep, a_lbo, 1024u);
             const uint64_t db = umma_smem_desc(sb + ks * b_kstep, b_lbo, 1024u);
-            umma_bf16(d_tmem, da, db, idesc, (i | ks) ? 1u : 0u);
+            if (CTAS == 2) umma_bf16_pair(d_tmem, da, db, idesc, (i | ks) ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, idesc, (i | ks) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          // smem slot reusable (in both CTAs of a pair) once these MMAs retire
+          if (CTAS == 2) umma_commit_pair(empty_bar(stage), 3);
+          else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tmem_full_bar(acc));  // accumulator complete (fires immediately when num_kb == 0)
-        if (t == static_cast<int>(blockIdx.x)) VQA_GSTAMP(4);
+        // accumulator complete (fires immediately when num_kb == 0)
+        if (CTAS == 2) umma_commit_pair(tmem_full_bar(acc), 3);
+        else umma_commit(tmem_full_bar(acc));
+        if (t == unit) VQA_GSTAMP(4);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -270,8 +305,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t ring = smem_base + C::STG_OFF + 2 * kPanelBytes;
       int slot = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN);
+      for (int t = unit; t < total_tiles; t += nunits) {
+        const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN, CTAS, rank);
         if (tc.kb_begin != 0) continue;             // the residual is added by the first k-slice only
         for (int pn = 0; pn < BN / 64; ++pn) {
           const int n = tc.n0 + pn * 64;
@@ -314,8 +349,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int buf = 0;                          // staging double buffer
     int rslot = 0;                        // residual ring position
     uint32_t rphase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN);
+    for (int t = unit; t < total_tiles; t += nunits) {
+      const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN, CTAS, rank);
       const bool first_split = (tc.kb_begin == 0);
       const bool add_bias = p.bias != nullptr && first_split;
       const bool add_res = kRes != 0 && first_split;
@@ -348,7 +383,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(tmem_full_bar(acc), acc_phase);
           tc_fence_after();
           waited = true;
-          if (t == static_cast<int>(blockIdx.x)) VQA_GSTAMP(5);
+          if (t == unit) VQA_GSTAMP(5);
         }
         if (active) {
           uint32_t accr[32];
@@ -366,7 +401,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // all of this warp's TMEM reads of the tile are done: hand the accumulator stage back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+          if (lane == 0) {
+            if (CTAS == 2) mbar_arrive_cluster(mapa_shared(tmem_empty_bar(acc), 0));
+            else mbar_arrive(tmem_empty_bar(acc));
+          }
         }
         if (active) {
           if (add_bias) {
@@ -493,11 +531,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   // ---- teardown --------------------------------------------------------------------------------
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // the leader's MMAs read the peer's shared memory: leave together
+  else __syncthreads();
   VQA_GSTAMP(8);
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -513,35 +553,53 @@ inline int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, int CTAS>
 int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
                 const GemmParams& p, int tiles_m, int tiles_n, int splits, cudaStream_t stream) {
-  using C = Cfg<BN, STAGES>;
+  using C = Cfg<BN, STAGES, CTAS>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;  // per-process; all devices share the same kernel image attributes
   cudaError_t e;
+  auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, CTAS>;
   if (!attr_set) {
-    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES, EPI>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  const int total = tiles_m * tiles_n * splits;
-  const int grid = total < sm_count() ? total : sm_count();
-  launch_pdl(gemm_tcgen05_kernel<BN, STAGES, EPI>, dim3(grid), dim3(kThreads), C::SMEM_BYTES, stream, tmA, tmB, tmOut,
-             tmRes, p, make_fastdiv(tiles_m), make_fastdiv(tiles_n), splits);
+  const int units_m = (tiles_m + CTAS - 1) / CTAS;     // a pair owns two consecutive m-tiles
+  const int total = units_m * tiles_n * splits;
+  const int max_units = sm_count() / CTAS;
+  const int grid = (total < max_units ? total : max_units) * CTAS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (CTAS == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmRes, p, make_fastdiv(units_m), make_fastdiv(tiles_n), splits);
+  if (e != cudaSuccess) return static_cast<int>(e);
   return static_cast<int>(cudaGetLastError());
 }
 
 // one translation unit per tile width instantiates these variants (compile time)
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CTAS>
 int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
               const GemmParams& p, int tiles_m, int tiles_n, int splits, cudaStream_t stream) {
   const int res = p.residual == nullptr ? 0 : (p.res_fp32 ? 2 : 1);
   const int code = epi_code(p.out_fp32 != 0, res, p.relu_mask != nullptr, p.drop_p > 0.f, p.atomic_out != 0);
 #define VQA_EPI_CASE(o, r, m, d, a)                                                                   \
   case epi_code(o, r, m, d, a):                                                                       \
-    return launch_impl<BN, STAGES, epi_code(o, r, m, d, a)>(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, splits, stream);
+    return launch_impl<BN, STAGES, epi_code(o, r, m, d, a), CTAS>(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, splits, \
+                                                                  stream);
   switch (code) {
     VQA_EPI_CASE(false, 0, false, false, false)  // bf16 out                      (qkv, convs, plain dgrad)
     VQA_EPI_CASE(false, 1, false, false, false)  // bf16 out + bf16 residual      (ResNet block tails)

@@ -1,5 +1,6 @@
 #include "gemm_ops.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include "tmap.cuh"
@@ -116,10 +117,11 @@ int finish_output_maps(GemmOp* op, bool pixels, int Nimg, int Ho, int Wo) {
 
 int gemm_op_init(GemmOp* op, int M, int N, int K, const void* A, long long lda, int a_mn,
                  const void* B, long long ldb, int b_mn, void* out, long long ldo, int out_fp32,
-                 const Epilogue& epi, int bn, int split_k) {
+                 const Epilogue& epi, int bn, int split_k, int ctas) {
   memset(&op->p, 0, sizeof(op->p));
   op->valid = false;
   if (bn != 64 && bn != 128 && bn != 256) { set_last_error("gemm: bn must be 64/128/256"); return -1; }
+  if (ctas != 1 && !(ctas == 2 && bn >= 128)) { set_last_error("gemm: CTA pairs need bn 128 or 256"); return -1; }
   if ((split_k > 1 || epi.accumulate) && !out_fp32) { set_last_error("gemm: split_k / accumulate need fp32 output"); return -1; }
   if ((lda & 7) || (ldb & 7)) { set_last_error("gemm: lda/ldb must be multiples of 8 elements"); return -1; }
   GemmParams& p = op->p;
@@ -127,7 +129,7 @@ int gemm_op_init(GemmOp* op, int M, int N, int K, const void* A, long long lda, 
   p.kb_total = (K + 63) / 64;
   p.a_mn = a_mn; p.b_mn = b_mn;
   p.a_mode = LOAD_2D; p.b_mode = LOAD_2D;
-  p.stage_tx_bytes = 128 * 64 * 2 + bn * 64 * 2;
+  p.stage_tx_bytes = 128 * 64 * 2 + (bn / ctas) * 64 * 2;
   p.out = out; p.ldo = ldo; p.out_fp32 = out_fp32; p.out_pixels = 0;
   p.atomic_out = (split_k > 1 || epi.accumulate) ? 1 : 0;
   fill_epilogue(p, epi);
@@ -135,21 +137,22 @@ int gemm_op_init(GemmOp* op, int M, int N, int K, const void* A, long long lda, 
   if (!a_mn) r = make_tmap_2d(&op->tmA, A, M, K, lda, 64, 128);
   else       r = make_tmap_2d(&op->tmA, A, K, M, lda, 64, 64);
   if (r) return r;
-  if (!b_mn) r = make_tmap_2d(&op->tmB, B, N, K, ldb, 64, bn);
+  if (!b_mn) r = make_tmap_2d(&op->tmB, B, N, K, ldb, 64, bn / ctas);
   else       r = make_tmap_2d(&op->tmB, B, K, N, ldb, 64, 64);
   if (r) return r;
   r = finish_output_maps(op, false, 0, 0, 0);
   if (r) return r;
-  op->bn = bn; op->split_k = split_k < 1 ? 1 : split_k;
+  op->bn = bn; op->split_k = split_k < 1 ? 1 : split_k; op->ctas = ctas;
   op->valid = true;
   return 0;
 }
 
 int conv_op_init(GemmOp* op, const ConvGeom& g, const void* x, const void* w, void* out, int out_fp32,
-                 const Epilogue& epi, int bn) {
+                 const Epilogue& epi, int bn, int ctas) {
   memset(&op->p, 0, sizeof(op->p));
   op->valid = false;
   if (bn != 64 && bn != 128 && bn != 256) { set_last_error("conv: bn must be 64/128/256"); return -1; }
+  if (ctas != 1 && !(ctas == 2 && bn >= 128)) { set_last_error("conv: CTA pairs need bn 128 or 256"); return -1; }
   GemmParams& p = op->p;
   int bw = 1, bh = 1, bb = 1;
   choose_box(g.Wo, g.Ho, g.Nimg, 128, false, &bw, &bh, &bb);
@@ -161,7 +164,7 @@ int conv_op_init(GemmOp* op, const ConvGeom& g, const void* x, const void* w, vo
   p.N = g.Cout;
   p.a_mn = 0; p.b_mn = 0;
   p.a_mode = LOAD_CONV; p.b_mode = LOAD_2D;
-  p.stage_tx_bytes = bw * bh * bb * 128 + bn * 64 * 2;
+  p.stage_tx_bytes = bw * bh * bb * 128 + (bn / ctas) * 64 * 2;
   p.out = out; p.ldo = g.Cout; p.out_fp32 = out_fp32; p.out_pixels = 1; p.atomic_out = 0;
   fill_epilogue(p, epi);
   int r;
@@ -198,20 +201,21 @@ int conv_op_init(GemmOp* op, const ConvGeom& g, const void* x, const void* w, vo
     p.stride_w = g.stride; p.stride_h = g.stride; p.pad_w = g.pad; p.pad_h = g.pad; p.dil_w = 1;
     Ktot = static_cast<long long>(g.R) * g.S * g.Cin;
   }
-  r = make_tmap_2d(&op->tmB, w, g.Cout, Ktot, Ktot, 64, bn);
+  r = make_tmap_2d(&op->tmB, w, g.Cout, Ktot, Ktot, 64, bn / ctas);
   if (r) return r;
   r = finish_output_maps(op, true, g.Nimg, g.Ho, g.Wo);
   if (r) return r;
-  op->bn = bn; op->split_k = 1;
+  op->bn = bn; op->split_k = 1; op->ctas = ctas;
   op->valid = true;
   return 0;
 }
 
 int conv_wgrad_op_init(GemmOp* op, const ConvGeom& g, const void* dy, const void* x, float* dw, int bn,
-                       int split_k) {
+                       int split_k, int ctas) {
   memset(&op->p, 0, sizeof(op->p));
   op->valid = false;
   if (bn != 64 && bn != 128 && bn != 256) { set_last_error("wgrad: bn must be 64/128/256"); return -1; }
+  if (ctas != 1 && !(ctas == 2 && bn >= 128)) { set_last_error("wgrad: CTA pairs need bn 128 or 256"); return -1; }
   if (g.stride != 1 || g.Ho != g.H || g.Wo != g.W) { set_last_error("wgrad: stride-1 same conv only"); return -1; }
   if (g.Cin % bn) { set_last_error("wgrad: Cin must be a multiple of bn"); return -1; }
   if (g.Cout % 8 || g.Cin % 8) { set_last_error("wgrad: channels must be multiples of 8"); return -1; }
@@ -228,7 +232,7 @@ int conv_wgrad_op_init(GemmOp* op, const ConvGeom& g, const void* dy, const void
   p.kb_total = p.tiles_w * p.tiles_h * ((g.Nimg + bb - 1) / bb);
   p.a_mn = 1; p.b_mn = 1;
   p.a_mode = LOAD_PIXELS_MN; p.b_mode = LOAD_PIXELS_MN;
-  p.stage_tx_bytes = 2 * 64 * 128 + (bn / 64) * 64 * 128;
+  p.stage_tx_bytes = 2 * 64 * 128 + (bn / ctas / 64) * 64 * 128;
   p.b_tap_cin = g.Cin; p.b_taps_s = g.S; p.pad_w = g.pad; p.pad_h = g.pad;
   p.out = dw; p.ldo = p.N; p.out_fp32 = 1; p.out_pixels = 0;
   p.atomic_out = split_k > 1 ? 1 : 0;
@@ -255,7 +259,7 @@ int conv_wgrad_op_init(GemmOp* op, const ConvGeom& g, const void* dy, const void
     int r = finish_output_maps(op, false, 0, 0, 0);
     if (r) return r;
   }
-  op->bn = bn; op->split_k = split_k < 1 ? 1 : split_k;
+  op->bn = bn; op->split_k = split_k < 1 ? 1 : split_k; op->ctas = ctas;
   op->valid = true;
   return 0;
 }
@@ -273,8 +277,13 @@ int gemm_op_run(const GemmOp* op, cudaStream_t stream) {
   p.fd_tiles_w = make_fastdiv(p.tiles_w); p.fd_tiles_h = make_fastdiv(p.tiles_h);
   p.fd_bx_w = make_fastdiv(p.bx_w); p.fd_bx_h = make_fastdiv(p.bx_h);
   p.dbg_clk = g_dbg_clk;
+  {
+    static int mode = -1;   // VQA_B200_SPLIT_PRODUCER=0 falls back to one issuing thread (measured slower on the whole step)
+    if (mode < 0) { const char* e = getenv("VQA_B200_SPLIT_PRODUCER"); mode = (e && e[0] == '0') ? 0 : 1; }
+    p.split_producer = mode;
+  }
   p.dbg_a_lbo = g_dbg[0]; p.dbg_a_sbo = g_dbg[1]; p.dbg_b_lbo = g_dbg[2]; p.dbg_b_sbo = g_dbg[3];
-  int r = launch_gemm(op->tmA, op->tmB, op->tmOut, op->tmRes, p, op->bn, op->split_k, stream);
+  int r = launch_gemm(op->tmA, op->tmB, op->tmOut, op->tmRes, p, op->bn, op->split_k, op->ctas, stream);
   if (r == -2) set_last_error("gemm: this epilogue combination (output type / residual / mask / dropout / accumulate) is not built");
   else if (r) set_last_error("gemm launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
   return r;

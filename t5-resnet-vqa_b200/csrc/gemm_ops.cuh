@@ -25,6 +25,7 @@ struct GemmOp {
   GemmParams p;
   int bn = 128;
   int split_k = 1;
+  int ctas = 1;        // 2: CTA pairs (cta_group::2)
   bool valid = false;
 };
 
@@ -34,7 +35,7 @@ struct GemmOp {
 // out is bf16 or fp32 with row stride ldo.  split_k > 1 requires fp32 out that was zeroed beforehand.
 int gemm_op_init(GemmOp* op, int M, int N, int K, const void* A, long long lda, int a_mn,
                  const void* B, long long ldb, int b_mn, void* out, long long ldo, int out_fp32,
-                 const Epilogue& epi, int bn, int split_k);
+                 const Epilogue& epi, int bn, int split_k, int ctas = 1);
 
 struct ConvGeom {
   int Nimg, H, W, Cin;     // input NHWC (bf16); for stem7 the input is the padded 8-channel layout
@@ -45,12 +46,12 @@ struct ConvGeom {
 // out[N,Ho,Wo,Cout] = epi( conv(x, w) ), w is bf16 [Cout, R*S*Cin] (tap-major, channel-minor);
 // for stem7 w is [Cout, 7*8*8].  residual (bf16 NHWC, same shape as out) and bias go through epi.
 int conv_op_init(GemmOp* op, const ConvGeom& g, const void* x, const void* w, void* out, int out_fp32,
-                 const Epilogue& epi, int bn);
+                 const Epilogue& epi, int bn, int ctas = 1);
 
 // Weight gradient of a stride-1 "same" RxS convolution: dW[Cout, R*S*Cin] (fp32, ld = R*S*Cin) =
 // sum over pixels dY[pix, Cout] * X[pix + tap, Cin].  dy: bf16 [N,Ho,Wo,Cout]; x: bf16 [N,H,W,Cin].
 int conv_wgrad_op_init(GemmOp* op, const ConvGeom& g, const void* dy, const void* x, float* dw,
-                       int bn, int split_k);
+                       int bn, int split_k, int ctas = 1);
 
 int gemm_op_run(const GemmOp* op, cudaStream_t stream);
 

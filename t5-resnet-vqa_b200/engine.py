@@ -87,7 +87,7 @@ class _Rec:
     # ---- contractions ----
     def gemm(self, M, N, K, A, lda, a_mn, B, ldb, b_mn, out, ldo, out_fp32, bias=None, relu=0, relu_mask=None,
              ldm=0, drop_p=0.0, sid=0, rng=None, residual=None, ldr=0, res_fp32=1, alpha=1.0, accumulate=0,
-             bn=None, split_k=1):
+             bn=None, split_k=1, pair=None):
         if bn is None:
             bn, split_k = pick_tile(M, N, K, out_fp32 and not relu and relu_mask is None and drop_p == 0.0
                                     and accumulate, split_k)
@@ -101,6 +101,7 @@ class _Rec:
         a.drop_p, a.drop_sid, a.rng = float(drop_p), sid, L.ptr(rng) if drop_p > 0 else None
         a.residual, a.ldr, a.res_fp32, a.res_first = L.ptr(residual), ldr, int(res_fp32), 0
         a.alpha, a.accumulate, a.bn, a.split_k = alpha, int(accumulate), bn, split_k
+        a.cta_pair = int(bool(pair)) if pair is not None else 0
         L.check(self.lib.vqa_gemm_bf16(self.plan, ctypes.byref(a), self._s()), "gemm")
 
     def linear(self, X, M, K, ldx, W, N, out, ldo, out_fp32=0, **kw):
@@ -116,23 +117,27 @@ class _Rec:
         self.gemm(N, K, M, dY, ldy, 1, X, ldx, 1, dW, K, 1, **kw)
 
     def conv(self, N, H, W, Cin, Cout, R, stride, pad, x, w, out, bias=None, residual=None, relu=1, stem7=0,
-             out_fp32=0, bn=None):
+             out_fp32=0, bn=None, pair=None):
         Ho = (H + 2 * pad - R) // stride + 1
         Wo = (W + 2 * pad - R) // stride + 1
         if bn is None:
             bn = pick_conv_tile(N * Ho * Wo, Cout)
+            if pair and bn < 128:
+                bn = 128
         a = L.ConvArgs()
         a.N, a.H, a.W, a.Cin, a.Cout, a.R, a.S = N, H, W, Cin, Cout, R, R
         a.stride, a.pad, a.Ho, a.Wo, a.stem7 = stride, pad, Ho, Wo, stem7
         a.x, a.w, a.out, a.out_fp32 = L.ptr(x), L.ptr(w), L.ptr(out), out_fp32
         a.bias, a.residual, a.relu, a.bn = L.ptr(bias), L.ptr(residual), int(relu), bn
+        a.cta_pair = int(bool(pair)) if pair is not None else 0
         L.check(self.lib.vqa_conv2d_bf16(self.plan, ctypes.byref(a), self._s()), "conv2d")
         return Ho, Wo
 
-    def conv_wgrad(self, N, H, W, Cin, Cout, dy, x, dw, bn, split_k):
+    def conv_wgrad(self, N, H, W, Cin, Cout, dy, x, dw, bn, split_k, pair=None):
         a = L.ConvWgradArgs()
         a.N, a.H, a.W, a.Cin, a.Cout, a.R, a.S, a.pad = N, H, W, Cin, Cout, 3, 3, 1
         a.dy, a.x, a.dw, a.bn, a.split_k = L.ptr(dy), L.ptr(x), L.ptr(dw), bn, split_k
+        a.cta_pair = int(bool(pair)) if pair is not None else 0
         L.check(self.lib.vqa_conv2d_wgrad_bf16(self.plan, ctypes.byref(a), self._s()), "conv2d_wgrad")
 
     def attn_fwd(self, B, H, Lq, Lk, hd, q, ldq, k, ldk, v, ldv, out, ldo, probs, bias, key_mask, scale, drop_p,
@@ -176,7 +181,7 @@ def _tile_cost(tiles, bn):
     SM pulls from L2 per k-block (128 A rows + bn B rows) plus a fixed part (pipeline fill, epilogue tail); fitted
     to tools/gemm_bench.py on B200 (it reproduces the measured best width on all 13 GEMM and 14 conv shapes)."""
     waves = (tiles + N_SM - 1) // N_SM
-    return waves * (bn + 160)
+    return waves * (bn + int(os.environ.get("VQA_B200_TILE_FIXED", "160")))
 
 
 def pick_tile(M, N, K, can_split, split_k=1):

@@ -18,7 +18,7 @@ class GemmArgs(ctypes.Structure):
                 ("relu_mask", c_vp), ("ldm", c_ll),
                 ("drop_p", c_f), ("drop_sid", c_u32), ("rng", c_vp),
                 ("residual", c_vp), ("ldr", c_ll), ("res_fp32", c_int), ("res_first", c_int),
-                ("alpha", c_f), ("accumulate", c_int), ("bn", c_int), ("split_k", c_int)]
+                ("alpha", c_f), ("accumulate", c_int), ("bn", c_int), ("split_k", c_int), ("cta_pair", c_int)]
 
 
 class ConvArgs(ctypes.Structure):
@@ -26,13 +26,13 @@ class ConvArgs(ctypes.Structure):
                 ("R", c_int), ("S", c_int), ("stride", c_int), ("pad", c_int), ("Ho", c_int),
                 ("Wo", c_int), ("stem7", c_int),
                 ("x", c_vp), ("w", c_vp), ("out", c_vp), ("out_fp32", c_int),
-                ("bias", c_vp), ("residual", c_vp), ("relu", c_int), ("bn", c_int)]
+                ("bias", c_vp), ("residual", c_vp), ("relu", c_int), ("bn", c_int), ("cta_pair", c_int)]
 
 
 class ConvWgradArgs(ctypes.Structure):
     _fields_ = [("N", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("Cout", c_int),
                 ("R", c_int), ("S", c_int), ("pad", c_int),
-                ("dy", c_vp), ("x", c_vp), ("dw", c_vp), ("bn", c_int), ("split_k", c_int)]
+                ("dy", c_vp), ("x", c_vp), ("dw", c_vp), ("bn", c_int), ("split_k", c_int), ("cta_pair", c_int)]
 
 
 class AttnFwdArgs(ctypes.Structure):

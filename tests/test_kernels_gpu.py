@@ -93,6 +93,81 @@ def test_wgrad(C, M, N, K, bn):
 
 
 # ------------------------------------------------------------------------------------------------
+# CTA pairs (cta_group::2): a cluster of two CTAs runs one 256-row MMA, each staging half of the B tile
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,bn", [(2048, 2304, 768, 256), (2048, 768, 768, 128), (2048, 3072, 768, 256),
+                                      (300, 256, 512, 128), (8192, 3072, 768, 256), (196, 1536, 768, 256)])
+def test_pair_linear_forward(C, M, N, K, bn):
+    X, W, b = rnd(M, K, seed=1, dtype=BF), rnd(N, K, seed=2, scale=K ** -0.5, dtype=BF), rnd(N, seed=3)
+    out = torch.zeros(M, N, dtype=BF, device="cuda")
+    C.linear(X, M, K, K, W, N, out, N, bias=b, relu=1, bn=bn, pair=True)
+    assert rel_fro(out, F.relu(X.float() @ W.float().t() + b)) < 6e-3
+
+
+def test_pair_fp32_residual_dropout_and_accumulate(C):
+    M, N, K = 2048, 768, 3072
+    X, W, R = rnd(M, K, seed=1, dtype=BF), rnd(N, K, seed=2, scale=K ** -0.5, dtype=BF), rnd(M, N, seed=3)
+    out = torch.zeros(M, N, device="cuda")
+    C.linear(X, M, K, K, W, N, out, N, out_fp32=1, residual=R, ldr=N, res_fp32=1, bn=128, pair=True)
+    ref = X.float() @ W.float().t() + R
+    assert rel_fro(out, ref) < 2e-5
+    C.linear(X, M, K, K, W, N, out, N, out_fp32=1, residual=R, ldr=N, res_fp32=1, accumulate=1, bn=128, pair=True)
+    assert rel_fro(out, 2 * ref) < 2e-5
+    rng = rng_state()
+    a, b = torch.zeros(M, N, device="cuda"), torch.zeros(M, N, device="cuda")
+    C.linear(X, M, K, K, W, N, a, N, out_fp32=1, residual=R, ldr=N, res_fp32=1, drop_p=0.1, sid=4, rng=rng, bn=128, pair=True)
+    C.linear(X, M, K, K, W, N, b, N, out_fp32=1, residual=R, ldr=N, res_fp32=1, drop_p=0.1, sid=4, rng=rng, bn=128)
+    assert rel_fro(a, b) < 1e-6       # same dropout mask, same sums as the single-CTA kernel
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(2048, 768, 3072, 256), (2048, 3072, 768, 128), (2048, 2304, 768, 128)])
+def test_pair_dgrad_with_relu_mask(C, M, N, K, bn):
+    dY = rnd(M, N, seed=1, dtype=BF)
+    W, act = rnd(N, K, seed=2, scale=N ** -0.5, dtype=BF), rnd(M, K, seed=3, dtype=BF)
+    out = torch.zeros(M, K, dtype=BF, device="cuda")
+    C.dgrad(dY, M, N, N, W, K, out, K, relu_mask=act, ldm=K, bn=bn, pair=True)
+    assert rel_fro(out, (dY.float() @ W.float()) * (act.float() > 0)) < 6e-3
+
+
+def test_pair_split_k(C):
+    M, N, K = 512, 512, 4096
+    X, W = rnd(M, K, seed=1, dtype=BF), rnd(N, K, seed=2, dtype=BF)
+    out = torch.zeros(M, N, device="cuda")
+    C.linear(X, M, K, K, W, N, out, N, out_fp32=1, bn=128, split_k=4, pair=True)
+    assert rel_fro(out, X.float() @ W.float().t()) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(2048, 3072, 768, 128), (2048, 768, 3072, 256), (196, 1536, 768, 128),
+                                      (2048, 2304, 768, 128), (1024, 3072, 3072, 128)])
+def test_pair_wgrad(C, M, N, K, bn):
+    dY, X = rnd(M, N, seed=1, dtype=BF), rnd(M, K, seed=2, dtype=BF)
+    dW = torch.zeros(N, K, device="cuda")
+    C.wgrad(dY, M, N, N, X, K, K, dW, bn=bn, pair=True)
+    assert rel_fro(dW, dY.float().t() @ X.float()) < 2e-5
+
+
+@pytest.mark.parametrize("N,H,Cin,Cout,R,s,p,bn,res", [
+    (4, 56, 64, 256, 1, 1, 0, 128, True), (4, 28, 128, 512, 1, 1, 0, 256, True),
+    (8, 14, 256, 256, 3, 1, 1, 128, True), (5, 7, 512, 2048, 1, 1, 0, 256, True),
+    (4, 56, 256, 512, 1, 2, 0, 128, False), (3, 8, 512, 768, 3, 1, 1, 256, False)])
+def test_pair_conv_bias_residual_relu(C, N, H, Cin, Cout, R, s, p, bn, res):
+    x = rnd(N, Cin, H, H, seed=1, dtype=BF)
+    w = rnd(Cout, Cin, R, R, seed=2, scale=(Cin * R * R) ** -0.5, dtype=BF)
+    b = rnd(Cout, seed=3)
+    ref = F.conv2d(x.float(), w.float(), b, stride=s, padding=p)
+    r = None
+    if res:
+        r = rnd(*ref.shape, seed=4, dtype=BF)
+        ref = ref + r.float()
+    ref = F.relu(ref)
+    out = torch.zeros(N, ref.shape[2], ref.shape[3], Cout, dtype=BF, device="cuda")
+    wk = w.permute(0, 2, 3, 1).contiguous()
+    C.conv(N, H, H, Cin, Cout, R, s, p, x.permute(0, 2, 3, 1).contiguous(), wk, out, bias=b,
+           residual=r.permute(0, 2, 3, 1).contiguous() if res else None, relu=1, bn=bn, pair=True)
+    assert rel_fro(out, ref.permute(0, 2, 3, 1).contiguous()) < 6e-3
+
+
+# ------------------------------------------------------------------------------------------------
 # convolutions
 # ------------------------------------------------------------------------------------------------
 def nhwc(t):
@@ -143,8 +218,10 @@ def test_stem_fold_pack_maxpool(C, N, H):
     assert rel_fro(out, nhwc(ref)) < 8e-3
 
 
-@pytest.mark.parametrize("N,H,Cin,bn,split", [(8, 7, 512, 256, 1), (16, 7, 2048, 256, 2), (4, 8, 512, 128, 1)])
-def test_convT_projection_forward_and_wgrad(C, N, H, Cin, bn, split):
+@pytest.mark.parametrize("N,H,Cin,bn,split,pair", [(8, 7, 512, 256, 1, False), (16, 7, 2048, 256, 2, False),
+                                                   (4, 8, 512, 128, 1, False), (16, 7, 2048, 256, 2, True),
+                                                   (8, 7, 512, 256, 1, True)])
+def test_convT_projection_forward_and_wgrad(C, N, H, Cin, bn, split, pair):
     """ConvTranspose2d(k3,s1,p1) == 3x3 same conv on the prepared weight; wgrad maps back to [Cin,Cout,3,3]."""
     Cout = 768
     x = rnd(N, Cin, H, H, seed=1, dtype=BF)
@@ -156,10 +233,10 @@ def test_convT_projection_forward_and_wgrad(C, N, H, Cin, bn, split):
     wk = torch.empty(Cout * 9 * Cin, dtype=BF, device="cuda")
     C.convT_weight_prep(w.detach(), wk, Cin, Cout)
     out = torch.zeros(N * H * H, Cout, dtype=BF, device="cuda")
-    C.conv(N, H, H, Cin, Cout, 3, 1, 1, nhwc(x), wk, out, bias=b, relu=0)
+    C.conv(N, H, H, Cin, Cout, 3, 1, 1, nhwc(x), wk, out, bias=b, relu=0, pair=pair)
     assert rel_fro(out, nhwc(ref.detach()).view(-1, Cout)) < 8e-3
     dwc = torch.zeros(Cout, 9 * Cin, device="cuda")
-    C.conv_wgrad(N, H, H, Cin, Cout, nhwc(dy), nhwc(x), dwc, bn, split)
+    C.conv_wgrad(N, H, H, Cin, Cout, nhwc(dy), nhwc(x), dwc, bn, split, pair=pair)
     dw = torch.empty_like(w)
     C.convT_wgrad_unprep(dwc, dw, Cin, Cout)
     assert rel_fro(dw, w.grad) < 2e-5

@@ -70,7 +70,7 @@ def time_torch(fn):
 def main():
     C = Caller(pkg)
     dev = "cuda"
-    print("%-34s %8s %8s %8s %8s | %8s" % ("shape", "bn64", "bn128", "bn256", "best TF", "cuBLAS"))
+    print("%-34s %7s %7s %7s %7s %7s %8s | %8s" % ("shape", "bn64", "bn128", "bn256", "pair128", "pair256", "best TF", "cuBLAS"))
     # forward-style (K-major x K-major), dgrad-style (B MN-major), wgrad-style (both MN-major)
     shapes = [("fwd", 2048, 768, 768), ("fwd", 2048, 2304, 768), ("fwd", 2048, 3072, 768), ("fwd", 2048, 768, 3072),
               ("dgrad", 2048, 768, 2304), ("dgrad", 2048, 3072, 768), ("dgrad", 2048, 768, 3072),
@@ -83,23 +83,23 @@ def main():
         fp32 = kind == "wgrad"
         out = torch.empty(M, N, device=dev, dtype=torch.float32 if fp32 else BF)
         res = []
-        for bn in (64, 128, 256):
+        for bn, pair in ((64, False), (128, False), (256, False), (128, True), (256, True)):
             if kind == "fwd":
-                fn = lambda r: r.gemm(M, N, K, A, K, 0, B, K, 0, out, N, int(fp32), bn=bn)
+                fn = lambda r: r.gemm(M, N, K, A, K, 0, B, K, 0, out, N, int(fp32), bn=bn, pair=pair)
             elif kind == "dgrad":
-                fn = lambda r: r.gemm(M, N, K, A, K, 0, Bt, N, 1, out, N, int(fp32), bn=bn)
+                fn = lambda r: r.gemm(M, N, K, A, K, 0, Bt, N, 1, out, N, int(fp32), bn=bn, pair=pair)
             else:
-                fn = lambda r: r.gemm(M, N, K, At, M, 1, Bt, N, 1, out, N, int(fp32), bn=bn)
+                fn = lambda r: r.gemm(M, N, K, At, M, 1, Bt, N, 1, out, N, int(fp32), bn=bn, pair=pair)
             res.append(time_ours(fn))
         ref = time_torch(lambda: torch.matmul(A, B.t()))
         fl = 2.0 * M * N * K
-        print("%-6s M%-6d N%-5d K%-5d       %8.1f %8.1f %8.1f %8.0f | %8.1f us (%4.0f TF)" % (
-            kind, M, N, K, res[0], res[1], res[2], fl / min(res) / 1e6, ref, fl / ref / 1e6))
+        print("%-6s M%-6d N%-5d K%-5d       %7.1f %7.1f %7.1f %7.1f %7.1f %8.0f | %8.1f us (%4.0f TF)" % (
+            kind, M, N, K, res[0], res[1], res[2], res[3], res[4], fl / min(res) / 1e6, ref, fl / ref / 1e6))
     # convolutions of ResNet-50 at batch 64 (NHWC) vs cuDNN channels_last bf16
     convs = [(56, 64, 64, 1, 1), (56, 64, 64, 3, 1), (56, 64, 256, 1, 1), (56, 256, 64, 1, 1), (28, 128, 128, 3, 1),
              (28, 128, 512, 1, 1), (28, 512, 128, 1, 1), (14, 256, 256, 3, 1), (14, 256, 1024, 1, 1),
              (14, 1024, 256, 1, 1), (7, 512, 512, 3, 1), (7, 512, 2048, 1, 1), (7, 2048, 512, 1, 1), (7, 2048, 768, 3, 1)]
-    print("\n%-36s %8s %8s %8s | %8s" % ("conv (B=64)", "bn64", "bn128", "bn256", "cuDNN"))
+    print("\n%-36s %7s %7s %7s %7s %7s | %8s" % ("conv (B=64)", "bn64", "bn128", "bn256", "pair128", "pair256", "cuDNN"))
     for H, Cin, Cout, R, s in convs:
         N = 64
         x = torch.randn(N, H, H, Cin, device=dev).to(BF)
@@ -108,19 +108,19 @@ def main():
         out = torch.empty(N, H, H, Cout, device=dev, dtype=BF)
         resd = torch.randn(N, H, H, Cout, device=dev).to(BF)
         res = []
-        for bn in (64, 128, 256):
+        for bn, pair in ((64, False), (128, False), (256, False), (128, True), (256, True)):
             if bn > 64 and Cout < bn:
                 res.append(float("nan"))
                 continue
             res.append(time_ours(lambda r: r.conv(N, H, H, Cin, Cout, R, s, R // 2, x, w, out, bias=b, residual=resd,
-                                                  relu=1, bn=bn)))
+                                                  relu=1, bn=bn, pair=pair)))
         xc = x.permute(0, 3, 1, 2)
         wc = w.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
         ref = time_torch(lambda: F.conv2d(xc, wc, None, s, R // 2))
         fl = 2.0 * N * H * H * Cout * R * R * Cin
         best = min(r for r in res if r == r)
-        print("%2dx%-2d %4d->%-4d k%d +res          %8.1f %8.1f %8.1f | %8.1f us  ours %4.0f TF" % (
-            H, H, Cin, Cout, R, res[0], res[1], res[2], ref, fl / best / 1e6))
+        print("%2dx%-2d %4d->%-4d k%d +res          %7.1f %7.1f %7.1f %7.1f %7.1f | %8.1f us  ours %4.0f TF" % (
+            H, H, Cin, Cout, R, res[0], res[1], res[2], res[3], res[4], ref, fl / best / 1e6))
 
 
 if __name__ == "__main__":

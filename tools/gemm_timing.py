@@ -8,25 +8,31 @@ from util import Caller
 C = Caller(pkg); lib = pkg.lib.load()
 BF = torch.bfloat16; dev = "cuda"
 names = ["start", "setup done", "pdl_wait done", "first stage full (mma)", "tile0 mma committed", "tile0 acc ready (epi)", "epi loop done", "stores drained", "teardown sync"]
-shapes = [("fwd", 2048, 768, 768, 128, 0), ("fwd", 2048, 768, 768, 128, 1), ("fwd", 2048, 2304, 768, 256, 0), ("fwd", 2048, 768, 3072, 128, 1),
-          ("wgrad", 768, 768, 2048, 64, 1), ("wgrad", 3072, 768, 2048, 128, 1)]
-for kind, M, N, K, bn, fp32 in shapes:
+shapes = [("fwd", 2048, 768, 768, 128, 0, 0), ("fwd", 2048, 768, 768, 128, 1, 0), ("fwd", 2048, 2304, 768, 256, 0, 0),
+          ("fwd", 2048, 768, 3072, 128, 1, 0), ("wgrad", 768, 768, 2048, 64, 1, 0), ("wgrad", 3072, 768, 2048, 128, 1, 0),
+          ("fwd", 2048, 2304, 768, 256, 0, 1), ("fwd", 8192, 3072, 768, 256, 0, 1), ("fwd", 8192, 3072, 768, 256, 0, 0)]
+if len(sys.argv) > 1:
+    shapes = shapes[-3:]
+for kind, M, N, K, bn, fp32, pair in shapes:
     A = torch.randn(M, K, device=dev).to(BF); B = torch.randn(N, K, device=dev).to(BF)
     At, Bt = A.t().contiguous(), B.t().contiguous()
     out = torch.empty(M, N, device=dev, dtype=torch.float32 if fp32 else BF)
     res = torch.randn(M, N, device=dev) if (fp32 and kind == "fwd") else None
-    buf = torch.zeros(11 * 16, dtype=torch.int64, device=dev)
+    buf = torch.zeros(22 * 16, dtype=torch.int64, device=dev)
     for it in range(3):
         if it == 2:
             lib.vqa_debug_gemm_timing(buf.data_ptr())
         if kind == "fwd":
-            C.gemm(M, N, K, A, K, 0, B, K, 0, out, N, fp32, bn=bn, residual=res, ldr=N, res_fp32=1)
+            C.gemm(M, N, K, A, K, 0, B, K, 0, out, N, fp32, bn=bn, residual=res, ldr=N, res_fp32=1, pair=bool(pair))
         else:
-            C.gemm(M, N, K, At, M, 1, Bt, N, 1, out, N, fp32, bn=bn)
+            C.gemm(M, N, K, At, M, 1, Bt, N, 1, out, N, fp32, bn=bn, pair=bool(pair))
         torch.cuda.synchronize()
     lib.vqa_debug_gemm_timing(None)
-    t = buf.cpu().view(11, 16)
+    t = buf.cpu().view(22, 16)
     t0 = int(t[0, 0])
-    print("%s M%d N%d K%d bn%d fp32=%d   cycles since start: producer(w0) mma(w1) epi(w2) epi(w9)" % (kind, M, N, K, bn, fp32))
+    print("%s M%d N%d K%d bn%d fp32=%d pair=%d   cycles since start: producer(w0) mma(w1) epi(w2) epi(w9)" % (kind, M, N, K, bn, fp32, pair))
     for i, n in enumerate(names):
         print("   %-26s" % n + "".join("%9s" % (str(int(t[w, i]) - t0) if int(t[w, i]) else "-") for w in (0, 1, 2, 9)))
+    print("   producer cta0 empty-pass i=0..6:", [int(t[0, 9 + i]) - t0 for i in range(7)])
+    print("   producer cta1 empty-pass i=0..6:", [int(t[11, 9 + i]) - int(t[11, 0]) for i in range(7)], "cta1 start-cta0 start", int(t[11, 0]) - t0)
+    print("   mma cta0 full-pass i=1..6      :", [int(t[1, 9 + i]) - t0 for i in range(6)])
