@@ -52,13 +52,13 @@ __device__ __forceinline__ uint32_t keep_bits(const DropCtx& dc, unsigned long l
   if (!dc.on) return 0xFFFFFFFFu;
   uint32_t keep = 0;
   if ((Lk & 7) == 0) {
+#pragma unroll 1
+    for (int g = 0; g * 8 < Lk; ++g) {   // rolled on purpose: run-once straight-line code is instruction-fetch bound
+      const Philox8 r = philox8(dc.seed, dc.offset, dc.sid, (base >> 3) + g);
+      uint32_t m = 0;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (g * 8 < Lk) {
-        const Philox8 r = philox8(dc.seed, dc.offset, dc.sid, (base >> 3) + g);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) keep |= (r.u16(e) >= dc.thresh ? 1u : 0u) << (g * 8 + e);
-      }
+      for (int e = 0; e < 8; ++e) m |= (r.u16(e) >= dc.thresh ? 1u : 0u) << e;
+      keep |= m << (g * 8);
     }
   } else {
     unsigned long long cur = ~0ull;
@@ -90,26 +90,46 @@ __device__ __forceinline__ void store_diag_row(uint8_t* tile, int row, int g, co
   }
 }
 
-// One TMEM row of NC fp32 columns -> bf16 -> global (16-byte stores)
+// 32 lanes x 8 consecutive fp32 columns (thread t of the warp gets lane base + t)
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// One TMEM row of NC fp32 columns, scaled by `mul` -> bf16 -> global (16-byte stores).  32 columns per round trip
+// (four loads in flight, one wait); rolled over the chunks because every CTA runs this exactly once.
 template <int NC>
-__device__ __forceinline__ void store_tmem_row(uint32_t taddr, __nv_bfloat16* dst, bool ok) {
-#pragma unroll
+__device__ __forceinline__ void store_tmem_row(uint32_t taddr, __nv_bfloat16* dst, bool ok, float mul) {
+#pragma unroll 1
   for (int c = 0; c < NC / 32; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32(taddr + c * 32, r);
+    uint32_t r[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tmem_ld_32x8(taddr + c * 32 + k * 8, r[k]);
     tmem_ld_wait();
     if (ok) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(r[8 * k + 0]), __uint_as_float(r[8 * k + 1]));
-        u.y = pack_bf16x2(__uint_as_float(r[8 * k + 2]), __uint_as_float(r[8 * k + 3]));
-        u.z = pack_bf16x2(__uint_as_float(r[8 * k + 4]), __uint_as_float(r[8 * k + 5]));
-        u.w = pack_bf16x2(__uint_as_float(r[8 * k + 6]), __uint_as_float(r[8 * k + 7]));
-        reinterpret_cast<uint4*>(dst + c * 32)[k] = u;
+        u.x = pack_bf16x2(__uint_as_float(r[k][0]) * mul, __uint_as_float(r[k][1]) * mul);
+        u.y = pack_bf16x2(__uint_as_float(r[k][2]) * mul, __uint_as_float(r[k][3]) * mul);
+        u.z = pack_bf16x2(__uint_as_float(r[k][4]) * mul, __uint_as_float(r[k][5]) * mul);
+        u.w = pack_bf16x2(__uint_as_float(r[k][6]) * mul, __uint_as_float(r[k][7]) * mul);
+        reinterpret_cast<uint4*>(dst)[c * 4 + k] = u;
       }
     }
   }
+}
+
+// 8 bf16 of row `row`, columns 32g + 8k .. +8, of a block-diagonal [128 x 128] K-major tile (two 64-column chunks of
+// 128 rows x 128 B, 128B swizzle)
+__device__ __forceinline__ void store_diag8(uint8_t* tile, int row, int g, int k, const float (&v)[8]) {
+  uint8_t* rowp = tile + (g >> 1) * kTile + (row >> 3) * 1024 + (row & 7) * 128;
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(rowp + ((((g & 1) * 4 + k) ^ (row & 7)) << 4)) = u;
 }
 
 struct RowCtx {
@@ -167,6 +187,40 @@ __device__ __forceinline__ void finish_scores(float (&s)[32], const uint32_t (&a
   }
 }
 
+// The row's 32 bias values, fetched BEFORE the score MMA is waited for (L2 latency off the critical path).
+__device__ __forceinline__ void load_bias_row(float4 (&bq)[8], const float* bias, const RowCtx& c, int Lq, int Lk) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) bq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias == nullptr) return;
+  const float* brow = bias + (static_cast<long long>(c.h) * Lq + (c.i < Lq ? c.i : 0)) * Lk;
+  if ((Lk & 3) == 0 && (reinterpret_cast<uintptr_t>(brow) & 15) == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q * 4 < Lk) bq[q] = __ldg(reinterpret_cast<const float4*>(brow) + q);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (q * 4 + e < Lk) v[e] = __ldg(brow + q * 4 + e);
+      bq[q] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+// scores of columns 8k .. 8k+7 of one row: acc * scale + bias, masked keys -> finfo.min (keys >= Lk: caller ignores)
+__device__ __forceinline__ void score8(float (&s)[8], const uint32_t (&acc)[8], int k, uint32_t visible, float scale,
+                                       const float4& b0, const float4& b1) {
+  const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const uint32_t vis = visible >> (k * 8);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float v = __uint_as_float(acc[e]) * scale + bv[e];
+    s[e] = ((vis >> e) & 1u) ? v : kMaskedScore;
+  }
+}
+
 struct FwdP {
   int B, H, Lq, Lk;
   __nv_bfloat16* out; long long ldo;
@@ -218,19 +272,30 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   VQA_STAMP(2);
 
   const int npairs = a.B * a.H;
-  if (t == 0) {
-    mbar_expect_tx(bar_tma, 3u * CH * kPairs * kBox);
-    for (int g = 0; g < kPairs; ++g) {
+  // one TMA box per lane of warp 0 (operand, pair, 64-column chunk): a single warp-level issue instead of 12..24 serial ones
+  if (warp == 0) {
+    if (t == 0) mbar_expect_tx(bar_tma, 3u * CH * kPairs * kBox);
+    __syncwarp();
+    if (t < 3 * CH * kPairs) {
+      const int opnd = t / (CH * kPairs), rem = t - opnd * (CH * kPairs);
+      const int g = rem / CH, c = rem - g * CH;
       int pr = blockIdx.x * kPairs + g;
       if (pr >= npairs) pr = npairs - 1;      // duplicate the last pair: finite data, results discarded
       const int b = pr / a.H, h = pr - b * a.H;
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        tma_load_2d(sQ + c * kTile + g * kBox, &tmQ, bar_tma, h * HD + c * 64, b * a.Lq);
-        tma_load_2d(sK + c * kTile + g * kBox, &tmK, bar_tma, h * HD + c * 64, b * a.Lk);
-        tma_load_2d(sV + c * kTile + g * kBox, &tmV, bar_tma, h * HD + c * 64, b * a.Lk);
-      }
+      const uint32_t dst = (opnd == 0 ? sQ : (opnd == 1 ? sK : sV)) + c * kTile + g * kBox;
+      const CUtensorMap* tm = opnd == 0 ? &tmQ : (opnd == 1 ? &tmK : &tmV);
+      tma_load_2d(dst, tm, bar_tma, h * HD + c * 64, b * (opnd == 0 ? a.Lq : a.Lk));
     }
+  }
+  __syncwarp();
+  // per-row context (mask ballot, dropout bits, bias row) is computed while the TMA loads are in flight
+  const RowCtx rc = row_ctx(a.B, a.H, a.Lq, a.Lk, a.key_mask);
+  const DropCtx dc = drop_ctx(a.drop_p, a.sid, a.rng);
+  const uint32_t keep = keep_bits(dc, static_cast<unsigned long long>(rc.prow) * a.Lk, a.Lk);
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  float4 bq[8];
+  load_bias_row(bq, a.bias, rc, a.Lq, a.Lk);
+  if (t == 0) {
     mbar_wait(bar_tma, 0);
     tc_fence_after();
     VQA_STAMP(3);
@@ -244,40 +309,49 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   __syncwarp();
 
-  const RowCtx rc = row_ctx(a.B, a.H, a.Lq, a.Lk, a.key_mask);
-  const DropCtx dc = drop_ctx(a.drop_p, a.sid, a.rng);
-  const uint32_t keep = keep_bits(dc, static_cast<unsigned long long>(rc.prow) * a.Lk, a.Lk);
-  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-
   VQA_STAMP(4);
   mbar_wait(bar_mma, 0);
   tc_fence_after();
   VQA_STAMP(5);
-  float p[32];
-  {
-    uint32_t acc[32];
-    tmem_ld_32x32(tmem + lane_base + warp * 32, acc);
-    tmem_ld_wait();
-    finish_scores(p, acc, rc, a.scale, a.bias, a.Lq, a.Lk);
-  }
+  const uint32_t t_s = tmem + lane_base + warp * 32;     // this row's 32 scores (diagonal block of the pair)
+  // pass 1: row maximum
   float mx = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < 32; ++j)
-    if ((rc.in_range >> j) & 1u) mx = fmaxf(mx, p[j]);
+  for (int k = 0; k < 4; ++k) {
+    if (k * 8 >= a.Lk) break;
+    uint32_t acc[8];
+    tmem_ld_32x8(t_s + k * 8, acc);
+    tmem_ld_wait();
+    float sc[8];
+    score8(sc, acc, k, rc.visible, a.scale, bq[2 * k], bq[2 * k + 1]);
+    const uint32_t inr = rc.in_range >> (k * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if ((inr >> e) & 1u) mx = fmaxf(mx, sc[e]);
+  }
+  // pass 2: exp, row sum, dropout, bf16 P (unnormalised: the 1/sum goes onto O, flash style)
   float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float e = ((rc.in_range >> j) & 1u) ? __expf(p[j] - mx) : 0.f;
-    p[j] = e;
-    sum += e;
+  for (int k = 0; k < 4; ++k) {
+    if (k * 8 >= a.Lk) break;
+    uint32_t acc[8];
+    tmem_ld_32x8(t_s + k * 8, acc);
+    tmem_ld_wait();
+    float sc[8];
+    score8(sc, acc, k, rc.visible, a.scale, bq[2 * k], bq[2 * k + 1]);
+    const uint32_t inr = rc.in_range >> (k * 8), kp = keep >> (k * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float ex = ((inr >> e) & 1u) ? __expf(sc[e] - mx) : 0.f;
+      sum += ex;
+      sc[e] = ((kp >> e) & 1u) ? ex : 0.f;
+    }
+    store_diag8(Pg, t, warp, k, sc);
   }
   const float inv = 1.f / sum;
   if (rc.row_ok && a.stats != nullptr) {
     *reinterpret_cast<float2*>(a.stats + 2 * rc.prow) = make_float2(mx, inv);
   }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) p[j] = ((keep >> j) & 1u) ? p[j] * inv * dc.scale : 0.f;
-  store_diag_row(Pg, t, warp, p);
   VQA_STAMP(6);
   fence_async_smem();
   tc_fence_before();
@@ -299,7 +373,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   VQA_STAMP(8);
   __nv_bfloat16* op = a.out + (static_cast<long long>(rc.b) * a.Lq + rc.i) * a.ldo + rc.h * HD;
-  store_tmem_row<HD>(tmem + lane_base + 128, op, rc.row_ok);
+  store_tmem_row<HD>(tmem + lane_base + 128, op, rc.row_ok, inv * dc.scale);
 
   VQA_STAMP(9);
   tc_fence_before();
@@ -369,20 +443,33 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   VQA_STAMP(2);
 
   const int npairs = a.B * a.H;
-  if (t == 0) {
-    mbar_expect_tx(bar_tma, 4u * CH * kPairs * kBox);
-    for (int g = 0; g < kPairs; ++g) {
+  if (warp == 0) {     // one TMA box per lane: (operand, pair, 64-column chunk)
+    if (t == 0) mbar_expect_tx(bar_tma, 4u * CH * kPairs * kBox);
+    __syncwarp();
+    if (t < 4 * CH * kPairs) {
+      const int opnd = t / (CH * kPairs), rem = t - opnd * (CH * kPairs);
+      const int g = rem / CH, c = rem - g * CH;
       int pr = blockIdx.x * kPairs + g;
       if (pr >= npairs) pr = npairs - 1;
       const int b = pr / a.H, h = pr - b * a.H;
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        tma_load_2d(sQ + c * kTile + g * kBox, &tmQ, bar_tma, h * HD + c * 64, b * a.Lq);
-        tma_load_2d(sdO + c * kTile + g * kBox, &tmdO, bar_tma, h * HD + c * 64, b * a.Lq);
-        tma_load_2d(sK + c * kTile + g * kBox, &tmK, bar_tma, h * HD + c * 64, b * a.Lk);
-        tma_load_2d(sV + c * kTile + g * kBox, &tmV, bar_tma, h * HD + c * 64, b * a.Lk);
-      }
+      const uint32_t dst = (opnd == 0 ? sQ : (opnd == 1 ? sdO : (opnd == 2 ? sK : sV))) + c * kTile + g * kBox;
+      const CUtensorMap* tm = opnd == 0 ? &tmQ : (opnd == 1 ? &tmdO : (opnd == 2 ? &tmK : &tmV));
+      tma_load_2d(dst, tm, bar_tma, h * HD + c * 64, b * (opnd < 2 ? a.Lq : a.Lk));
     }
+  }
+  __syncwarp();
+  const RowCtx rc = row_ctx(a.B, a.H, a.Lq, a.Lk, a.key_mask);
+  const DropCtx dc = drop_ctx(a.drop_p, a.sid, a.rng);
+  const uint32_t keep = keep_bits(dc, static_cast<unsigned long long>(rc.prow) * a.Lk, a.Lk);
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  float4 bq[8];
+  load_bias_row(bq, a.bias, rc, a.Lq, a.Lk);
+  float mx = 0.f, inv = 0.f;
+  if (rc.row_ok) {
+    const float2 st = *reinterpret_cast<const float2*>(a.stats + 2 * rc.prow);
+    mx = st.x; inv = st.y;
+  }
+  if (t == 0) {
     mbar_wait(bar_tma, 0);
     tc_fence_after();
     VQA_STAMP(3);
@@ -402,66 +489,67 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   __syncwarp();
 
-  const RowCtx rc = row_ctx(a.B, a.H, a.Lq, a.Lk, a.key_mask);
-  const DropCtx dc = drop_ctx(a.drop_p, a.sid, a.rng);
-  const uint32_t keep = keep_bits(dc, static_cast<unsigned long long>(rc.prow) * a.Lk, a.Lk);
-  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-  float mx = 0.f, inv = 0.f;
-  if (rc.row_ok) {
-    const float2 st = *reinterpret_cast<const float2*>(a.stats + 2 * rc.prow);
-    mx = st.x; inv = st.y;
-  }
-
   VQA_STAMP(4);
   mbar_wait(bar_mma, 0);
   tc_fence_after();
   VQA_STAMP(5);
-  float p[32], ds[32];
-  {
-    uint32_t acc[32];
-    tmem_ld_32x32(tmem + lane_base + warp * 32, acc);
-    tmem_ld_wait();
-    finish_scores(p, acc, rc, a.scale, a.bias, a.Lq, a.Lk);
-    tmem_ld_32x32(tmem + lane_base + 128 + warp * 32, acc);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) ds[j] = __uint_as_float(acc[j]);
-  }
+  const uint32_t t_s = tmem + lane_base + warp * 32;          // S block of this row
+  const uint32_t t_dp = tmem + lane_base + 128 + warp * 32;   // dP block of this row
   // rows that do not exist (i >= Lq, pair beyond B*H) get P = 0 so they add nothing to dK / dV
+  // pass 1: rowdot = sum_j P_j dP_j (dP through the dropout mask)
   float rowdot = 0.f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const bool live = rc.row_ok && ((rc.in_range >> j) & 1u);
-    const float pj = live ? __expf(p[j] - mx) * inv : 0.f;
-    const float m = ((keep >> j) & 1u) ? dc.scale : 0.f;
-    const float dp = live ? ds[j] * m : 0.f;
-    rowdot = fmaf(pj, dp, rowdot);
-    p[j] = pj;
-    ds[j] = dp;
-  }
+  for (int k = 0; k < 4; ++k) {
+    if (k * 8 >= a.Lk) break;
+    uint32_t acc[8], dacc[8];
+    tmem_ld_32x8(t_s + k * 8, acc);
+    tmem_ld_32x8(t_dp + k * 8, dacc);
+    tmem_ld_wait();
+    float sc[8];
+    score8(sc, acc, k, rc.visible, a.scale, bq[2 * k], bq[2 * k + 1]);
+    const uint32_t inr = rc.row_ok ? (rc.in_range >> (k * 8)) : 0u, kp = keep >> (k * 8);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) ds[j] = p[j] * (ds[j] - rowdot);
-  if (a.dbias != nullptr && rc.row_ok) {
-    float* dbrow = a.dbias + (static_cast<long long>(rc.h) * a.Lq + rc.i) * a.Lk;
-    if ((a.Lk & 3) == 0 && (reinterpret_cast<uintptr_t>(dbrow) & 15) == 0) {
-#pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4)
-        if (q4 * 4 < a.Lk)
-          atomicAdd(reinterpret_cast<float4*>(dbrow) + q4,
-                    make_float4(ds[4 * q4], ds[4 * q4 + 1], ds[4 * q4 + 2], ds[4 * q4 + 3]));
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < a.Lk) atomicAdd(dbrow + j, ds[j]);
+    for (int e = 0; e < 8; ++e) {
+      const float pj = ((inr >> e) & 1u) ? __expf(sc[e] - mx) * inv : 0.f;
+      const float dp = ((kp >> e) & 1u) ? __uint_as_float(dacc[e]) * dc.scale : 0.f;
+      rowdot = fmaf(pj, dp, rowdot);
     }
   }
+  // pass 2: dS = P (dP - rowdot); bias gradient; bf16 operands of the three output MMAs
+  float* dbrow = (a.dbias != nullptr && rc.row_ok) ? a.dbias + (static_cast<long long>(rc.h) * a.Lq + rc.i) * a.Lk : nullptr;
+  const bool dbvec = dbrow != nullptr && (a.Lk & 3) == 0 && (reinterpret_cast<uintptr_t>(dbrow) & 15) == 0;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    p[j] = ((keep >> j) & 1u) ? p[j] * dc.scale : 0.f;   // dropped probabilities (operand of dV)
-    ds[j] *= a.scale;                                     // both dQ and dK carry the score scale
+  for (int k = 0; k < 4; ++k) {
+    if (k * 8 >= a.Lk) break;
+    uint32_t acc[8], dacc[8];
+    tmem_ld_32x8(t_s + k * 8, acc);
+    tmem_ld_32x8(t_dp + k * 8, dacc);
+    tmem_ld_wait();
+    float sc[8], ds[8];
+    score8(sc, acc, k, rc.visible, a.scale, bq[2 * k], bq[2 * k + 1]);
+    const uint32_t inr = rc.row_ok ? (rc.in_range >> (k * 8)) : 0u, kp = keep >> (k * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float pj = ((inr >> e) & 1u) ? __expf(sc[e] - mx) * inv : 0.f;
+      const float m = ((kp >> e) & 1u) ? dc.scale : 0.f;
+      ds[e] = pj * (__uint_as_float(dacc[e]) * m - rowdot);
+      sc[e] = pj * m;                      // dropped probabilities (operand of dV)
+    }
+    if (dbrow != nullptr) {
+      if (dbvec) {
+        atomicAdd(reinterpret_cast<float4*>(dbrow) + 2 * k, make_float4(ds[0], ds[1], ds[2], ds[3]));
+        atomicAdd(reinterpret_cast<float4*>(dbrow) + 2 * k + 1, make_float4(ds[4], ds[5], ds[6], ds[7]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (k * 8 + e < a.Lk) atomicAdd(dbrow + k * 8 + e, ds[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ds[e] *= a.scale;   // both dQ and dK carry the score scale
+    store_diag8(Pdg, t, warp, k, sc);
+    store_diag8(dSg, t, warp, k, ds);
   }
-  store_diag_row(Pdg, t, warp, p);
-  store_diag_row(dSg, t, warp, ds);
   VQA_STAMP(6);
   fence_async_smem();
   tc_fence_before();
@@ -494,12 +582,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   VQA_STAMP(8);
   {
     __nv_bfloat16* qp = a.dq + (static_cast<long long>(rc.b) * a.Lq + rc.i) * a.lddq + rc.h * HD;
-    store_tmem_row<HD>(tmem + lane_base + cDQ, qp, rc.row_ok);
+    store_tmem_row<HD>(tmem + lane_base + cDQ, qp, rc.row_ok, 1.f);
     const bool key_ok = rc.pair_ok && rc.i < a.Lk;
     __nv_bfloat16* kp = a.dk + (static_cast<long long>(rc.b) * a.Lk + rc.i) * a.lddk + rc.h * HD;
-    store_tmem_row<HD>(tmem + lane_base + cDK, kp, key_ok);
+    store_tmem_row<HD>(tmem + lane_base + cDK, kp, key_ok, 1.f);
     __nv_bfloat16* vp = a.dv + (static_cast<long long>(rc.b) * a.Lk + rc.i) * a.lddv + rc.h * HD;
-    store_tmem_row<HD>(tmem + lane_base + cDV, vp, key_ok);
+    store_tmem_row<HD>(tmem + lane_base + cDV, vp, key_ok, 1.f);
   }
   VQA_STAMP(9);
   tc_fence_before();
