@@ -189,7 +189,7 @@ def profile_plans(pkg, model, st):
     rows = []
     with torch.cuda.stream(side):
         sp = ctypes.c_void_p(side.cuda_stream)
-        for plan in [st.fwd] + [s.plan for s in st.bwd_segments]:
+        for plan in list(st.fwd_plans) + [s.plan for s in st.bwd_segments]:
             n = lib.vqa_plan_size(plan)
             best = None
             for _ in range(3):

@@ -219,6 +219,13 @@ class Engine:
         self.use_graphs = _env_flag("VQA_B200_GRAPHS", True)
         self.use_lanes = _env_flag("VQA_B200_LANES", True)
         self.use_tc_attention = _env_flag("VQA_B200_TC_ATTENTION", True)
+        # The fused optimizer runs on its own stream and only this engine's consumers of the parameters wait for it,
+        # so the next step's frozen backbone (which needs nothing but the images) overlaps the HBM-bound AdamW pass.
+        self.async_optimizer = _env_flag("VQA_B200_ASYNC_OPTIMIZER", True) and self.use_lanes
+        self.s_vis = None           # vision stream (backbone + projection of the forward)
+        self.s_opt = None           # optimizer stream
+        self.opt_event = None       # recorded after the last fused optimizer pass
+        self.ev_vis = None
         self.vision_sig = None
         self.param_sig = None
         self.shadow_fresh = False
@@ -358,19 +365,43 @@ class Engine:
         return tuple(p._version for p in self.params)
 
     def _refresh_shadow(self):
-        """bf16 copies of the fp32 master weights (what the GEMMs read) + the conv view of the projection."""
+        """bf16 copies of the fp32 master weights (what the GEMMs read), on the current stream.  Only needed when
+        something other than the fused optimizer changed the parameters (it writes the shadow itself)."""
         sig = self._param_signature()
-        r = self.rec(None)
         if not (self.shadow_fresh and sig == self.param_sig):
-            r.cast_f32_bf16(self.master, self.shadow, self.total)
+            self.rec(None).cast_f32_bf16(self.master, self.shadow, self.total)
             self.proj_dirty = True
+        self.param_sig = sig
+        self.shadow_fresh = True
+
+    def _refresh_projection(self):
+        """The ConvTranspose2d weight re-expressed as the equivalent 3x3 conv weight (current stream)."""
         if self.proj_dirty:
             proj = self.model._projection()
             Cin, Cout = proj.weight.shape[0], proj.weight.shape[1]
-            r.convT_weight_prep(self.mp(proj.weight), self.proj_w, Cin, Cout)
+            self.rec(None).convT_weight_prep(self.mp(proj.weight), self.proj_w, Cin, Cout)
             self.proj_dirty = False
-        self.param_sig = sig
-        self.shadow_fresh = True
+
+    # ------------------------------------------------------------------------------------------
+    # streams
+    # ------------------------------------------------------------------------------------------
+    def optimizer_stream(self):
+        """Stream the fused optimizer launches on (None: the caller's current stream)."""
+        if not self.async_optimizer:
+            return None
+        if self.s_opt is None:
+            self.s_opt = torch.cuda.Stream(device=self.device)
+        return self.s_opt
+
+    def note_optimizer_launched(self, stream):
+        self.opt_event = torch.cuda.Event()
+        self.opt_event.record(stream)
+
+    def wait_optimizer(self, stream=None):
+        """Order `stream` (default: current) after the last fused optimizer pass.  Called by every consumer of the
+        parameters the engine controls: forward, weight preparation, state_dict(), optimizer.state_dict()."""
+        if self.opt_event is not None:
+            (stream or torch.cuda.current_stream(self.device)).wait_event(self.opt_event)
 
     def note_fused_update(self, covered):
         """Called by VQAFusedAdamW after it updated `covered` of this engine's parameters in place (raw
@@ -398,9 +429,9 @@ class Engine:
             maybe_enable(self)
 
     def prepare(self):
-        """Refresh the derived weight caches (folded BN convs, bf16 shadows) if their sources changed."""
+        """Refresh the folded frozen-backbone weights if their sources changed (the trainable caches are refreshed
+        inside forward(), after the optimizer)."""
         self._prepare_vision()
-        self._refresh_shadow()
 
     def get_plan(self, B, Lt, H, W, training, has_labels, want_features):
         key = (B, Lt, H, W, bool(training), bool(has_labels), bool(want_features))
@@ -415,7 +446,28 @@ class Engine:
         L.check(self.lib.vqa_plan_run(plan, ctypes.c_void_p(self._stream())), "plan_run")
 
     def forward(self, st, ids, mask, labels, images):
-        """Copy the inputs into the plan's static buffers and replay the forward plan."""
+        """Copy the inputs into the plans' static buffers and replay the four forward plans: the vision branch on
+        its own stream (the backbone does not wait for the optimizer), the text branch on the caller's stream."""
+        main = torch.cuda.current_stream(self.device)
+        if self.use_lanes:
+            if self.s_vis is None:
+                self.s_vis = torch.cuda.Stream(device=self.device)
+                self.ev_vis = torch.cuda.Event()
+            vis = self.s_vis
+            ev = torch.cuda.Event()
+            ev.record(main)              # whatever produced the inputs (and last step's backward) is on `main`
+            vis.wait_event(ev)
+            if images.is_cuda:
+                images.record_stream(vis)
+            with torch.cuda.stream(vis):
+                st.images.copy_(images, non_blocking=True)
+                self.run_plan(st.fwd_vis)
+                self.wait_optimizer(vis)
+                self._refresh_projection()
+                self.run_plan(st.fwd_proj)
+                self.ev_vis.record(vis)
+        else:
+            st.images.copy_(images, non_blocking=True)
         st.ids.copy_(ids, non_blocking=True)
         if mask is not None:
             st.mask.copy_(mask, non_blocking=True)
@@ -423,8 +475,16 @@ class Engine:
             st.mask.fill_(1)
         if labels is not None:
             st.labels.copy_(labels, non_blocking=True)
-        st.images.copy_(images, non_blocking=True)
-        self.run_plan(st.fwd)
+        self.wait_optimizer(main)
+        self._refresh_shadow()
+        if not self.use_lanes:
+            self.run_plan(st.fwd_vis)
+            self._refresh_projection()
+            self.run_plan(st.fwd_proj)
+        self.run_plan(st.fwd_text)
+        if self.use_lanes:
+            main.wait_event(self.ev_vis)
+        self.run_plan(st.fwd_fuse)
         self.run_id += 1
         st.run_id = self.run_id
         self.last_state = st

@@ -79,6 +79,9 @@ class ResnetVQAModel(nn.Module):
         self.max_answer_length = 5
         self.temperature_scaler = 1.5
         object.__setattr__(self, "_engine", Engine(self))
+        # the fused optimizer may still be running on its own stream: anything that reads the parameters through
+        # state_dict() (checkpoints, trainer/callbacks.py:34-46) is ordered after it
+        self.register_state_dict_pre_hook(lambda module, prefix, keep_vars: module._engine.wait_optimizer())
         self._load_pretrained()
 
     # the reference always starts from pretrained torchvision / HF weights (model/resnet_vqa_model.py:51-62);
@@ -110,6 +113,12 @@ class ResnetVQAModel(nn.Module):
         if mode == "1" and len(loaded) != 2:
             raise RuntimeError("VQA_B200_PRETRAINED=1 but pretrained weights are not available offline")
         self.pretrained_loaded = loaded
+
+    def named_parameters(self, *args, **kwargs):
+        """Same iterator as nn.Module's; reading parameters through it (or parameters(), state_dict()) is ordered
+        after a fused optimizer pass that may still be running on the engine's optimizer stream."""
+        self._engine.wait_optimizer()
+        return super().named_parameters(*args, **kwargs)
 
     def _projection(self):
         return self.downscale_layer if self.vision_model_name == "resnet50" else self.upscale_layer

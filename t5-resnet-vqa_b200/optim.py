@@ -109,6 +109,8 @@ class VQAFusedAdamW(torch.optim.Optimizer):
     def state_dict(self):
         """torch layout.  The per-group step counter is one tensor shared by the group's parameters here; torch's
         AdamW advances `step` once per parameter, so a checkpoint must carry an independent copy for each."""
+        for eng in {r["engine"] for r in (self._ranges or []) if r["engine"] is not None}:
+            eng.wait_optimizer()
         sd = super().state_dict()
         sd["state"] = {k: {**v, "step": v["step"].clone()} if "step" in v else dict(v)
                        for k, v in sd["state"].items()}
@@ -147,6 +149,14 @@ class VQAFusedAdamW(torch.optim.Optimizer):
             gnorm_ptr = self._gnorm.data_ptr()
         steps = {}
         engines = {}
+        side = {}      # engine -> its optimizer stream (ordered after everything queued on the current stream)
+        for r in self._ranges:
+            eng = r["engine"]
+            if eng is not None and eng not in side:
+                so = eng.optimizer_stream()
+                if so is not None:
+                    so.wait_stream(torch.cuda.current_stream(r["dev"]))
+                side[eng] = so
         for r in self._ranges:
             group = self.param_groups[r["group"]]
             gi = r["group"]
@@ -155,9 +165,10 @@ class VQAFusedAdamW(torch.optim.Optimizer):
                 steps[gi] = float(r["step"].add_(1.0))
             t = steps[gi]
             b1, b2 = group["betas"]
-            s = ctypes.c_void_p(torch.cuda.current_stream(r["dev"]).cuda_stream)
-            r_gnorm, r_max = gnorm_ptr, self.max_grad_norm
             eng = r["engine"]
+            so = side.get(eng) if eng is not None else None
+            s = ctypes.c_void_p((so if so is not None else torch.cuda.current_stream(r["dev"])).cuda_stream)
+            r_gnorm, r_max = gnorm_ptr, self.max_grad_norm
             if eng is not None and eng.pending_clip is not None:   # clip_grad_norm_ deferred its scaling to us
                 r_gnorm, r_max = eng.clip_sumsq.data_ptr(), eng.pending_clip
             L.check(lib.vqa_adamw_amsgrad(
@@ -172,7 +183,15 @@ class VQAFusedAdamW(torch.optim.Optimizer):
         for eng, covered in engines.items():
             eng.note_fused_update(covered)
             eng.pending_clip = None
+            if side.get(eng) is not None:
+                eng.note_optimizer_launched(side[eng])
         return loss
+
+    def zero_grad(self, set_to_none=True):
+        if not set_to_none:      # zeroing in place would race with an optimizer pass still reading the gradients
+            for eng in {r["engine"] for r in (self._ranges or []) if r["engine"] is not None}:
+                eng.wait_optimizer()
+        super().zero_grad(set_to_none=set_to_none)
 
 
 _torch_clip_grad_norm_ = torch.nn.utils.clip_grad_norm_

@@ -23,10 +23,10 @@ class Segment:
 
 class State:
     def destroy(self, lib):
-        for p in [self.fwd] + [s.plan for s in self.bwd_segments]:
+        for p in list(self.fwd_plans) + [s.plan for s in self.bwd_segments]:
             if p:
                 lib.vqa_plan_destroy(p)
-        self.fwd, self.bwd_segments = None, []
+        self.fwd_plans, self.bwd_segments = [], []
 
 
 class _Alloc:
@@ -78,18 +78,21 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     st.glogp = al(B, A, dtype=f32, zero=True)
     st.glogp_used = False
 
-    fwd = lib.vqa_plan_create()
-    r = eng.rec(fwd)
+    # The forward is four plans so that independent parts run on different streams (engine.forward):
+    #   fwd_vis   frozen backbone: needs only the images -> starts while the previous step's optimizer still runs
+    #   fwd_proj  channel projection (trainable weights)  -> vision stream, after the optimizer
+    #   fwd_text  T5 encoder + the start of SGA layer 1    -> main stream, after the optimizer
+    #   fwd_fuse  everything from the first use of the vision tokens on -> main stream, after fwd_proj
+    st.fwd_vis, st.fwd_proj = lib.vqa_plan_create(), lib.vqa_plan_create()
+    st.fwd_text, st.fwd_fuse = lib.vqa_plan_create(), lib.vqa_plan_create()
+    st.fwd_plans = [st.fwd_vis, st.fwd_proj, st.fwd_text, st.fwd_fuse]
+    r = eng.rec(st.fwd_vis)
     M = B * Lt
 
     # =============================================================================================
     # frozen ResNet body (tv:266-277 without avgpool/fc), NHWC bf16, BatchNorm folded
     # =============================================================================================
-    # The backbone + projection chain is independent of the T5 encoder: it is recorded on lane 1 and overlaps the
-    # encoder (lane 0) until the first guided attention needs the vision tokens.
     two_lanes = eng.use_lanes
-    if two_lanes:
-        r.lane(1)
     vm = m.vision_model
     stem_in = al(B, H, W + 8, 8)
     r.image_to_stem(st.images, stem_in, B, H, W)
@@ -149,9 +152,9 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     Ty = Hf * Wf
     My = B * Ty
     y0 = al(My, D)
+    r = eng.rec(st.fwd_proj)
     r.conv(B, Hf, Wf, Cf, D, 3, 1, 1, feat, eng.proj_w, y0, bias=eng.mp(proj.bias), relu=0)
-    if two_lanes:
-        r.lane(0)
+    r = eng.rec(st.fwd_text)
 
     # =============================================================================================
     # T5 encoder (hf:637-792)
@@ -235,8 +238,8 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
                         sv["mean1"], sv["rstd1"], M, D, float(sga.norm1.norm.eps))
         # mhatt2(v=y, k=y, q=x1)
         r.linear(sv["x1b"], M, D, D, eng.sp(m2.linear_q.weight), D, sv["q2"], D, bias=eng.mp(m2.linear_q.bias))
-        if li == 0 and two_lanes:
-            r.join()    # the vision tokens (lane 1) are needed from here on
+        if li == 0:
+            r = eng.rec(st.fwd_fuse)    # the vision tokens (vision stream) are needed from here on
         r.linear(y_bf16, Myl, D, D, eng.sp(m2.linear_v.weight), 2 * D, sv["vk2"], 2 * D,
                  bias=eng.mp(m2.linear_v.bias))
         vk = sv["vk2"]
@@ -268,8 +271,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     r.linear(pooled_b, B, D, D, eng.sp(cls.weight), A, logits, Apad, out_fp32=1, bias=eng.mp(cls.bias), bn=64)
     r.logsoftmax_nll_fwd(logits, Apad, st.labels if has_labels else None, st.logp,
                          st.loss if has_labels else None, B, A)
-    st.fwd = fwd
-    st.n_fwd_launches = lib.vqa_plan_size(fwd)
+    st.n_fwd_launches = sum(lib.vqa_plan_size(p) for p in st.fwd_plans)
 
     # =============================================================================================
     # backward
@@ -506,11 +508,13 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             sp = ctypes.c_void_p(side.cuda_stream)
-            L.check(lib.vqa_plan_run(fwd, sp), "plan warm-up (fwd)")
+            for fp in st.fwd_plans:
+                L.check(lib.vqa_plan_run(fp, sp), "plan warm-up (fwd)")
             for s in segs:
                 L.check(lib.vqa_plan_run(s.plan, sp), "plan warm-up (bwd)")
             side.synchronize()
-            L.check(lib.vqa_plan_capture_graph(fwd, sp), "graph capture (fwd)")
+            for fp in st.fwd_plans:
+                L.check(lib.vqa_plan_capture_graph(fp, sp), "graph capture (fwd)")
             for s in segs:
                 L.check(lib.vqa_plan_capture_graph(s.plan, sp), "graph capture (bwd)")
             side.synchronize()
