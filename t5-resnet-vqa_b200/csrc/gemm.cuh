@@ -75,6 +75,7 @@ struct GemmParams {
   int res_first;              // 1: add the residual before ReLU (ResNet block), else after dropout
   float alpha;                 // scale applied to the accumulator before everything else
   int split_producer;          // 1: B tiles are issued by a second thread (see gemm_kernel.cuh)
+  int dbg_mode;                // bring-up: 1 = skip the MMAs, 2 = skip the loads (VQA_B200_GEMM_DBG)
   long long* dbg_clk;          // bring-up: clock64 stamps of CTA 0 (vqa_debug_gemm_timing), else null
   int dbg_a_lbo, dbg_a_sbo, dbg_b_lbo, dbg_b_sbo;  // bring-up overrides of the MN-major descriptor strides (0 = default)
 };

@@ -178,125 +178,175 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0 || warp == 3 + kEpiWarps) {
     // ===================================== TMA producers =====================================
+    // A tiles are issued from warp 0, B tiles from the last warp, so the two operands' issue latencies overlap.
+    // The k-loop is kept as short as a scalar instruction stream can be: the WHOLE warp runs the (uniform) loop and
+    // polls the barrier, lane 0 alone issues; every per-k-block coordinate is carried incrementally (no division,
+    // no parameter reload inside the loop).  Measured (tools/gemm_dbg.py): the previous generic loop body cost
+    // ~500 cycles per k-block on its own, more than the MMAs of a 128 x 128 x 64 block (256 cycles).
     const bool do_a = warp == 0;
-    // Operands that need several TMA instructions per k-block (MN-major chunks, convolution taps) are issued by two
-    // threads, A from warp 0 and B from the last warp, so their issue latencies overlap; a plain K-major pair
-    // (one box each) is issued by warp 0 alone (measured: tools/gemm_bench.py).
-    const bool split = p.split_producer != 0;
-    const bool do_b = split ? (warp != 0) : (warp == 0);
-    if (lane == 0 && (do_a || do_b)) {
-      auto load2 = [](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
-        if (CTAS == 2) tma_load_2d_pair(dst, m, bar, c0, c1);
-        else tma_load_2d(dst, m, bar, c0, c1);
-      };
-      auto load4 = [](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
-        if (CTAS == 2) tma_load_4d_pair(dst, m, bar, c0, c1, c2, c3);
-        else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
-      };
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = unit; t < total_tiles; t += nunits) {
-        const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN, CTAS, rank);
-        for (int i = 0; i < tc.num_kb; ++i) {
-          const int kb = tc.kb_begin + i;
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          if (i < 7 && t == unit && do_a) VQA_GSTAMP(9 + i);
-          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t sb = sa + C::A_BYTES;
-          // pair: both CTAs' loads are credited to the LEADER's full barrier (the leader issues the MMA)
-          const uint32_t fb = CTAS == 2 ? mapa_shared(full_bar(stage), 0) : full_bar(stage);
-          // one arrival per stage (the leader's A producer); the peer's bytes are simply counted by the same barrier
-          if (leader && do_a) mbar_expect_tx(full_bar(stage), static_cast<uint32_t>(p.stage_tx_bytes) * CTAS);
-          const int nb0 = tc.n0 + rank * (BN / CTAS);   // first B-tile row / column staged by this CTA
-          // pixel box visited by this k-block when the contraction runs over pixels
-          int kw0 = 0, kh0 = 0, kn0 = 0;
-          if (p.a_mode == LOAD_PIXELS_MN || p.b_mode == LOAD_PIXELS_MN) {
-            const int tw = kb % p.tiles_w;
-            const int th = (kb / p.tiles_w) % p.tiles_h;
-            const int tn = kb / (p.tiles_w * p.tiles_h);
-            kw0 = tw * p.bx_w; kh0 = th * p.bx_h; kn0 = tn * p.bx_n;
-          }
-          // ---- A ----
-          if (!do_a) {
-          } else if (p.a_mode == LOAD_2D) {
-            if (!p.a_mn) {
-              load2(sa, &tmA, fb, kb * BK, tc.m0);
-            } else {
-#pragma unroll
-              for (int j = 0; j < BM / 64; ++j)
-                load2(sa + j * kChunkBytes, &tmA, fb, tc.m0 + 64 * j, kb * BK);
-            }
-          } else if (p.a_mode == LOAD_CONV) {
-            const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
-            const int r = tap / p.taps_s, s = tap - r * p.taps_s;
-            load4(sa, &tmA, fb, cc * 64, tc.pw0 * p.stride_w - p.pad_w + s * p.dil_w,
-                  tc.ph0 * p.stride_h - p.pad_h + r, tc.pn0);
-          } else {  // LOAD_PIXELS_MN
-#pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              load4(sa + j * kChunkBytes, &tmA, fb, tc.m0 + 64 * j, kw0, kh0, kn0);
-          }
-          // ---- B ----
-          if (!do_b) {
-          } else if (p.b_mode == LOAD_2D) {
-            if (!p.b_mn) {
-              load2(sb, &tmB, fb, kb * BK, nb0);
-            } else {
-#pragma unroll
-              for (int j = 0; j < BN / CTAS / 64; ++j)
-                load2(sb + j * kChunkBytes, &tmB, fb, nb0 + 64 * j, kb * BK);
-            }
-          } else {  // LOAD_PIXELS_MN: column n -> (tap, input channel)
-            const int tap = nb0 / p.b_tap_cin, ci0 = nb0 - tap * p.b_tap_cin;
-            const int r = tap / p.b_taps_s, s = tap - r * p.b_taps_s;
-#pragma unroll
-            for (int j = 0; j < BN / CTAS / 64; ++j)
-              load4(sb + j * kChunkBytes, &tmB, fb, ci0 + 64 * j, kw0 + s - p.pad_w,
-                    kh0 + r - p.pad_h, kn0);
-          }
+    const int a_mode = p.a_mode, a_mn = p.a_mn, b_mode = p.b_mode, b_mn = p.b_mn;
+    const uint32_t tx_bytes = static_cast<uint32_t>(p.stage_tx_bytes) * CTAS;
+    // pair: both CTAs' loads are credited to the LEADER's full barrier (the leader issues the MMA)
+    const uint32_t fb0 = CTAS == 2 ? mapa_shared(full_bar(0), 0) : full_bar(0);
+    const bool arrive = leader && do_a;   // one arrival per stage; everybody's bytes are counted by the same barrier
+    auto load2 = [](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+      tma_load_2d_e<CTAS>(dst, m, bar, c0, c1);
+    };
+    auto load4 = [](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+      tma_load_4d_e<CTAS>(dst, m, bar, c0, c1, c2, c3);
+    };
+    const bool pdbg = p.dbg_clk != nullptr && blockIdx.x < 2 && do_a;
+    long long pdbg_wait = 0, pdbg_t0 = pdbg ? clock64() : 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    // one pipeline slot: wait until the MMAs of the previous round have released it, announce the bytes, then `issue`
+#define VQA_PRODUCE(ISSUE)                                                            \
+    do {                                                                              \
+      const long long pc0 = pdbg ? clock64() : 0;                                     \
+      mbar_wait_lean(empty_bar(stage), phase ^ 1u);                                   \
+      if (pdbg) pdbg_wait += clock64() - pc0;                                         \
+      const uint32_t fb = fb0 + 8u * stage;                                           \
+      const uint32_t sa = smem_base + stage * C::STAGE_BYTES;                         \
+      const uint32_t sb = sa + C::A_BYTES;                                            \
+      (void)sa; (void)sb;                                                             \
+      if (arrive) mbar_expect_tx_e(full_bar(stage), tx_bytes);                        \
+      ISSUE;                                                                          \
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }                              \
+    } while (0)
+    for (int t = unit; t < total_tiles; t += nunits) {
+      const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN, CTAS, rank);
+      const int nkb = tc.num_kb;
+      if (p.dbg_mode >= 2) {   // bring-up: no loads at all (measures the MMA side alone)
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait_lean(empty_bar(stage), phase ^ 1u);
+          if (arrive) mbar_arrive_e(full_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        continue;
+      }
+      if (do_a) {
+        if (a_mode == LOAD_2D && !a_mn) {
+          int k0 = tc.kb_begin * BK;
+          for (int i = 0; i < nkb; ++i, k0 += BK) VQA_PRODUCE(load2(sa, &tmA, fb, k0, tc.m0));
+        } else if (a_mode == LOAD_2D) {
+          int k0 = tc.kb_begin * BK;
+          for (int i = 0; i < nkb; ++i, k0 += BK)
+            VQA_PRODUCE(load2(sa, &tmA, fb, tc.m0, k0); load2(sa + kChunkBytes, &tmA, fb, tc.m0 + 64, k0));
+        } else if (a_mode == LOAD_CONV) {
+          // k-block -> (filter row r, filter column s, 64-channel chunk cc), advanced like an odometer
+          const int cchunks = p.cchunks, taps_s = p.taps_s, dil_w = p.dil_w;
+          const int tap = tc.kb_begin / cchunks;
+          int cc = tc.kb_begin - tap * cchunks;
+          int r = tap / taps_s;
+          int sx = tap - r * taps_s;
+          const int w0 = tc.pw0 * p.stride_w - p.pad_w, h0 = tc.ph0 * p.stride_h - p.pad_h;
+          for (int i = 0; i < nkb; ++i) {
+            VQA_PRODUCE(load4(sa, &tmA, fb, cc * 64, w0 + sx * dil_w, h0 + r, tc.pn0));
+            if (++cc == cchunks) { cc = 0; if (++sx == taps_s) { sx = 0; ++r; } }
+          }
+        } else {  // LOAD_PIXELS_MN: k-block -> pixel box (tw, th, tn)
+          const int tiles_w = p.tiles_w, tiles_h = p.tiles_h, bx_w = p.bx_w, bx_h = p.bx_h, bx_n = p.bx_n;
+          int tw = tc.kb_begin % tiles_w;
+          int th = (tc.kb_begin / tiles_w) % tiles_h;
+          int tn = tc.kb_begin / (tiles_w * tiles_h);
+          for (int i = 0; i < nkb; ++i) {
+            VQA_PRODUCE(load4(sa, &tmA, fb, tc.m0, tw * bx_w, th * bx_h, tn * bx_n);
+                        load4(sa + kChunkBytes, &tmA, fb, tc.m0 + 64, tw * bx_w, th * bx_h, tn * bx_n));
+            if (++tw == tiles_w) { tw = 0; if (++th == tiles_h) { th = 0; ++tn; } }
+          }
+        }
+      } else {
+        const int nb0 = tc.n0 + rank * (BN / CTAS);   // first B-tile row / column staged by this CTA
+        if (b_mode == LOAD_2D && !b_mn) {
+          int k0 = tc.kb_begin * BK;
+          for (int i = 0; i < nkb; ++i, k0 += BK) VQA_PRODUCE(load2(sb, &tmB, fb, k0, nb0));
+        } else if (b_mode == LOAD_2D) {
+          int k0 = tc.kb_begin * BK;
+          for (int i = 0; i < nkb; ++i, k0 += BK) {
+            VQA_PRODUCE(_Pragma("unroll") for (int j = 0; j < BN / CTAS / 64; ++j)
+                            load2(sb + j * kChunkBytes, &tmB, fb, nb0 + 64 * j, k0));
+          }
+        } else {  // LOAD_PIXELS_MN: column n -> (tap, input channel); k-block -> pixel box
+          const int tiles_w = p.tiles_w, tiles_h = p.tiles_h, bx_w = p.bx_w, bx_h = p.bx_h, bx_n = p.bx_n;
+          const int tap = nb0 / p.b_tap_cin, ci0 = nb0 - tap * p.b_tap_cin;
+          const int r = tap / p.b_taps_s, sx = tap - r * p.b_taps_s;
+          const int dw = sx - p.pad_w, dh = r - p.pad_h;
+          int tw = tc.kb_begin % tiles_w;
+          int th = (tc.kb_begin / tiles_w) % tiles_h;
+          int tn = tc.kb_begin / (tiles_w * tiles_h);
+          for (int i = 0; i < nkb; ++i) {
+            VQA_PRODUCE(_Pragma("unroll") for (int j = 0; j < BN / CTAS / 64; ++j)
+                            load4(sb + j * kChunkBytes, &tmB, fb, ci0 + 64 * j, tw * bx_w + dw, th * bx_h + dh, tn * bx_n));
+            if (++tw == tiles_w) { tw = 0; if (++th == tiles_h) { th = 0; ++tn; } }
+          }
         }
       }
     }
+#undef VQA_PRODUCE
+    if (pdbg && lane == 0) {
+      p.dbg_clk[(blockIdx.x * 11 + 0) * 16 + 12] = pdbg_wait;
+      p.dbg_clk[(blockIdx.x * 11 + 0) * 16 + 13] = clock64() - pdbg_t0;
+    }
   } else if (warp == 1) {
     // ===================================== MMA issuer ========================================
-    if (lane == 0 && leader) {
+    // The whole warp of the leader CTA runs the loop (so every operand is warp-uniform and lives in uniform
+    // registers); lane 0 issues.  Descriptors: constant high word, low word = (address >> 4) advanced by constants.
+    if (leader) {
       const uint32_t idesc = umma_idesc_bf16(BM * CTAS, BN, p.a_mn != 0, p.b_mn != 0);
       const uint32_t a_lbo = p.a_mn ? kChunkBytes : 16u, b_lbo = p.b_mn ? kChunkBytes : 16u;
-      const uint32_t a_kstep = p.a_mn ? 16u * 128u : 32u, b_kstep = p.b_mn ? 16u * 128u : 32u;
+      const uint32_t a_k16 = (p.a_mn ? 16u * 128u : 32u) >> 4, b_k16 = (p.b_mn ? 16u * 128u : 32u) >> 4;
+      const uint64_t da0 = umma_smem_desc(smem_base, a_lbo, 1024u);
+      const uint64_t db0 = umma_smem_desc(smem_base + C::A_BYTES, b_lbo, 1024u);
+      const uint32_t da_hi = static_cast<uint32_t>(da0 >> 32), db_hi = static_cast<uint32_t>(db0 >> 32);
+      const uint32_t da_lo0 = static_cast<uint32_t>(da0), db_lo0 = static_cast<uint32_t>(db0);
+      const int dbg_mode = p.dbg_mode;
+      const bool dbg_on = p.dbg_clk != nullptr && blockIdx.x < 2;
+      long long dbg_wait = 0, dbg_issue = 0;   // bring-up: cycles this warp spent waiting for data / issuing
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = unit; t < total_tiles; t += nunits) {
         const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN, CTAS, rank);
-        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator stage
+        mbar_wait_lean(tmem_empty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int i = 0; i < tc.num_kb; ++i) {
-          mbar_wait(full_bar(stage), phase);
+        const int nkb = tc.num_kb;
+        for (int i = 0; i < nkb; ++i) {
+          const long long c0 = dbg_on ? clock64() : 0;
+          mbar_wait_lean(full_bar(stage), phase);
           tc_fence_after();
+          const long long c1 = dbg_on ? clock64() : 0;
           if (i == 0 && t == unit) VQA_GSTAMP(3);
-          if (i >= 1 && i < 7 && t == unit) VQA_GSTAMP(8 + i);
-          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t sb = sa + C::A_BYTES;
+          const uint32_t soff = static_cast<uint32_t>(stage * (C::STAGE_BYTES >> 4));
+          const uint32_t la = da_lo0 + soff, lb = db_lo0 + soff;
+          if (dbg_mode == 0) {
 #pragma unroll
-          for (int ks = 0; ks < BK / 16; ++ks) {
-            const uint64_t da = umma_smem_desc(sa + ks * a_kstep, a_lbo, 1024u);
-            const uint64_t db = umma_smem_desc(sb + ks * b_kstep, b_lbo, 1024u);
-            if (CTAS == 2) umma_bf16_pair(d_tmem, da, db, idesc, (i | ks) ? 1u : 0u);
-            else umma_bf16(d_tmem, da, db, idesc, (i | ks) ? 1u : 0u);
+            for (int ks = 0; ks < BK / 16; ++ks) {
+              const uint64_t da = (static_cast<uint64_t>(da_hi) << 32) | (la + ks * a_k16);
+              const uint64_t db = (static_cast<uint64_t>(db_hi) << 32) | (lb + ks * b_k16);
+              umma_bf16_e<CTAS>(d_tmem, da, db, idesc, (i | ks) ? 1u : 0u);
+            }
+          } else if (dbg_mode == 2 || dbg_mode == 3) {   // bring-up: 2 = no loads, 3 = no loads and one MMA per block
+            for (int ks = 0; ks < (dbg_mode == 3 ? 1 : BK / 16); ++ks) {
+              const uint64_t da = (static_cast<uint64_t>(da_hi) << 32) | (la + ks * a_k16);
+              const uint64_t db = (static_cast<uint64_t>(db_hi) << 32) | (lb + ks * b_k16);
+              umma_bf16_e<CTAS>(d_tmem, da, db, idesc, (i | ks) ? 1u : 0u);
+            }
           }
           // smem slot reusable (in both CTAs of a pair) once these MMAs retire
-          if (CTAS == 2) umma_commit_pair(empty_bar(stage), 3);
-          else umma_commit(empty_bar(stage));
+          umma_commit_e<CTAS>(empty_bar(stage));
+          if (dbg_on) { const long long c2 = clock64(); dbg_wait += c1 - c0; dbg_issue += c2 - c1; }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         // accumulator complete (fires immediately when num_kb == 0)
-        if (CTAS == 2) umma_commit_pair(tmem_full_bar(acc), 3);
-        else umma_commit(tmem_full_bar(acc));
+        umma_commit_e<CTAS>(tmem_full_bar(acc));
         if (t == unit) VQA_GSTAMP(4);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      if (dbg_on && lane == 0) {
+        p.dbg_clk[(blockIdx.x * 11 + 1) * 16 + 12] = dbg_wait;
+        p.dbg_clk[(blockIdx.x * 11 + 1) * 16 + 13] = dbg_issue;
       }
     }
   } else if (warp == 2 + kEpiWarps) {

@@ -282,6 +282,7 @@ int gemm_op_run(const GemmOp* op, cudaStream_t stream) {
     if (mode < 0) { const char* e = getenv("VQA_B200_SPLIT_PRODUCER"); mode = (e && e[0] == '0') ? 0 : 1; }
     p.split_producer = mode;
   }
+  { static int dm = -1; if (dm < 0) { const char* e = getenv("VQA_B200_GEMM_DBG"); dm = e ? atoi(e) : 0; } p.dbg_mode = dm; }
   p.dbg_a_lbo = g_dbg[0]; p.dbg_a_sbo = g_dbg[1]; p.dbg_b_lbo = g_dbg[2]; p.dbg_b_sbo = g_dbg[3];
   int r = launch_gemm(op->tmA, op->tmB, op->tmOut, op->tmRes, p, op->bn, op->split_k, op->ctas, stream);
   if (r == -2) set_last_error("gemm: this epilogue combination (output type / residual / mask / dropout / accumulate) is not built");

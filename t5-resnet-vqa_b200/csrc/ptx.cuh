@@ -67,6 +67,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Hot-loop variant (producer / MMA issuer): no clock reads in the spin; try_wait suspends in hardware between polls,
+// so an iteration bound is an equally good watchdog and costs one add.
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++n > (1u << 27)) __trap();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA
 // ---------------------------------------------------------------------------------------------
@@ -249,6 +258,89 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
       "h"(cta_mask)
       : "memory");
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// "_e" (elected) variants for the GEMM hot loops: called by a whole CONVERGED warp with warp-uniform operands; one
+// elected lane issues.  Keeping the election inside the asm block (instead of an `if (lane == 0)` region around it)
+// lets ptxas keep the operands in uniform registers without the per-instruction ELECT / R2UR.BROADCAST waterfall loop
+// it emits for code it has to treat as divergent.
+// ---------------------------------------------------------------------------------------------
+#define VQA_ELECT_BEGIN "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+#define VQA_ELECT_END "\n\t}\n"
+__device__ __forceinline__ void mbar_expect_tx_e(uint32_t bar, uint32_t bytes) {
+  asm volatile(VQA_ELECT_BEGIN "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" VQA_ELECT_END ::"r"(bar),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_e(uint32_t bar) {
+  asm volatile(VQA_ELECT_BEGIN "@pe mbarrier.arrive.shared::cta.b64 _, [%0];" VQA_ELECT_END ::"r"(bar) : "memory");
+}
+template <int CTAS>
+__device__ __forceinline__ void tma_load_2d_e(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  if (CTAS == 2) {
+    asm volatile(VQA_ELECT_BEGIN
+                 "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+                 "{%3, %4}], [%2];" VQA_ELECT_END ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+  } else {
+    asm volatile(VQA_ELECT_BEGIN
+                 "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+                 "[%2];" VQA_ELECT_END ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+  }
+}
+template <int CTAS>
+__device__ __forceinline__ void tma_load_4d_e(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                              int c3) {
+  if (CTAS == 2) {
+    asm volatile(VQA_ELECT_BEGIN
+                 "@pe cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+                 "{%3, %4, %5, %6}], [%2];" VQA_ELECT_END ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+  } else {
+    asm volatile(VQA_ELECT_BEGIN
+                 "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+                 "%6}], [%2];" VQA_ELECT_END ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+  }
+}
+// accumulate = 0 overwrites the accumulator (first MMA of a tile)
+template <int CTAS>
+__device__ __forceinline__ void umma_bf16_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  if (CTAS == 2) {
+    asm volatile(VQA_ELECT_BEGIN
+                 ".reg .pred pa;\n\tsetp.ne.b32 pa, %4, 0;\n\t"
+                 "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, pa;" VQA_ELECT_END ::"r"(tmem_d),
+                 "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+                 : "memory");
+  } else {
+    asm volatile(VQA_ELECT_BEGIN
+                 ".reg .pred pa;\n\tsetp.ne.b32 pa, %4, 0;\n\t"
+                 "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;" VQA_ELECT_END ::"r"(tmem_d),
+                 "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+                 : "memory");
+  }
+}
+template <int CTAS>
+__device__ __forceinline__ void umma_commit_e(uint32_t bar) {
+  if (CTAS == 2) {
+    asm volatile(VQA_ELECT_BEGIN
+                 "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 VQA_ELECT_END ::"r"(bar),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+  } else {
+    asm volatile(VQA_ELECT_BEGIN "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 VQA_ELECT_END ::"r"(bar)
+                 : "memory");
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

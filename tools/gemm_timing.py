@@ -8,7 +8,7 @@ from util import Caller
 C = Caller(pkg); lib = pkg.lib.load()
 BF = torch.bfloat16; dev = "cuda"
 names = ["start", "setup done", "pdl_wait done", "first stage full (mma)", "tile0 mma committed", "tile0 acc ready (epi)", "epi loop done", "stores drained", "teardown sync"]
-shapes = [("fwd", 2048, 768, 768, 128, 0, 0), ("fwd", 2048, 768, 768, 128, 1, 0), ("fwd", 2048, 2304, 768, 256, 0, 0),
+shapes = [("fwd", 2048, 768, 3072, 128, 0, 0), ("fwd", 2048, 768, 3072, 256, 0, 0), ("fwd", 2048, 768, 768, 128, 0, 0), ("fwd", 2048, 768, 768, 128, 1, 0), ("fwd", 2048, 2304, 768, 256, 0, 0),
           ("fwd", 2048, 768, 3072, 128, 1, 0), ("wgrad", 768, 768, 2048, 64, 1, 0), ("wgrad", 3072, 768, 2048, 128, 1, 0),
           ("fwd", 2048, 2304, 768, 256, 0, 1), ("fwd", 8192, 3072, 768, 256, 0, 1), ("fwd", 8192, 3072, 768, 256, 0, 0)]
 if len(sys.argv) > 1:
@@ -33,6 +33,7 @@ for kind, M, N, K, bn, fp32, pair in shapes:
     print("%s M%d N%d K%d bn%d fp32=%d pair=%d   cycles since start: producer(w0) mma(w1) epi(w2) epi(w9)" % (kind, M, N, K, bn, fp32, pair))
     for i, n in enumerate(names):
         print("   %-26s" % n + "".join("%9s" % (str(int(t[w, i]) - t0) if int(t[w, i]) else "-") for w in (0, 1, 2, 9)))
+    print("   cta0: producer cycles waiting for empty slots %d of %d total | MMA warp cycles waiting for data %d, issuing %d" % (int(t[0, 12]), int(t[0, 13]), int(t[1, 12]), int(t[1, 13])))
     print("   producer cta0 empty-pass i=0..6:", [int(t[0, 9 + i]) - t0 for i in range(7)])
     print("   producer cta1 empty-pass i=0..6:", [int(t[11, 9 + i]) - int(t[11, 0]) for i in range(7)], "cta1 start-cta0 start", int(t[11, 0]) - t0)
     print("   mma cta0 full-pass i=1..6      :", [int(t[1, 9 + i]) - t0 for i in range(6)])
