@@ -18,19 +18,38 @@ inline int norm_grid(int M) {
   return g < 1 ? 1 : g;
 }
 
+// Column sums of the per-warp partials in shared memory -> one vector red.add (4 columns) per thread into global:
+// a quarter of the L2 atomic operations of a per-column atomicAdd (the per-address serialisation at the L2 is what
+// bounds these kernels' tails when 256 CTAs add into the same 768 columns).
+template <int D>
+__device__ __forceinline__ void reduce_cols_atomic(const float (*red)[D], float* __restrict__ dst) {
+  for (int c4 = threadIdx.x; c4 < D / 4; c4 += kThreads) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < kWarps; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(&red[j][c4 * 4]);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    atomicAdd(reinterpret_cast<float4*>(dst) + c4, s);
+  }
+}
+
 // --------------------------------------------------------------------------------------------------
 template <int NC>
 __global__ void __launch_bounds__(kThreads)
 rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y_bf16,
                    float* __restrict__ y_f32, float* __restrict__ rstd, int M, float eps, float drop_p,
                    uint32_t sid, const unsigned long long* __restrict__ rng) {
-  pdl_grid_sync();
+  // parameters are only written by optimizer kernels, which are full (event) dependencies of the plan: they may be
+  // read before the programmatic-dependency wait, which only guards the previous kernel's activations
+  pdl_launch_dependents();
   constexpr int D = NC * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const DropCtx dc = drop_ctx(drop_p, sid, rng);
   float wv[NC][8];
 #pragma unroll
   for (int c = 0; c < NC; ++c) load_f32x8(w + (c * 32 + lane) * 8, wv[c]);
+  pdl_wait();
+  const DropCtx dc = drop_ctx(drop_p, sid, rng);
   for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
     const float* xr = x + static_cast<long long>(row) * D;
     float xv[NC][8];
@@ -64,31 +83,40 @@ rmsnorm_bwd_kernel(const void* __restrict__ dy, int dy_fp32, const float* __rest
                    float* __restrict__ dx, float* __restrict__ dw, int M, float drop_p, uint32_t sid,
                    const unsigned long long* __restrict__ rng, __nv_bfloat16* __restrict__ g_out, float g_drop_p,
                    uint32_t g_sid) {
-  pdl_grid_sync();
+  pdl_launch_dependents();
   constexpr int D = NC * 256;
-  __shared__ float red[kWarps][D];
+  __shared__ __align__(16) float red[kWarps][D];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const DropCtx dc = drop_ctx(drop_p, sid, rng);
-  const DropCtx dcg = drop_ctx(g_out != nullptr ? g_drop_p : 0.f, g_sid, rng);
   float wv[NC][8], dwp[NC][8];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    load_f32x8(w + (c * 32 + lane) * 8, wv[c]);
+    load_f32x8(w + (c * 32 + lane) * 8, wv[c]);   // parameters: safe before the dependency wait (see rmsnorm_fwd)
 #pragma unroll
     for (int i = 0; i < 8; ++i) dwp[c][i] = 0.f;
   }
+  pdl_wait();
+  const DropCtx dc = drop_ctx(drop_p, sid, rng);
+  const DropCtx dcg = drop_ctx(g_out != nullptr ? g_drop_p : 0.f, g_sid, rng);
   for (int row = blockIdx.x * kWarps + warp; row < M; row += gridDim.x * kWarps) {
     const long long base = static_cast<long long>(row) * D;
     const float r = rstd[row];
-    float xv[NC][8], g[NC][8];
+    float xv[NC][8], g[NC][8], dr[NC][8];
     float dot = 0.f;
+    // every load of the row is issued before the first use (one memory round trip per row instead of three)
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const long long col = (c * 32 + lane) * 8;
       load_f32x8(x + base + col, xv[c]);
+      if (dy_fp32) load_f32x8(static_cast<const float*>(dy) + base + col, g[c]);
+      else load_bf16x8(static_cast<const __nv_bfloat16*>(dy) + base + col, g[c]);
+      if (dres != nullptr) load_f32x8(dres + base + col, dr[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const long long col = (c * 32 + lane) * 8;
       float d[8];
-      if (dy_fp32) load_f32x8(static_cast<const float*>(dy) + base + col, d);
-      else load_bf16x8(static_cast<const __nv_bfloat16*>(dy) + base + col, d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d[i] = g[c][i];
       drop8(dc, static_cast<unsigned long long>(base + col), d);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -106,10 +134,8 @@ rmsnorm_bwd_kernel(const void* __restrict__ dy, int dy_fp32, const float* __rest
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = r * g[c][i] - xv[c][i] * k;
       if (dres != nullptr) {
-        float dr[8];
-        load_f32x8(dres + base + col, dr);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] += dr[i];
+        for (int i = 0; i < 8; ++i) o[i] += dr[c][i];
       }
       store_f32x8(dx + base + col, o);
       if (g_out != nullptr) {   // dropout-masked bf16 copy: the GEMM operand of the next sub-layer's backward
@@ -124,12 +150,7 @@ rmsnorm_bwd_kernel(const void* __restrict__ dy, int dy_fp32, const float* __rest
 #pragma unroll
       for (int i = 0; i < 8; ++i) red[warp][(c * 32 + lane) * 8 + i] = dwp[c][i];
     __syncthreads();
-    for (int col = threadIdx.x; col < D; col += kThreads) {
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < kWarps; ++j) s += red[j][col];
-      atomicAdd(dw + col, s);
-    }
+    reduce_cols_atomic<D>(red, dw);
   }
 }
 
@@ -190,7 +211,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, 
                      const unsigned long long* __restrict__ rng, float* __restrict__ g_colsum) {
   pdl_grid_sync();
   constexpr int D = NC * 256;
-  __shared__ float red[kWarps][D];
+  __shared__ __align__(16) float red[kWarps][D];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const DropCtx dcg = drop_ctx(g_out != nullptr ? g_drop_p : 0.f, g_sid, rng);
   float gsp[NC][8];
@@ -248,24 +269,14 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, 
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[warp][(c * 32 + lane) * 8 + i] = dgp[c][i];
   __syncthreads();
-  for (int col = threadIdx.x; col < D; col += kThreads) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < kWarps; ++j) s += red[j][col];
-    atomicAdd(dgamma + col, s);
-  }
+  reduce_cols_atomic<D>(red, dgamma);
   __syncthreads();
 #pragma unroll
   for (int c = 0; c < NC; ++c)
 #pragma unroll
     for (int i = 0; i < 8; ++i) red[warp][(c * 32 + lane) * 8 + i] = dbp[c][i];
   __syncthreads();
-  for (int col = threadIdx.x; col < D; col += kThreads) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < kWarps; ++j) s += red[j][col];
-    atomicAdd(dbeta + col, s);
-  }
+  reduce_cols_atomic<D>(red, dbeta);
   if (g_out != nullptr && g_colsum != nullptr) {
     __syncthreads();
 #pragma unroll
@@ -273,12 +284,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, 
 #pragma unroll
       for (int i = 0; i < 8; ++i) red[warp][(c * 32 + lane) * 8 + i] = gsp[c][i];
     __syncthreads();
-    for (int col = threadIdx.x; col < D; col += kThreads) {
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < kWarps; ++j) s += red[j][col];
-      atomicAdd(g_colsum + col, s);
-    }
+    reduce_cols_atomic<D>(red, g_colsum);
   }
 }
 

@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 using namespace vqa;
 
@@ -130,6 +131,21 @@ inline int stream_grid(long long items, int threads) {
   return b < 1 ? 1 : static_cast<int>(b);
 }
 
+// Persistent grid of the AdamW pass.  Measured on the whole step (bench.py, B200): 16 / 4 / 3 / 2 CTAs per SM give
+// 5.98 / 6.00 / 6.04 / 6.13 ms, i.e. leaving thread slots free for the next step's backbone convolutions (which run
+// beside this pass on another stream) buys nothing: both are HBM-bound there.  VQA_B200_ADAMW_CTAS overrides.
+inline int adamw_grid(long long items, int threads) {
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    const char* e = getenv("VQA_B200_ADAMW_CTAS");
+    per_sm = e ? atoi(e) : 16;
+    if (per_sm < 1 || per_sm > 16) per_sm = 16;
+  }
+  long long b = (items + threads - 1) / threads;
+  if (b > 148LL * per_sm) b = 148LL * per_sm;
+  return b < 1 ? 1 : static_cast<int>(b);
+}
+
 }  // namespace
 
 extern "C" {
@@ -176,7 +192,7 @@ int vqa_adamw_amsgrad(void* plan, float* p, const float* g, float* m, float* v, 
   h.max_norm = max_norm; h.amsgrad = amsgrad;
   note_op("adamw", 0.0, (amsgrad ? 36.0 : 28.0) * static_cast<double>(n) + (shadow ? 2.0 * n : 0.0));
   return submit(plan, stream, [=](cudaStream_t s) {
-    launch_pdl(adamw_kernel, dim3(stream_grid((n >> 2) + 4, 256)), dim3(256), 0, s, p, g, m, v, vmax, static_cast<__nv_bfloat16*>(shadow), n, h,
+    launch_pdl(adamw_kernel, dim3(adamw_grid((n >> 2) + 4, 256)), dim3(256), 0, s, p, g, m, v, vmax, static_cast<__nv_bfloat16*>(shadow), n, h,
                                                                 gnorm_sq);
     return launch_status("adamw");
   });

@@ -11,9 +11,33 @@ names = ["start", "setup done", "pdl_wait done", "first stage full (mma)", "tile
 shapes = [("fwd", 2048, 768, 3072, 128, 0, 0), ("fwd", 2048, 768, 3072, 256, 0, 0), ("fwd", 2048, 768, 768, 128, 0, 0), ("fwd", 2048, 768, 768, 128, 1, 0), ("fwd", 2048, 2304, 768, 256, 0, 0),
           ("fwd", 2048, 768, 3072, 128, 1, 0), ("wgrad", 768, 768, 2048, 64, 1, 0), ("wgrad", 3072, 768, 2048, 128, 1, 0),
           ("fwd", 2048, 2304, 768, 256, 0, 1), ("fwd", 8192, 3072, 768, 256, 0, 1), ("fwd", 8192, 3072, 768, 256, 0, 0)]
-if len(sys.argv) > 1:
+if len(sys.argv) > 1 and sys.argv[1] == "conv":
+    shapes = [("conv", 14, 256, 1024, 256, 1, 1), ("conv", 14, 256, 1024, 256, 0, 1), ("conv", 56, 64, 256, 256, 1, 1), ("conv", 56, 64, 256, 64, 1, 1),
+              ("conv", 14, 256, 256, 256, 0, 3), ("conv", 28, 128, 512, 256, 1, 1)]
+elif len(sys.argv) > 1:
     shapes = shapes[-3:]
 for kind, M, N, K, bn, fp32, pair in shapes:
+    if kind == "conv":
+        H, Cin, Cout, bn, has_res, R = M, N, K, bn, fp32, pair
+        NB = 64
+        x = torch.randn(NB, H, H, Cin, device=dev).to(BF); w = torch.randn(Cout, R, R, Cin, device=dev).to(BF)
+        b = torch.randn(Cout, device=dev); out = torch.empty(NB, H, H, Cout, device=dev, dtype=BF)
+        rs = torch.randn(NB, H, H, Cout, device=dev).to(BF) if has_res else None
+        buf = torch.zeros(22 * 16, dtype=torch.int64, device=dev)
+        for it in range(3):
+            if it == 2:
+                lib.vqa_debug_gemm_timing(buf.data_ptr())
+            C.conv(NB, H, H, Cin, Cout, R, 1, R // 2, x, w, out, bias=b, residual=rs, relu=1, bn=bn)
+            torch.cuda.synchronize()
+        lib.vqa_debug_gemm_timing(None)
+        t = buf.cpu().view(22, 16)
+        t0 = int(t[0, 0])
+        tiles = ((NB * H * H + 127) // 128) * ((Cout + bn - 1) // bn)
+        print("conv %dx%d %d->%d k%d res=%d bn%d (%d tiles, %.2f per SM)  cycles since start: producer(w0) mma(w1) epi(w2) epi(w9)" % (H, H, Cin, Cout, R, has_res, bn, tiles, tiles / 148))
+        for i, n in enumerate(names):
+            print("   %-26s" % n + "".join("%9s" % (str(int(t[w, i]) - t0) if int(t[w, i]) else "-") for w in (0, 1, 2, 9)))
+        print("   cta0: producer cycles waiting for empty slots %d of %d total | MMA warp cycles waiting for data %d, issuing %d" % (int(t[0, 12]), int(t[0, 13]), int(t[1, 12]), int(t[1, 13])))
+        continue
     A = torch.randn(M, K, device=dev).to(BF); B = torch.randn(N, K, device=dev).to(BF)
     At, Bt = A.t().contiguous(), B.t().contiguous()
     out = torch.empty(M, N, device=dev, dtype=torch.float32 if fp32 else BF)
