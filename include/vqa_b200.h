@@ -89,7 +89,14 @@ typedef struct {
   int bn;        /* output tile width: 64, 128 or 256 */
   int split_k;   /* >1: fp32 out must be zeroed by the caller; partial sums are red.add'ed */
   int cta_pair;  /* 1: CTA pairs (cta_group::2): 256-row MMA, B tile split across two SMs; bn must be 128 or 256 */
+  int ksplit;    /* >1: cluster split-K: ksplit CTAs (one thread-block cluster) per output tile, each contracting a
+                    k-slice; partial sums meet in ks_ws and every epilogue (incl. ReLU / dropout / bf16 output) still
+                    applies.  Needs tiles x ksplit <= 148 and K >= 128 * ksplit; excludes split_k, accumulate, cta_pair */
+  void* ks_ws;   /* device workspace, >= vqa_gemm_ksplit_workspace(M, N, bn, ksplit) bytes, 16-byte aligned; must not be
+                    shared by launches that can run concurrently (other streams / plan lanes) */
+  long long ks_ws_bytes;
 } vqa_gemm_args;
+long long vqa_gemm_ksplit_workspace(int M, int N, int bn, int ksplit);
 int vqa_gemm_bf16(void* plan, const vqa_gemm_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -105,6 +112,7 @@ typedef struct {
   const float* bias; const void* residual; int relu;
   int bn;
   int cta_pair;
+  int ksplit; void* ks_ws; long long ks_ws_bytes;   /* cluster split-K as in vqa_gemm_args (M = N*Ho*Wo, N = Cout) */
 } vqa_conv_args;
 int vqa_conv2d_bf16(void* plan, const vqa_conv_args* a, void* stream);
 

@@ -21,6 +21,12 @@ int vqa_debug_gemm_timing(long long* buf) {
   return 0;
 }
 
+long long vqa_gemm_ksplit_workspace(int M, int N, int bn, int ksplit) {
+  if (ksplit <= 1 || bn <= 0) return 0;
+  const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  return static_cast<long long>(gemm_ksplit_ws_bytes(tiles, ksplit, bn));
+}
+
 int vqa_gemm_bf16(void* plan, const vqa_gemm_args* a, void* stream) {
   Epilogue e;
   e.bias = a->bias; e.relu = a->relu;
@@ -29,6 +35,7 @@ int vqa_gemm_bf16(void* plan, const vqa_gemm_args* a, void* stream) {
   e.rng = reinterpret_cast<const unsigned long long*>(a->rng);
   e.residual = a->residual; e.ldr = a->ldr; e.res_fp32 = a->res_fp32; e.res_first = a->res_first;
   e.alpha = a->alpha; e.accumulate = a->accumulate;
+  e.ksplit = a->ksplit; e.ks_ws = static_cast<float*>(a->ks_ws); e.ks_ws_bytes = static_cast<size_t>(a->ks_ws_bytes);
   GemmOp op;
   int r = gemm_op_init(&op, a->M, a->N, a->K, a->A, a->lda, a->a_mn, a->B, a->ldb, a->b_mn, a->out,
                        a->ldo, a->out_fp32, e, a->bn, a->split_k, a->cta_pair ? 2 : 1);
@@ -43,6 +50,7 @@ int vqa_conv2d_bf16(void* plan, const vqa_conv_args* a, void* stream) {
   g.stride = a->stride; g.pad = a->pad; g.Ho = a->Ho; g.Wo = a->Wo; g.stem7 = a->stem7;
   Epilogue e;
   e.bias = a->bias; e.relu = a->relu; e.residual = a->residual; e.ldr = a->Cout; e.res_fp32 = 0; e.res_first = 1;
+  e.ksplit = a->ksplit; e.ks_ws = static_cast<float*>(a->ks_ws); e.ks_ws_bytes = static_cast<size_t>(a->ks_ws_bytes);
   GemmOp op;
   int r = conv_op_init(&op, g, a->x, a->w, a->out, a->out_fp32, e, a->bn, a->cta_pair ? 2 : 1);
   if (r) return r;

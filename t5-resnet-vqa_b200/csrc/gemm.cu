@@ -11,6 +11,11 @@ int launch_gemm_bn128(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&
 int launch_gemm_bn256(const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, const GemmParams&, int, int, int,
                      int, cudaStream_t);
 
+int gemm_out_tiles(const GemmParams& p, int bn) {
+  const int tiles_m = p.a_mode == LOAD_CONV ? p.tiles_w * p.tiles_h * ((p.Nimg + p.bx_n - 1) / p.bx_n) : (p.M + 127) / 128;
+  return tiles_m * ((p.N + bn - 1) / bn);
+}
+
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
                 const GemmParams& p, int bn, int split_k, int ctas, cudaStream_t stream) {
   int tiles_m;

@@ -74,6 +74,9 @@ struct GemmParams {
   int res_fp32;
   int res_first;              // 1: add the residual before ReLU (ResNet block), else after dropout
   float alpha;                 // scale applied to the accumulator before everything else
+  int ksplit;                  // > 1: cluster split-K: `ksplit` CTAs (one cluster) share an output tile, each contracts a
+                               // k-slice, exchanges partial accumulators through ks_ws and finishes a column range
+  float* ks_ws;                // workspace: clusters x ksplit x (bn/32) x 128 x 32 fp32
   int split_producer;          // 1: B tiles are issued by a second thread (see gemm_kernel.cuh)
   int dbg_mode;                // bring-up: 1 = skip the MMAs, 2 = skip the loads (VQA_B200_GEMM_DBG)
   long long* dbg_clk;          // bring-up: clock64 stamps of CTA 0 (vqa_debug_gemm_timing), else null
@@ -85,6 +88,11 @@ struct GemmParams {
 // tmOut: store map of the output (box = 128 rows / pixel box x 128 bytes); tmRes: same geometry over the bf16 residual.
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
                 const GemmParams& p, int bn, int split_k, int ctas, cudaStream_t stream);
+// number of output tiles (128 x bn) of a launch and the workspace bytes cluster split-K needs for it
+int gemm_out_tiles(const GemmParams& p, int bn);
+inline size_t gemm_ksplit_ws_bytes(int out_tiles, int ksplit, int bn) {
+  return static_cast<size_t>(out_tiles) * ksplit * (bn / 32) * 128 * 32 * sizeof(float);
+}
 // ctas = 2: CTA pairs (cta_group::2, 256-row MMA, the B tile split between the two CTAs); bn must be 128 or 256
 
 }  // namespace vqa

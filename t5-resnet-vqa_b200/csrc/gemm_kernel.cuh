@@ -55,7 +55,7 @@ struct Cfg {
   // output panel [0, 2) and the two-slot bf16 residual ring [2, 4)
   static constexpr int STG_BYTES = 4 * kPanelBytes;
   static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
-  static constexpr int NBARS = 2 * STAGES + 8;  // full[], empty[], tmem_full[2], tmem_empty[2], res_full[2], res_empty[2]
+  static constexpr int NBARS = 2 * STAGES + 9;  // full[], empty[], tmem_full[2], tmem_empty[2], res_full[2], res_empty[2], ksplit
   static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
   static constexpr int TMEM_COLS = 2 * BN;      // two accumulator stages (128, 256 or 512 columns)
 };
@@ -107,7 +107,9 @@ __host__ __device__ constexpr int epi_code(bool out_fp32, int res, bool mask, bo
   return (out_fp32 ? 1 : 0) | (res << 1) | (mask ? 8 : 0) | (drop ? 16 : 0) | (atomic ? 32 : 0);
 }
 
-template <int BN, int STAGES, int EPI, int CTAS>
+// KS: cluster split-K support compiled in (a separate set of instantiations, so that the default kernels do not carry
+// its code: +50 % instructions cost 0.3 ms per training step in instruction-cache misses of ~400 short launches).
+template <int BN, int STAGES, int EPI, int CTAS, bool KS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -131,17 +133,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   auto res_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 4 + a); };
   auto res_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 6 + a); };
+  const uint32_t ks_bar = bar_base + 8u * (2 * STAGES + 8);   // cluster split-K: the peers' partial sums have landed
   const uint32_t tmem_slot = bar_base + 8u * C::NBARS;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + C::BAR_OFF + 8 * C::NBARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = static_cast<int>(fd_tiles_m.d * fd_tiles_n.d) * splits;
-  // scheduling unit: one CTA, or a CTA pair (cluster of 2) that owns two consecutive m-tiles of one n-tile
+  // cluster split-K (CTAS == 1 only): the KSP CTAs of a cluster share one output tile; CTA `krank` contracts k-slice
+  // `krank`, hands the partial sums of the columns it does not own to their owners through p.ks_ws, and finishes
+  // (bias / activation / residual / store) its own column range.  The cluster is co-scheduled by the hardware, so
+  // waiting for a peer can never deadlock, whatever else runs on the GPU.
+  const int KSP = (KS && CTAS == 1 && p.ksplit > 1) ? p.ksplit : 1;
+  const int krank = KSP > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int out_tiles = static_cast<int>(fd_tiles_m.d * fd_tiles_n.d);
+  const int total_tiles = KSP > 1 ? out_tiles : out_tiles * splits;
+  // scheduling unit: one CTA, a CTA pair (cluster of 2) that owns two consecutive m-tiles of one n-tile, or a
+  // split-K cluster
   const int rank = CTAS == 2 ? static_cast<int>(cluster_ctarank()) : 0;
   const bool leader = rank == 0;
-  const int unit = static_cast<int>(blockIdx.x) / CTAS;
-  const int nunits = static_cast<int>(gridDim.x) / CTAS;
+  const int unit = static_cast<int>(blockIdx.x) / (CTAS * KSP);
+  const int nunits = static_cast<int>(gridDim.x) / (CTAS * KSP);
+  // column range this CTA finishes, in 32-column chunks, handed out in 64-column panels: [own_lo, own_hi)
+  constexpr int NCH = BN / 32;
+  int own_lo = 0, own_hi = NCH;
+  if (KS && KSP > 1) {
+    const int npan = NCH / 2, base = npan / KSP, rem = npan - base * KSP;
+    own_lo = 2 * (krank * base + (krank < rem ? krank : rem));
+    own_hi = own_lo + 2 * (base + (krank < rem ? 1 : 0));
+  }
+  auto coord = [&](int t) {
+    return (KS && KSP > 1) ? tile_coord(p, t + krank * out_tiles, fd_tiles_m, fd_tiles_n, KSP, BN, CTAS, rank)
+                   : tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN, CTAS, rank);
+  };
 
   // ---- one-time setup (overlaps the previous kernel's tail under programmatic dependent launch) ----
   VQA_GSTAMP(0);
@@ -161,6 +184,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(res_full_bar(a), 1);
       mbar_init(res_empty_bar(a), kEpiWarps);
     }
+    mbar_init(ks_bar, KSP > 1 ? KSP - 1 : 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -168,7 +192,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     else { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  if (CTAS == 2) cluster_sync_all();   // the peer's barriers must be initialised before anyone signals them
+  if (CTAS == 2 || (KS && KSP > 1)) cluster_sync_all();   // the peers' barriers must be initialised before anyone signals them
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
@@ -214,9 +238,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }                              \
     } while (0)
     for (int t = unit; t < total_tiles; t += nunits) {
-      const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN, CTAS, rank);
+      const TileCoord tc = coord(t);
       const int nkb = tc.num_kb;
-      if (p.dbg_mode >= 2) {   // bring-up: no loads at all (measures the MMA side alone)
+      if (p.dbg_mode >= 2 && p.dbg_mode <= 4) {   // bring-up: no loads at all (measures the MMA side alone)
         for (int i = 0; i < nkb; ++i) {
           mbar_wait_lean(empty_bar(stage), phase ^ 1u);
           if (arrive) mbar_arrive_e(full_bar(stage));
@@ -302,32 +326,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int dbg_mode = p.dbg_mode;
       const bool dbg_on = p.dbg_clk != nullptr && blockIdx.x < 2;
       long long dbg_wait = 0, dbg_issue = 0;   // bring-up: cycles this warp spent waiting for data / issuing
+      uint32_t next_ready = 0;                 // the next stage's full barrier has already been seen complete
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = unit; t < total_tiles; t += nunits) {
-        const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN, CTAS, rank);
+        const TileCoord tc = coord(t);
         mbar_wait_lean(tmem_empty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         const int nkb = tc.num_kb;
         for (int i = 0; i < nkb; ++i) {
           const long long c0 = dbg_on ? clock64() : 0;
-          mbar_wait_lean(full_bar(stage), phase);
+          if (!next_ready) mbar_wait_lean(full_bar(stage), phase);   // else: already seen full by the previous block's poll
           tc_fence_after();
           const long long c1 = dbg_on ? clock64() : 0;
           if (i == 0 && t == unit) VQA_GSTAMP(3);
           const uint32_t soff = static_cast<uint32_t>(stage * (C::STAGE_BYTES >> 4));
           const uint32_t la = da_lo0 + soff, lb = db_lo0 + soff;
           if (dbg_mode == 0) {
+            static_assert(BK == 64, "umma_kblock4_e issues four K = 16 MMAs");
+            const int ns = stage + 1 == STAGES ? 0 : stage + 1;
+            next_ready = umma_kblock4_e<CTAS>(d_tmem, (static_cast<uint64_t>(da_hi) << 32) | la,
+                                              (static_cast<uint64_t>(db_hi) << 32) | lb, a_k16, b_k16, idesc, i ? 1u : 0u,
+                                              empty_bar(stage), full_bar(ns), ns == 0 ? (phase ^ 1u) : phase);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            if (dbg_on) { const long long c2 = clock64(); dbg_wait += c1 - c0; dbg_issue += c2 - c1; }
+            continue;
+          } else if (dbg_mode == 6) {   // bring-up: blocking wait per k-block, four separately elected MMAs (the previous loop)
 #pragma unroll
             for (int ks = 0; ks < BK / 16; ++ks) {
               const uint64_t da = (static_cast<uint64_t>(da_hi) << 32) | (la + ks * a_k16);
               const uint64_t db = (static_cast<uint64_t>(db_hi) << 32) | (lb + ks * b_k16);
               umma_bf16_e<CTAS>(d_tmem, da, db, idesc, (i | ks) ? 1u : 0u);
             }
-          } else if (dbg_mode == 2 || dbg_mode == 3) {   // bring-up: 2 = no loads, 3 = no loads and one MMA per block
+          } else if (dbg_mode == 2 || dbg_mode == 3 || dbg_mode == 5) {   // bring-up: 2 = no loads, 3 = no loads and one MMA per block, 5 = unfused issue
             for (int ks = 0; ks < (dbg_mode == 3 ? 1 : BK / 16); ++ks) {
               const uint64_t da = (static_cast<uint64_t>(da_hi) << 32) | (la + ks * a_k16);
               const uint64_t db = (static_cast<uint64_t>(db_hi) << 32) | (lb + ks * b_k16);
@@ -336,6 +370,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           // smem slot reusable (in both CTAs of a pair) once these MMAs retire
           umma_commit_e<CTAS>(empty_bar(stage));
+          next_ready = 0;
           if (dbg_on) { const long long c2 = clock64(); dbg_wait += c1 - c0; dbg_issue += c2 - c1; }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -356,9 +391,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int slot = 0;
       uint32_t phase = 0;
       for (int t = unit; t < total_tiles; t += nunits) {
-        const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN, CTAS, rank);
-        if (tc.kb_begin != 0) continue;             // the residual is added by the first k-slice only
-        for (int pn = 0; pn < BN / 64; ++pn) {
+        const TileCoord tc = coord(t);
+        if (tc.kb_begin != 0 && KSP == 1) continue;   // atomic split-K: the residual is added by the first k-slice only
+        for (int pn = own_lo / 2; pn < own_hi / 2; ++pn) {
           const int n = tc.n0 + pn * 64;
           if (n >= p.N) break;
           mbar_wait(res_empty_bar(slot), phase ^ 1u);
@@ -400,8 +435,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int rslot = 0;                        // residual ring position
     uint32_t rphase = 0;
     for (int t = unit; t < total_tiles; t += nunits) {
-      const TileCoord tc = tile_coord(p, t, fd_tiles_m, fd_tiles_n, splits, BN, CTAS, rank);
-      const bool first_split = (tc.kb_begin == 0);
+      const TileCoord tc = coord(t);
+      const bool first_split = (tc.kb_begin == 0) || KSP > 1;   // cluster split-K: every CTA finishes its own columns
       const bool add_bias = p.bias != nullptr && first_split;
       const bool add_res = kRes != 0 && first_split;
       const long long grow = static_cast<long long>(tc.m0) + row;     // global row (linear outputs)
@@ -409,10 +444,57 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t t_tile = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
       bool waited = false;
 
+      if (KS && KSP > 1) {
+        // ---- cluster split-K, phase 1: partial sums of the columns other CTAs finish go to the workspace ----
+        mbar_wait(tmem_full_bar(acc), acc_phase);
+        tc_fence_after();
+        waited = true;
+        // workspace layout [cluster][source CTA][chunk][k = 0..7][row] float4: a warp's store / load instruction covers
+        // 32 consecutive float4 (512 contiguous bytes)
+        float4* wsrc = reinterpret_cast<float4*>(p.ks_ws) + (static_cast<size_t>(unit) * KSP + krank) * (NCH * 8 * 128) + row;
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+        for (int c = half; c < NCH; c += 2) {
+          if (c >= own_lo && c < own_hi) continue;
+          const int n = tc.n0 + c * 32;
+          if (!(kOutF32 ? (n < p.N) : ((n & ~63) < p.N))) continue;
+          uint32_t accr[32];
+          if (tc.num_kb > 0) {
+            tmem_ld_32x32(t_tile + static_cast<uint32_t>(c * 32), accr);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) accr[i] = 0u;
+          }
+          float4* dst = wsrc + c * (8 * 128);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            __stcg(dst + k * 128, make_float4(__uint_as_float(accr[4 * k]) * p.alpha, __uint_as_float(accr[4 * k + 1]) * p.alpha,
+                                        __uint_as_float(accr[4 * k + 2]) * p.alpha, __uint_as_float(accr[4 * k + 3]) * p.alpha));
+        }
+        if (own_hi <= own_lo) {   // this CTA finishes nothing: its TMEM reads are over
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        }
+        VQA_GSTAMP(9);
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");   // this thread's partial sums are visible in the cluster
+        named_bar_sync(3, 32 * kEpiWarps);
+        VQA_GSTAMP(10);
+        if (ew == 0 && lane == 0) {
+          // release.cluster: our stores are visible to the owner once it has seen the arrival.  Only CTAs that finish
+          // columns wait (and are therefore still resident); a CTA that owns nothing may already have exited.
+          const int npan = NCH / 2, base = npan / KSP, rem = npan - base * KSP;
+          for (int r = 0; r < KSP; ++r)
+            if (r != krank && base + (r < rem ? 1 : 0) > 0) mbar_arrive_cluster(mapa_shared(ks_bar, r));
+        }
+        if (own_hi > own_lo) mbar_wait_cluster(ks_bar, static_cast<uint32_t>(((t - unit) / nunits) & 1));
+        VQA_GSTAMP(11);
+      }
+
+#pragma unroll 1
+      for (int c = own_lo + half; c < own_hi; c += 2) {
         const int n = tc.n0 + c * 32;
-        const bool last_chunk = (c + 2 >= BN / 32);
+        const bool last_chunk = (c + 2 >= own_hi);
         // uniform over the barrier group: fp32 panels are one chunk wide, bf16 panels two (one per column half)
         const bool active = kOutF32 ? (n < p.N) : ((n & ~63) < p.N);
         float v[32];
@@ -428,6 +510,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint4* mp = reinterpret_cast<const uint4*>(p.relu_mask + grow * p.ldm + n);
 #pragma unroll
           for (int k = 0; k < 4; ++k) rmsk[k] = __ldg(mp + k);
+        }
+        float4 pks[8];
+        if (KS && KSP > 1 && active) {   // first peer's partial sums of this chunk
+          const float4* src = reinterpret_cast<const float4*>(p.ks_ws) +
+                              ((static_cast<size_t>(unit) * KSP + (krank + 1) % KSP) * NCH + c) * (8 * 128) + row;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pks[k] = __ldcg(src + k * 128);
         }
         if (!waited) {
           mbar_wait(tmem_full_bar(acc), acc_phase);
@@ -446,6 +535,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(accr[i]) * p.alpha;
+          if (KS && KSP > 1) {
+            // phase 2: add the peers' partial sums of this chunk (in L2, read past L1).  The first peer's loads were
+            // issued before the accumulator read; every further peer's loads are issued before the previous peer's
+            // values are consumed, so one L2 round trip is exposed per chunk, not one per peer.
+            int r = (krank + 1) % KSP;
+            for (int i = 1; i < KSP; ++i) {
+              float4 cur[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) cur[k] = pks[k];
+              const int rn = (r + 1) % KSP;
+              if (i + 1 < KSP) {
+                const float4* src = reinterpret_cast<const float4*>(p.ks_ws) +
+                                    ((static_cast<size_t>(unit) * KSP + rn) * NCH + c) * (8 * 128) + row;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) pks[k] = __ldcg(src + k * 128);
+              }
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                v[4 * k] += cur[k].x; v[4 * k + 1] += cur[k].y; v[4 * k + 2] += cur[k].z; v[4 * k + 3] += cur[k].w;
+              }
+              r = rn;
+            }
+          }
         }
         if (last_chunk) {
           // all of this warp's TMEM reads of the tile are done: hand the accumulator stage back
@@ -603,23 +715,25 @@ inline int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES, int EPI, int CTAS>
+template <int BN, int STAGES, int EPI, int CTAS, bool KS>
 int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
                 const GemmParams& p, int tiles_m, int tiles_n, int splits, cudaStream_t stream) {
   using C = Cfg<BN, STAGES, CTAS>;
   static_assert(C::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;  // per-process; all devices share the same kernel image attributes
   cudaError_t e;
-  auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, CTAS>;
+  auto kern = gemm_tcgen05_kernel<BN, STAGES, EPI, CTAS, KS>;
   if (!attr_set) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
   const int units_m = (tiles_m + CTAS - 1) / CTAS;     // a pair owns two consecutive m-tiles
-  const int total = units_m * tiles_n * splits;
-  const int max_units = sm_count() / CTAS;
-  const int grid = (total < max_units ? total : max_units) * CTAS;
+  const int ksp = (KS && CTAS == 1 && p.ksplit > 1) ? p.ksplit : 1;   // cluster split-K: a cluster of ksp CTAs per tile
+  const int total = units_m * tiles_n * (ksp > 1 ? 1 : splits);
+  const int max_units = sm_count() / (CTAS * ksp);
+  if (ksp > 1 && total > max_units) return -3;          // one tile per cluster (the workspace is not double-buffered)
+  const int grid = (total < max_units ? total : max_units) * CTAS * ksp;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -629,9 +743,9 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (CTAS == 2) {
+  if (CTAS == 2 || ksp > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    attr[na].val.clusterDim.x = CTAS == 2 ? 2 : ksp; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
@@ -648,8 +762,11 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
   const int code = epi_code(p.out_fp32 != 0, res, p.relu_mask != nullptr, p.drop_p > 0.f, p.atomic_out != 0);
 #define VQA_EPI_CASE(o, r, m, d, a)                                                                   \
   case epi_code(o, r, m, d, a):                                                                       \
-    return launch_impl<BN, STAGES, epi_code(o, r, m, d, a), CTAS>(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, splits, \
-                                                                  stream);
+    if (CTAS == 1 && p.ksplit > 1)                                                                    \
+      return launch_impl<BN, STAGES, epi_code(o, r, m, d, a), CTAS, CTAS == 1>(tmA, tmB, tmOut, tmRes, p, tiles_m,    \
+                                                                               tiles_n, splits, stream);              \
+    return launch_impl<BN, STAGES, epi_code(o, r, m, d, a), CTAS, false>(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, \
+                                                                         splits, stream);
   switch (code) {
     VQA_EPI_CASE(false, 0, false, false, false)  // bf16 out                      (qkv, convs, plain dgrad)
     VQA_EPI_CASE(false, 1, false, false, false)  // bf16 out + bf16 residual      (ResNet block tails)

@@ -22,6 +22,25 @@ void fill_epilogue(GemmParams& p, const Epilogue& e) {
   p.res_fp32 = e.res_fp32;
   p.res_first = e.res_first;
   p.alpha = e.alpha;
+  p.ksplit = e.ksplit > 1 ? e.ksplit : 1;
+  p.ks_ws = e.ks_ws;
+}
+
+// cluster split-K preconditions (the kernel trusts them)
+int check_ksplit(const GemmOp* op, const Epilogue& e, int bn, int split_k, int ctas) {
+  const GemmParams& p = op->p;
+  if (p.ksplit <= 1) return 0;
+  if (ctas != 1 || split_k > 1 || p.atomic_out) { set_last_error("gemm: cluster split-K excludes CTA pairs, split_k and accumulate"); return -1; }
+  if (p.ksplit > 8 || p.ksplit > bn / 64 * 4) { set_last_error("gemm: ksplit must be <= 8"); return -1; }
+  if (p.kb_total < 2 * p.ksplit) { set_last_error("gemm: cluster split-K needs at least 2 k-blocks per slice"); return -1; }
+  const int tiles = gemm_out_tiles(p, bn);
+  if (tiles * p.ksplit > 148) { set_last_error("gemm: cluster split-K needs tiles x ksplit <= 148 (%d x %d)", tiles, p.ksplit); return -1; }
+  if (e.ks_ws == nullptr || e.ks_ws_bytes < gemm_ksplit_ws_bytes(tiles, p.ksplit, bn) ||
+      (reinterpret_cast<uintptr_t>(e.ks_ws) & 15)) {
+    set_last_error("gemm: cluster split-K workspace missing or too small (%zu bytes needed)", gemm_ksplit_ws_bytes(tiles, p.ksplit, bn));
+    return -1;
+  }
+  return 0;
 }
 
 // Pixel box (w, h, images) with at most `rows` output pixels that covers [Wo, Ho, Nimg] with the
@@ -142,6 +161,8 @@ int gemm_op_init(GemmOp* op, int M, int N, int K, const void* A, long long lda, 
   if (r) return r;
   r = finish_output_maps(op, false, 0, 0, 0);
   if (r) return r;
+  r = check_ksplit(op, epi, bn, split_k, ctas);
+  if (r) return r;
   op->bn = bn; op->split_k = split_k < 1 ? 1 : split_k; op->ctas = ctas;
   op->valid = true;
   return 0;
@@ -205,6 +226,8 @@ int conv_op_init(GemmOp* op, const ConvGeom& g, const void* x, const void* w, vo
   if (r) return r;
   r = finish_output_maps(op, true, g.Nimg, g.Ho, g.Wo);
   if (r) return r;
+  r = check_ksplit(op, epi, bn, 1, ctas);
+  if (r) return r;
   op->bn = bn; op->split_k = 1; op->ctas = ctas;
   op->valid = true;
   return 0;
@@ -237,6 +260,7 @@ int conv_wgrad_op_init(GemmOp* op, const ConvGeom& g, const void* dy, const void
   p.out = dw; p.ldo = p.N; p.out_fp32 = 1; p.out_pixels = 0;
   p.atomic_out = split_k > 1 ? 1 : 0;
   p.alpha = 1.f;
+  p.ksplit = 1;
   {
     const uint64_t dims[4] = {static_cast<uint64_t>(g.Cout), static_cast<uint64_t>(g.Wo),
                               static_cast<uint64_t>(g.Ho), static_cast<uint64_t>(g.Nimg)};
@@ -285,7 +309,8 @@ int gemm_op_run(const GemmOp* op, cudaStream_t stream) {
   { static int dm = -1; if (dm < 0) { const char* e = getenv("VQA_B200_GEMM_DBG"); dm = e ? atoi(e) : 0; } p.dbg_mode = dm; }
   p.dbg_a_lbo = g_dbg[0]; p.dbg_a_sbo = g_dbg[1]; p.dbg_b_lbo = g_dbg[2]; p.dbg_b_sbo = g_dbg[3];
   int r = launch_gemm(op->tmA, op->tmB, op->tmOut, op->tmRes, p, op->bn, op->split_k, op->ctas, stream);
-  if (r == -2) set_last_error("gemm: this epilogue combination (output type / residual / mask / dropout / accumulate) is not built");
+  if (r == -3) set_last_error("gemm: cluster split-K needs one output tile per cluster");
+  else if (r == -2) set_last_error("gemm: this epilogue combination (output type / residual / mask / dropout / accumulate) is not built");
   else if (r) set_last_error("gemm launch failed: %s", cudaGetErrorString(static_cast<cudaError_t>(r)));
   return r;
 }

@@ -18,6 +18,9 @@ struct Epilogue {
   int res_first = 0;
   float alpha = 1.f;
   int accumulate = 0;  // fp32 out += result (red.add) instead of store
+  int ksplit = 1;      // > 1: cluster split-K over `ksplit` CTAs per output tile (needs ks_ws; see gemm.cuh)
+  float* ks_ws = nullptr;
+  size_t ks_ws_bytes = 0;
 };
 
 struct GemmOp {

@@ -216,6 +216,20 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(remote_bar) : "memory");
 }
+// wait for a phase whose arrivals come from other CTAs of the cluster (pairs with mbar_arrive_cluster's release)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, n = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && ++n > (1u << 27)) __trap();
+  }
+}
 // TMA loads of a CTA pair: data lands in THIS CTA's shared memory, the byte count is credited to `bar`, which may
 // live in the peer (leader) CTA
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
@@ -341,6 +355,56 @@ __device__ __forceinline__ void umma_commit_e(uint32_t bar) {
                  VQA_ELECT_END ::"r"(bar)
                  : "memory");
   }
+}
+
+// One k-block of the GEMM main loop as a single instruction group: a NON-blocking poll of the next stage's full
+// barrier is issued first, then the four MMAs (K = 16 each) and the commit that releases the stage; the poll's result
+// is read last, so its latency (a passing mbarrier wait costs ~140 cycles on its own, tools/ubench/handshake.cu)
+// overlaps the MMA issue instead of preceding it.  Returns 1 when the next stage is already full.
+// Whole converged warp, warp-uniform operands; descriptors advance by (a_step, b_step) >> 4 encoded bytes per MMA.
+template <int CTAS>
+__device__ __forceinline__ uint32_t umma_kblock4_e(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t a_step,
+                                                   uint32_t b_step, uint32_t idesc, uint32_t accumulate,
+                                                   uint32_t empty_bar, uint32_t next_full_bar, uint32_t next_parity) {
+  uint32_t ready;
+  const uint64_t da1 = da + a_step, da2 = da + 2 * a_step, da3 = da + 3 * a_step;
+  const uint64_t db1 = db + b_step, db2 = db + 2 * b_step, db3 = db + 3 * b_step;
+  if (CTAS == 2) {
+    asm volatile(
+        "{\n\t.reg .pred pe, pa, pt, pw;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 pw, [%13], %14;\n\t"
+        "setp.ne.b32 pa, %11, 0;\n\t"
+        "setp.eq.u32 pt, 0, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %6, %10, pa;\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%1], %3, %7, %10, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%1], %4, %8, %10, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%1], %5, %9, %10, pt;\n\t"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%12], %15;\n\t"
+        "selp.u32 %0, 1, 0, pw;\n\t}\n"
+        : "=r"(ready)
+        : "r"(tmem_d), "l"(da), "l"(da1), "l"(da2), "l"(da3), "l"(db), "l"(db1), "l"(db2), "l"(db3), "r"(idesc),
+          "r"(accumulate), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "h"(static_cast<uint16_t>(3))
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred pe, pa, pt, pw;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 pw, [%13], %14;\n\t"
+        "setp.ne.b32 pa, %11, 0;\n\t"
+        "setp.eq.u32 pt, 0, 0;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %6, %10, pa;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %7, %10, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], %4, %8, %10, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], %5, %9, %10, pt;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t"
+        "selp.u32 %0, 1, 0, pw;\n\t}\n"
+        : "=r"(ready)
+        : "r"(tmem_d), "l"(da), "l"(da1), "l"(da2), "l"(da3), "l"(db), "l"(db1), "l"(db2), "l"(db3), "r"(idesc),
+          "r"(accumulate), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity)
+        : "memory");
+  }
+  return ready;
 }
 
 // ---------------------------------------------------------------------------------------------

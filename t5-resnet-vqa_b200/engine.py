@@ -49,8 +49,22 @@ def t5_relative_buckets(L_q, L_k, num_buckets=32, max_distance=128):
 class _Rec:
     """Thin typed front of the C ABI: appends launches to `plan` (or runs them now when plan is None)."""
 
-    def __init__(self, lib, plan, stream_fn):
+    KS_WS_BYTES = 148 * 8 * 128 * 32 * 4   # largest cluster split-K workspace any launch can need (19.4 MB)
+
+    def __init__(self, lib, plan, stream_fn, ws_store=None):
         self.lib, self.plan, self.stream_fn = lib, plan, stream_fn
+        self._lane = 0
+        # cluster split-K workspaces, one per lane: launches of different lanes / plans may run concurrently and
+        # must not share one.  ws_store (a dict owned by the plan's State) keeps them alive with the plan.
+        self._ws = ws_store if ws_store is not None else {}
+
+    def _ks_workspace(self):
+        key = (self.plan, self._lane)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.empty(self.KS_WS_BYTES, dtype=torch.uint8, device="cuda")
+            self._ws[key] = t
+        return t
 
     def _s(self):
         return None if self.plan is not None else self.stream_fn()
@@ -60,6 +74,7 @@ class _Rec:
 
     # ---- lanes (parallel branches of a plan) ----
     def lane(self, n):
+        self._lane = n
         if self.plan is not None:
             L.check(self.lib.vqa_plan_set_lane(self.plan, n), "plan_set_lane")
 
@@ -87,10 +102,12 @@ class _Rec:
     # ---- contractions ----
     def gemm(self, M, N, K, A, lda, a_mn, B, ldb, b_mn, out, ldo, out_fp32, bias=None, relu=0, relu_mask=None,
              ldm=0, drop_p=0.0, sid=0, rng=None, residual=None, ldr=0, res_fp32=1, alpha=1.0, accumulate=0,
-             bn=None, split_k=1, pair=None):
+             bn=None, split_k=1, pair=None, ksplit=None):
         if bn is None:
-            bn, split_k = pick_tile(M, N, K, out_fp32 and not relu and relu_mask is None and drop_p == 0.0
-                                    and accumulate, split_k)
+            bn, ks = pick_tile(M, N, K, allow_ksplit=not accumulate and split_k == 1 and not pair)
+            if ksplit is None:
+                ksplit = ks
+        ksplit = int(ksplit or 1)
         a = L.GemmArgs()
         a.M, a.N, a.K = M, N, K
         a.A, a.lda, a.a_mn = L.ptr(A), lda, a_mn
@@ -102,6 +119,10 @@ class _Rec:
         a.residual, a.ldr, a.res_fp32, a.res_first = L.ptr(residual), ldr, int(res_fp32), 0
         a.alpha, a.accumulate, a.bn, a.split_k = alpha, int(accumulate), bn, split_k
         a.cta_pair = int(bool(pair)) if pair is not None else 0
+        a.ksplit = ksplit
+        if ksplit > 1:
+            ws = self._ks_workspace()
+            a.ks_ws, a.ks_ws_bytes = ws.data_ptr(), ws.numel()
         L.check(self.lib.vqa_gemm_bf16(self.plan, ctypes.byref(a), self._s()), "gemm")
 
     def linear(self, X, M, K, ldx, W, N, out, ldo, out_fp32=0, **kw):
@@ -117,19 +138,24 @@ class _Rec:
         self.gemm(N, K, M, dY, ldy, 1, X, ldx, 1, dW, K, 1, **kw)
 
     def conv(self, N, H, W, Cin, Cout, R, stride, pad, x, w, out, bias=None, residual=None, relu=1, stem7=0,
-             out_fp32=0, bn=None, pair=None):
+             out_fp32=0, bn=None, pair=None, ksplit=None):
         Ho = (H + 2 * pad - R) // stride + 1
         Wo = (W + 2 * pad - R) // stride + 1
         if bn is None:
             bn = pick_conv_tile(N * Ho * Wo, Cout)
             if pair and bn < 128:
                 bn = 128
+        ksplit = int(ksplit or 1)
         a = L.ConvArgs()
         a.N, a.H, a.W, a.Cin, a.Cout, a.R, a.S = N, H, W, Cin, Cout, R, R
         a.stride, a.pad, a.Ho, a.Wo, a.stem7 = stride, pad, Ho, Wo, stem7
         a.x, a.w, a.out, a.out_fp32 = L.ptr(x), L.ptr(w), L.ptr(out), out_fp32
         a.bias, a.residual, a.relu, a.bn = L.ptr(bias), L.ptr(residual), int(relu), bn
         a.cta_pair = int(bool(pair)) if pair is not None else 0
+        a.ksplit = ksplit
+        if ksplit > 1:
+            ws = self._ks_workspace()
+            a.ks_ws, a.ks_ws_bytes = ws.data_ptr(), ws.numel()
         L.check(self.lib.vqa_conv2d_bf16(self.plan, ctypes.byref(a), self._s()), "conv2d")
         return Ho, Wo
 
@@ -184,17 +210,37 @@ def _tile_cost(tiles, bn):
     return waves * (bn + int(os.environ.get("VQA_B200_TILE_FIXED", "160")))
 
 
-def pick_tile(M, N, K, can_split, split_k=1):
-    """Output tile width for the persistent 128 x bn tcgen05 GEMM (one CTA per SM)."""
+# Launch-time model of the tcgen05 GEMM on B200 (microseconds; tools/gemm_bench.py, graph-replayed, L2-warm):
+# t = fixed(bn) + waves * k_blocks_per_CTA * per_kblock(bn) [+ exchange when a cluster splits K].  It reproduces the
+# measured best configuration of the step's 13 GEMM shapes to within 10 %.
+_GEMM_FIXED = {64: 3.6, 128: 3.8, 256: 4.7}
+_GEMM_KB = {64: 0.20, 128: 0.253, 256: 0.30}
+_GEMM_KSPLIT_EXCHANGE = 1.3
+
+
+def pick_tile(M, N, K, allow_ksplit=True):
+    """(tile width, cluster split-K factor) of the persistent 128 x bn tcgen05 GEMM (one CTA per SM)."""
     tm = (M + 127) // 128
+    kb = (K + 63) // 64
+    # Cluster split-K is opt-in: on the isolated K = 3072 / 2304 GEMMs it is 5..10 % faster (tools/gemm_bench.py), but inside
+    # the step, where two plan lanes keep the SMs busy, co-scheduling whole clusters costs more than the shorter k-loops
+    # save (bench.py on B200: 6.68 ms/step with it, 6.17 without).
+    use_ks = allow_ksplit and _env_flag("VQA_B200_KSPLIT", False)
     best = None
     for bn in (256, 128, 64):
         if bn > 64 and N <= bn // 2:
             continue
-        cost = _tile_cost(tm * ((N + bn - 1) // bn), bn)
-        if best is None or cost < best[0]:
-            best = (cost, bn)
-    return best[1], 1
+        tiles = tm * ((N + bn - 1) // bn)
+        waves = (tiles + N_SM - 1) // N_SM
+        cands = [(1, _GEMM_FIXED[bn] + waves * kb * _GEMM_KB[bn])]
+        if use_ks:
+            for ks in (2, 3, 4):
+                if tiles * ks <= N_SM and kb >= 4 * ks:
+                    cands.append((ks, _GEMM_FIXED[bn] + -(-kb // ks) * _GEMM_KB[bn] + _GEMM_KSPLIT_EXCHANGE))
+        for ks, cost in cands:
+            if best is None or cost < best[0] - 1e-9:
+                best = (cost, bn, ks)
+    return best[1], best[2]
 
 
 def pick_conv_tile(M, Cout):
@@ -319,8 +365,9 @@ class Engine:
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def rec(self, plan=None):
-        return _Rec(self.lib, plan, self._stream)
+    def rec(self, plan=None, ws_store=None):
+        """ws_store: dict that owns the cluster split-K workspaces of the plan being recorded (they must outlive it)."""
+        return _Rec(self.lib, plan, self._stream, ws_store)
 
     # ------------------------------------------------------------------------------------------
     # weight preparation

@@ -18,7 +18,8 @@ class GemmArgs(ctypes.Structure):
                 ("relu_mask", c_vp), ("ldm", c_ll),
                 ("drop_p", c_f), ("drop_sid", c_u32), ("rng", c_vp),
                 ("residual", c_vp), ("ldr", c_ll), ("res_fp32", c_int), ("res_first", c_int),
-                ("alpha", c_f), ("accumulate", c_int), ("bn", c_int), ("split_k", c_int), ("cta_pair", c_int)]
+                ("alpha", c_f), ("accumulate", c_int), ("bn", c_int), ("split_k", c_int), ("cta_pair", c_int),
+                ("ksplit", c_int), ("ks_ws", c_vp), ("ks_ws_bytes", c_ll)]
 
 
 class ConvArgs(ctypes.Structure):
@@ -26,7 +27,8 @@ class ConvArgs(ctypes.Structure):
                 ("R", c_int), ("S", c_int), ("stride", c_int), ("pad", c_int), ("Ho", c_int),
                 ("Wo", c_int), ("stem7", c_int),
                 ("x", c_vp), ("w", c_vp), ("out", c_vp), ("out_fp32", c_int),
-                ("bias", c_vp), ("residual", c_vp), ("relu", c_int), ("bn", c_int), ("cta_pair", c_int)]
+                ("bias", c_vp), ("residual", c_vp), ("relu", c_int), ("bn", c_int), ("cta_pair", c_int),
+                ("ksplit", c_int), ("ks_ws", c_vp), ("ks_ws_bytes", c_ll)]
 
 
 class ConvWgradArgs(ctypes.Structure):
@@ -58,6 +60,7 @@ SIGNATURES = {
     "vqa_version": (c_int, []),
     "vqa_debug_set_umma": (c_int, [c_int, c_int, c_int, c_int]),
     "vqa_debug_gemm_timing": (c_int, [_P]),
+    "vqa_gemm_ksplit_workspace": (c_ll, [c_int, c_int, c_int, c_int]),
     "vqa_plan_create": (c_vp, []),
     "vqa_plan_destroy": (c_int, [_P]),
     "vqa_plan_size": (c_int, [_P]),

@@ -47,6 +47,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     st.training, st.run_id = training, -1
     al = _Alloc(dev)
     st.alloc = al
+    st.ks_store = {}   # cluster split-K workspaces, one per (plan, lane); live as long as the plans
     f32, bf16, i64 = torch.float32, torch.bfloat16, torch.int64
     rng = eng.rng
     D = 768
@@ -86,7 +87,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     st.fwd_vis, st.fwd_proj = lib.vqa_plan_create(), lib.vqa_plan_create()
     st.fwd_text, st.fwd_fuse = lib.vqa_plan_create(), lib.vqa_plan_create()
     st.fwd_plans = [st.fwd_vis, st.fwd_proj, st.fwd_text, st.fwd_fuse]
-    r = eng.rec(st.fwd_vis)
+    r = eng.rec(st.fwd_vis, st.ks_store)
     M = B * Lt
 
     # =============================================================================================
@@ -152,9 +153,9 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     Ty = Hf * Wf
     My = B * Ty
     y0 = al(My, D)
-    r = eng.rec(st.fwd_proj)
+    r = eng.rec(st.fwd_proj, st.ks_store)
     r.conv(B, Hf, Wf, Cf, D, 3, 1, 1, feat, eng.proj_w, y0, bias=eng.mp(proj.bias), relu=0)
-    r = eng.rec(st.fwd_text)
+    r = eng.rec(st.fwd_text, st.ks_store)
 
     # =============================================================================================
     # T5 encoder (hf:637-792)
@@ -239,7 +240,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
         # mhatt2(v=y, k=y, q=x1)
         r.linear(sv["x1b"], M, D, D, eng.sp(m2.linear_q.weight), D, sv["q2"], D, bias=eng.mp(m2.linear_q.bias))
         if li == 0:
-            r = eng.rec(st.fwd_fuse)    # the vision tokens (vision stream) are needed from here on
+            r = eng.rec(st.fwd_fuse, st.ks_store)    # the vision tokens (vision stream) are needed from here on
         r.linear(y_bf16, Myl, D, D, eng.sp(m2.linear_v.weight), 2 * D, sv["vk2"], 2 * D,
                  bias=eng.mp(m2.linear_v.bias))
         vk = sv["vk2"]
@@ -341,7 +342,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
 
     # ---- segment 0: head + SGA ----
     bp = new_segment()
-    r = eng.rec(bp)
+    r = eng.rec(bp, st.ks_store)
     side.bind(r)
     n_small = eng.total - eng.n_big
     r.memset_zero(eng.grad.data_ptr() + 4 * eng.n_big, 4 * n_small)
@@ -434,7 +435,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
 
     # ---- T5 encoder backward, a few blocks per segment; the projection's gradients ride on lane 1 ----
     bp = new_segment()
-    r = eng.rec(bp)
+    r = eng.rec(bp, st.ks_store)
     side.bind(r)
 
     def proj_leaf():
@@ -495,7 +496,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
             close_segment(bp, seg_lo, hi)
             seg_lo = hi
             bp = new_segment()
-            r = eng.rec(bp)
+            r = eng.rec(bp, st.ks_store)
             side.bind(r)
     r.t5_bias_grad(dbias_pos, bucket, eng.gp(relw), nH, Lt, cfg["num_buckets"])
     r.embedding_bwd(st.ids, dH, eng.gp(t5.embed_tokens.weight), M, D, vocab, p_t5, sid_embed, rng)

@@ -88,9 +88,20 @@ def test_tile_heuristics_and_buckets(pkg):
     from t5_resnet_vqa_b200 import engine as E
     from oracle import vqa_oracle as O
     for M, N in [(2048, 768), (2048, 2304), (64, 170), (200704, 64), (3136, 2048), (128, 768)]:
-        bn, sk = E.pick_tile(M, N, 768, False)
-        assert bn in (64, 128, 256) and sk == 1
-    assert E.pick_tile(64, 170, 768, False)[0] <= 128
+        bn, ks = E.pick_tile(M, N, 768, allow_ksplit=False)
+        assert bn in (64, 128, 256) and ks == 1
+    assert E.pick_tile(64, 170, 768, allow_ksplit=False)[0] <= 128
+    # cluster split-K is chosen only where a cluster per tile fits the 148 SMs, and for deep contractions
+    for M, N, K in [(2048, 768, 3072), (2048, 768, 2304), (768, 768, 2048), (2048, 768, 768), (2048, 3072, 768)]:
+        bn, ks = E.pick_tile(M, N, K)
+        tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+        assert ks == 1 or (tiles * ks <= 148 and (K + 63) // 64 >= 4 * ks)
+    assert E.pick_tile(2048, 768, 3072)[1] == 1      # opt-in (VQA_B200_KSPLIT=1): slower inside the step
+    os.environ["VQA_B200_KSPLIT"] = "1"
+    try:
+        assert E.pick_tile(2048, 768, 3072)[1] > 1 and E.pick_tile(2048, 3072, 768)[1] == 1
+    finally:
+        del os.environ["VQA_B200_KSPLIT"]
     for L in (16, 32, 20):
         assert torch.equal(E.t5_relative_buckets(L, L).long(), O.t5_buckets(L, L))
 

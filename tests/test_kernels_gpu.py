@@ -93,6 +93,89 @@ def test_wgrad(C, M, N, K, bn):
 
 
 # ------------------------------------------------------------------------------------------------
+# cluster split-K: a thread-block cluster per output tile, k-slices per CTA, partial sums exchanged through a
+# workspace, every CTA finishing (bias / ReLU / dropout / residual / store) a column range of the tile
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,bn,ks", [(2048, 768, 3072, 256, 3), (2048, 768, 3072, 256, 2), (2048, 768, 2304, 256, 3),
+                                         (2048, 768, 3072, 128, 1), (1000, 700, 1544, 128, 2), (256, 170, 2048, 64, 4),
+                                         (2048, 768, 768, 256, 3)])
+def test_ksplit_linear_forward_bias_relu(C, M, N, K, bn, ks):
+    X, W, b = rnd(M, K, seed=1, dtype=BF), rnd(N, K, seed=2, scale=K ** -0.5, dtype=BF), rnd(N, seed=3)
+    ldo = (N + 7) // 8 * 8
+    out = torch.zeros(M, ldo, dtype=BF, device="cuda")
+    C.linear(X, M, K, K, W, N, out, ldo, bias=b, relu=1, bn=bn, ksplit=ks)
+    ref = F.relu(X.float() @ W.float().t() + b)
+    assert rel_fro(out[:, :N], ref) < 6e-3
+    if ldo > N:
+        assert float(out[:, N:].abs().max()) == 0.0
+    # the exchange must not depend on what an earlier launch left in the workspace
+    C.linear(X, M, K, K, W, N, out, ldo, bias=b, relu=1, bn=bn, ksplit=ks)
+    assert rel_fro(out[:, :N], ref) < 6e-3
+
+
+def test_ksplit_fp32_residual_dropout(C):
+    M, N, K = 2048, 768, 3072
+    X, W, R = rnd(M, K, seed=1, dtype=BF), rnd(N, K, seed=2, scale=K ** -0.5, dtype=BF), rnd(M, N, seed=3)
+    out = torch.zeros(M, N, device="cuda")
+    C.linear(X, M, K, K, W, N, out, N, out_fp32=1, residual=R, ldr=N, res_fp32=1, bn=256, ksplit=3)
+    ref = X.float() @ W.float().t() + R
+    assert rel_fro(out, ref) < 2e-5
+    # dropout: the mask depends on the element index only, so it must equal the unsplit launch's exactly
+    a, b = torch.zeros(M, N, device="cuda"), torch.zeros(M, N, device="cuda")
+    rs = rng_state()
+    C.linear(X, M, K, K, W, N, a, N, out_fp32=1, residual=R, ldr=N, res_fp32=1, drop_p=0.1, sid=5, rng=rs, bn=256, ksplit=3)
+    C.linear(X, M, K, K, W, N, b, N, out_fp32=1, residual=R, ldr=N, res_fp32=1, drop_p=0.1, sid=5, rng=rs, bn=128)
+    assert torch.equal(a == R, b == R)
+    assert rel_fro(a, b) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K,bn,ks", [(2048, 3072, 768, 256, 3), (2048, 2304, 768, 256, 3)])
+def test_ksplit_dgrad_with_relu_mask(C, M, N, K, bn, ks):
+    dY = rnd(M, N, seed=1, dtype=BF)
+    W, act = rnd(N, K, seed=2, scale=N ** -0.5, dtype=BF), rnd(M, K, seed=3, dtype=BF)
+    out = torch.zeros(M, K, dtype=BF, device="cuda")
+    C.dgrad(dY, M, N, N, W, K, out, K, relu_mask=act, ldm=K, bn=bn, ksplit=ks)
+    ref = (dY.float() @ W.float()) * (act.float() > 0)
+    assert rel_fro(out, ref) < 6e-3
+
+
+@pytest.mark.parametrize("M,N,K,bn,ks", [(2048, 768, 768, 128, 4), (2048, 768, 3072, 256, 2), (2048, 2304, 768, 256, 2)])
+def test_ksplit_wgrad(C, M, N, K, bn, ks):
+    dY, X = rnd(M, N, seed=1, dtype=BF), rnd(M, K, seed=2, dtype=BF)
+    dW = torch.full((N, K), 7.0, device="cuda")     # a plain store: stale contents must not matter
+    C.wgrad(dY, M, N, N, X, K, K, dW, bn=bn, ksplit=ks)
+    assert rel_fro(dW, dY.float().t() @ X.float()) < 2e-5
+
+
+@pytest.mark.parametrize("N,H,Cin,Cout,R,bn,ks,res", [(64, 7, 512, 512, 3, 256, 2, True), (16, 7, 512, 512, 3, 128, 4, False),
+                                                      (8, 14, 256, 256, 3, 256, 3, True)])
+def test_ksplit_conv_bias_residual_relu(C, N, H, Cin, Cout, R, bn, ks, res):
+    x = rnd(N, Cin, H, H, seed=1, dtype=BF)
+    w = rnd(Cout, Cin, R, R, seed=2, scale=(Cin * R * R) ** -0.5, dtype=BF)
+    b = rnd(Cout, seed=3)
+    ref = F.conv2d(x.float(), w.float(), b, stride=1, padding=R // 2)
+    r = None
+    if res:
+        r = rnd(*ref.shape, seed=4, dtype=BF)
+        ref = ref + r.float()
+    ref = F.relu(ref)
+    out = torch.zeros(N, H, H, Cout, dtype=BF, device="cuda")
+    wk = w.permute(0, 2, 3, 1).contiguous()
+    C.conv(N, H, H, Cin, Cout, R, 1, R // 2, nhwc(x), wk, out, bias=b, residual=nhwc(r) if res else None, relu=1, bn=bn,
+           ksplit=ks)
+    assert rel_fro(out, nhwc(ref)) < 6e-3
+
+
+def test_ksplit_rejects_bad_configurations(C):
+    X, W = rnd(2048, 768, seed=1, dtype=BF), rnd(3072, 768, seed=2, dtype=BF)
+    out = torch.zeros(2048, 3072, dtype=BF, device="cuda")
+    with pytest.raises(RuntimeError, match="148"):
+        C.linear(X, 2048, 768, 768, W, 3072, out, 3072, bn=256, ksplit=2)   # 192 tiles x 2 CTAs do not fit the SMs
+    with pytest.raises(RuntimeError, match="k-blocks"):
+        C.linear(X[:128], 128, 768, 768, W[:256], 256, out, 3072, bn=256, ksplit=8)
+
+
+# ------------------------------------------------------------------------------------------------
 # CTA pairs (cta_group::2): a cluster of two CTAs runs one 256-row MMA, each staging half of the B tile
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,N,K,bn", [(2048, 2304, 768, 256), (2048, 768, 768, 128), (2048, 3072, 768, 256),

@@ -7,11 +7,15 @@ import t5_resnet_vqa_b200 as pkg
 from util import Caller
 C = Caller(pkg); lib = pkg.lib.load()
 BF = torch.bfloat16; dev = "cuda"
-names = ["start", "setup done", "pdl_wait done", "first stage full (mma)", "tile0 mma committed", "tile0 acc ready (epi)", "epi loop done", "stores drained", "teardown sync"]
+names = ["start", "setup done", "pdl_wait done", "first stage full (mma)", "tile0 mma committed", "tile0 acc ready (epi)", "epi loop done", "stores drained", "teardown sync", "ksplit: partials dumped", "ksplit: fence + barrier", "ksplit: peers arrived"]
 shapes = [("fwd", 2048, 768, 3072, 128, 0, 0), ("fwd", 2048, 768, 3072, 256, 0, 0), ("fwd", 2048, 768, 768, 128, 0, 0), ("fwd", 2048, 768, 768, 128, 1, 0), ("fwd", 2048, 2304, 768, 256, 0, 0),
           ("fwd", 2048, 768, 3072, 128, 1, 0), ("wgrad", 768, 768, 2048, 64, 1, 0), ("wgrad", 3072, 768, 2048, 128, 1, 0),
           ("fwd", 2048, 2304, 768, 256, 0, 1), ("fwd", 8192, 3072, 768, 256, 0, 1), ("fwd", 8192, 3072, 768, 256, 0, 0)]
-if len(sys.argv) > 1 and sys.argv[1] == "conv":
+KS = 1
+if len(sys.argv) > 1 and sys.argv[1] == "ksplit":
+    shapes = [("fwd", 2048, 768, 3072, 256, 0, 0)]
+    KS = int(sys.argv[2])
+elif len(sys.argv) > 1 and sys.argv[1] == "conv":
     shapes = [("conv", 14, 256, 1024, 256, 1, 1), ("conv", 14, 256, 1024, 256, 0, 1), ("conv", 56, 64, 256, 256, 1, 1), ("conv", 56, 64, 256, 64, 1, 1),
               ("conv", 14, 256, 256, 256, 0, 3), ("conv", 28, 128, 512, 256, 1, 1)]
 elif len(sys.argv) > 1:
@@ -47,7 +51,7 @@ for kind, M, N, K, bn, fp32, pair in shapes:
         if it == 2:
             lib.vqa_debug_gemm_timing(buf.data_ptr())
         if kind == "fwd":
-            C.gemm(M, N, K, A, K, 0, B, K, 0, out, N, fp32, bn=bn, residual=res, ldr=N, res_fp32=1, pair=bool(pair))
+            C.gemm(M, N, K, A, K, 0, B, K, 0, out, N, fp32, bn=bn, residual=res, ldr=N, res_fp32=1, pair=bool(pair), ksplit=KS)
         else:
             C.gemm(M, N, K, At, M, 1, Bt, N, 1, out, N, fp32, bn=bn, pair=bool(pair))
         torch.cuda.synchronize()
