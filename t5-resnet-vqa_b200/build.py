@@ -24,12 +24,20 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared library; returns its path."""
+def build(force=False, verbose=False, debug=False):
+    """Compile every .cu under csrc/ into one shared library; returns its path.  debug=True builds the diagnostic
+    variant libvqa_b200_dbg.so (-DVQA_GEMM_DEBUG: phase stamps and load-only / MMA-only modes of the GEMM kernel, used
+    by tools/gemm_timing.py and tools/gemm_dbg.py through VQA_B200_LIB)."""
+    if debug:
+        return _build_into(os.path.join(HERE, "libvqa_b200_dbg.so"), os.path.join(HERE, "build_dbg"),
+                           FLAGS + ["-DVQA_GEMM_DEBUG"], True, verbose)
     if not force and not _stale():
         return LIB
+    return _build_into(LIB, os.path.join(HERE, "build"), FLAGS, force, verbose)
+
+
+def _build_into(LIB, objdir, FLAGS, force, verbose):
     objs = []
-    objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in _sources():
@@ -54,4 +62,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

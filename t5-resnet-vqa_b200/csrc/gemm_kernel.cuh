@@ -32,7 +32,18 @@
 #include "ptx.cuh"
 #include "rng.cuh"
 
+// Bring-up instrumentation (phase stamps, load-only / MMA-only modes) is compiled only into the diagnostic library
+// (python t5-resnet-vqa_b200/build.py --debug -> libvqa_b200_dbg.so, selected with VQA_B200_LIB): it is ~10 % of the
+// kernel's instructions, and the step's ~400 short launches pay for every instruction-cache line they touch.
+#ifdef VQA_GEMM_DEBUG
+#define VQA_DBG_MODE(p) ((p).dbg_mode)
+#define VQA_DBG_CLK(p) ((p).dbg_clk)
 #define VQA_GSTAMP(k) do { if (p.dbg_clk != nullptr && blockIdx.x < 2 && (threadIdx.x & 31) == 0) p.dbg_clk[(blockIdx.x * 11 + (threadIdx.x >> 5)) * 16 + (k)] = clock64(); } while (0)
+#else
+#define VQA_DBG_MODE(p) 0
+#define VQA_DBG_CLK(p) (static_cast<long long*>(nullptr))
+#define VQA_GSTAMP(k) do { } while (0)
+#endif
 
 namespace vqa {
 
@@ -219,7 +230,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     auto load4 = [](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
       tma_load_4d_e<CTAS>(dst, m, bar, c0, c1, c2, c3);
     };
-    const bool pdbg = p.dbg_clk != nullptr && blockIdx.x < 2 && do_a;
+    const bool pdbg = VQA_DBG_CLK(p) != nullptr && blockIdx.x < 2 && do_a;
     long long pdbg_wait = 0, pdbg_t0 = pdbg ? clock64() : 0;
     int stage = 0;
     uint32_t phase = 0;
@@ -240,7 +251,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int t = unit; t < total_tiles; t += nunits) {
       const TileCoord tc = coord(t);
       const int nkb = tc.num_kb;
-      if (p.dbg_mode >= 2 && p.dbg_mode <= 4) {   // bring-up: no loads at all (measures the MMA side alone)
+      if (VQA_DBG_MODE(p) >= 2 && VQA_DBG_MODE(p) <= 4) {   // bring-up: no loads at all (measures the MMA side alone)
         for (int i = 0; i < nkb; ++i) {
           mbar_wait_lean(empty_bar(stage), phase ^ 1u);
           if (arrive) mbar_arrive_e(full_bar(stage));
@@ -323,8 +334,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint64_t db0 = umma_smem_desc(smem_base + C::A_BYTES, b_lbo, 1024u);
       const uint32_t da_hi = static_cast<uint32_t>(da0 >> 32), db_hi = static_cast<uint32_t>(db0 >> 32);
       const uint32_t da_lo0 = static_cast<uint32_t>(da0), db_lo0 = static_cast<uint32_t>(db0);
-      const int dbg_mode = p.dbg_mode;
-      const bool dbg_on = p.dbg_clk != nullptr && blockIdx.x < 2;
+      const int dbg_mode = VQA_DBG_MODE(p);
+      const bool dbg_on = VQA_DBG_CLK(p) != nullptr && blockIdx.x < 2;
       long long dbg_wait = 0, dbg_issue = 0;   // bring-up: cycles this warp spent waiting for data / issuing
       uint32_t next_ready = 0;                 // the next stage's full barrier has already been seen complete
       int stage = 0;
@@ -396,7 +407,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int pn = own_lo / 2; pn < own_hi / 2; ++pn) {
           const int n = tc.n0 + pn * 64;
           if (n >= p.N) break;
-          mbar_wait(res_empty_bar(slot), phase ^ 1u);
+          mbar_wait_lean(res_empty_bar(slot), phase ^ 1u);
           mbar_expect_tx(res_full_bar(slot), static_cast<uint32_t>(p.res_tx_bytes));
           if (p.out_pixels) tma_load_4d(ring + slot * kPanelBytes, &tmRes, res_full_bar(slot), n, tc.pw0, tc.ph0, tc.pn0);
           else tma_load_2d(ring + slot * kPanelBytes, &tmRes, res_full_bar(slot), n, tc.m0);
@@ -446,7 +457,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
       if (KS && KSP > 1) {
         // ---- cluster split-K, phase 1: partial sums of the columns other CTAs finish go to the workspace ----
-        mbar_wait(tmem_full_bar(acc), acc_phase);
+        mbar_wait_lean(tmem_full_bar(acc), acc_phase);
         tc_fence_after();
         waited = true;
         // workspace layout [cluster][source CTA][chunk][k = 0..7][row] float4: a warp's store / load instruction covers
@@ -519,7 +530,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < 8; ++k) pks[k] = __ldcg(src + k * 128);
         }
         if (!waited) {
-          mbar_wait(tmem_full_bar(acc), acc_phase);
+          mbar_wait_lean(tmem_full_bar(acc), acc_phase);
           tc_fence_after();
           waited = true;
           if (t == unit) VQA_GSTAMP(5);
@@ -584,7 +595,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (kRes == 1 && add_res) {
             // bf16 residual panel (64 columns) from the TMA ring; this warp's chunk is one 64-byte half of the row
-            mbar_wait(res_full_bar(rslot), rphase);
+            mbar_wait_lean(res_full_bar(rslot), rphase);
             const uint8_t* rrow = stg_gen + (2 + rslot) * kPanelBytes + row_off;
             float rs[32];
 #pragma unroll

@@ -3,7 +3,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvqa_b200.so")
+# VQA_B200_LIB selects another build of the same sources (the diagnostic libvqa_b200_dbg.so); never a fallback
+LIB_PATH = os.environ.get("VQA_B200_LIB") or os.path.join(_HERE, "libvqa_b200.so")
 
 c_int, c_ll, c_vp, c_f, c_u32, c_d = (ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_float,
                                       ctypes.c_uint32, ctypes.c_double)
