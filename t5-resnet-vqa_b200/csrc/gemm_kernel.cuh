@@ -180,23 +180,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // ---- one-time setup (overlaps the previous kernel's tail under programmatic dependent launch) ----
   VQA_GSTAMP(0);
   pdl_launch_dependents();
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmOut);
-    if (kRes == 1) tma_prefetch_desc(&tmRes);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);        // the leader's expect_tx arrival (+ the bytes of every producer)
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), kEpiWarps * CTAS);   // the leader waits for both CTAs' epilogues
-      mbar_init(res_full_bar(a), 1);
-      mbar_init(res_empty_bar(a), kEpiWarps);
-    }
-    mbar_init(ks_bar, KSP > 1 ? KSP - 1 : 1);
+  if (warp == 0) {
+    // one barrier per lane (initialising ~20 barriers from one thread is ~400 cycles of every launch's start-up)
+    if (lane < 2 * STAGES) mbar_init(bar_base + 8u * lane, 1);   // full[]: the leader's expect_tx arrival; empty[]: commit
+    else if (lane < 2 * STAGES + 2) mbar_init(bar_base + 8u * lane, 1);                   // tmem_full[2]
+    else if (lane < 2 * STAGES + 4) mbar_init(bar_base + 8u * lane, kEpiWarps * CTAS);    // tmem_empty[2]: both CTAs' epilogues
+    else if (lane < 2 * STAGES + 6) mbar_init(bar_base + 8u * lane, 1);                   // res_full[2]
+    else if (lane < 2 * STAGES + 8) mbar_init(bar_base + 8u * lane, kEpiWarps);           // res_empty[2]
+    else if (lane == 2 * STAGES + 8) mbar_init(ks_bar, KSP > 1 ? KSP - 1 : 1);
+    static_assert(2 * STAGES + 9 <= 32, "one barrier per lane");
     mbar_fence_init();
+  } else if (warp == 2 && lane < 4) {
+    const CUtensorMap* tm = lane == 0 ? &tmA : (lane == 1 ? &tmB : (lane == 2 ? &tmOut : &tmRes));
+    if (lane < 3 || kRes == 1) tma_prefetch_desc(tm);
   }
   if (warp == 1) {
     if (CTAS == 2) { tmem_alloc_pair(tmem_slot, C::TMEM_COLS); tmem_relinquish_pair(); }
