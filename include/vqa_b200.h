@@ -63,6 +63,10 @@ int vqa_plan_wait(void* plan, int mark);
 /* measurement aid: eager replay with a CUDA event between launches; ms_out[vqa_plan_size] device durations
  * (synchronises the stream).  op_info: kernel family and the algorithmic flops / HBM bytes of launch i. */
 int vqa_plan_profile(void* plan, void* stream, float* ms_out, int spin_us);
+/* Back-to-back device time of the launches whose op name is in `names` ("gemm,conv,..."): `reps` passes between one
+ * pair of events, no per-launch gaps (bench.py's roofline numerator / denominator).  Ignores data dependencies. */
+int vqa_plan_time_ops(void* plan, void* stream, const char* names, int reps, float* ms_per_rep,
+                      double* flops_per_rep, int* launches_per_rep);
 int vqa_plan_op_info(void* plan, int i, const char** name, double* flops, double* bytes);
 
 /* ------------------------------------------------------------------------------------------------

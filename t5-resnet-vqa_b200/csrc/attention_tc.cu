@@ -31,7 +31,12 @@ constexpr int kTile = 128 * 128;          // bytes of one 64-column chunk: 128 r
 constexpr int kBox = kSlot * 128;         // bytes one TMA box delivers (32 rows x 64 bf16)
 constexpr float kMaskedScore = -3.4028234663852886e38f;  // torch.finfo(float32).min (hf additive mask)
 
+// phase stamps are compiled only into the diagnostic library (build.py --debug), as in gemm_kernel.cuh
+#ifdef VQA_GEMM_DEBUG
 #define VQA_STAMP(k) do { if (a.dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) a.dbg[(threadIdx.x >> 5) * 16 + (k)] = clock64(); } while (0)
+#else
+#define VQA_STAMP(k) do { } while (0)
+#endif
 
 long long* g_attn_dbg = nullptr;
 
@@ -296,7 +301,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   float4 bq[8];
   load_bias_row(bq, a.bias, rc, a.Lq, a.Lk);
   if (t == 0) {
-    mbar_wait(bar_tma, 0);
+    mbar_wait_lean(bar_tma, 0);
     tc_fence_after();
     VQA_STAMP(3);
     const uint32_t idesc = umma_idesc_bf16(128, 128, false, false);
@@ -310,7 +315,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncwarp();
 
   VQA_STAMP(4);
-  mbar_wait(bar_mma, 0);
+  mbar_wait_lean(bar_mma, 0);
   tc_fence_after();
   VQA_STAMP(5);
   const uint32_t t_s = tmem + lane_base + warp * 32;     // this row's 32 scores (diagonal block of the pair)
@@ -369,7 +374,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     umma_commit(bar_mma);
   }
   __syncwarp();
-  mbar_wait(bar_mma, 1);
+  mbar_wait_lean(bar_mma, 1);
   tc_fence_after();
   VQA_STAMP(8);
   __nv_bfloat16* op = a.out + (static_cast<long long>(rc.b) * a.Lq + rc.i) * a.ldo + rc.h * HD;
@@ -470,7 +475,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mx = st.x; inv = st.y;
   }
   if (t == 0) {
-    mbar_wait(bar_tma, 0);
+    mbar_wait_lean(bar_tma, 0);
     tc_fence_after();
     VQA_STAMP(3);
     const uint32_t idesc = umma_idesc_bf16(128, 128, false, false);
@@ -490,7 +495,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncwarp();
 
   VQA_STAMP(4);
-  mbar_wait(bar_mma, 0);
+  mbar_wait_lean(bar_mma, 0);
   tc_fence_after();
   VQA_STAMP(5);
   const uint32_t t_s = tmem + lane_base + warp * 32;          // S block of this row
@@ -577,7 +582,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     umma_commit(bar_mma);
   }
   __syncwarp();
-  mbar_wait(bar_mma, 1);
+  mbar_wait_lean(bar_mma, 1);
   tc_fence_after();
   VQA_STAMP(8);
   {

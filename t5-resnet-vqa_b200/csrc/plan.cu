@@ -3,6 +3,9 @@
 #include "../../include/vqa_b200.h"
 #include "common.cuh"
 
+#include <string>
+#include <vector>
+
 using namespace vqa;
 
 extern "C" {
@@ -205,6 +208,42 @@ int vqa_plan_profile(void* plan, void* stream, float* ms_out, int spin_us) {
   if (rc == 0)
     for (size_t i = 0; i < n; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
   for (auto& ev_i : ev) cudaEventDestroy(ev_i);
+  return rc;
+}
+
+// Back-to-back device time of a family of launches: replays only the ops whose name is listed in `names` (comma
+// separated, e.g. "gemm,conv,conv_wgrad") `reps` times on `stream` between ONE pair of events, programmatic dependent
+// launch on, nothing in between - the kernels' durations as they run inside the step, without the event-to-event gap
+// the per-launch table above pays for every launch.  Data dependencies are ignored (timing only; run it last).
+int vqa_plan_time_ops(void* plan, void* stream, const char* names, int reps, float* ms_per_rep, double* flops_per_rep,
+                      int* launches_per_rep) {
+  if (plan == nullptr || names == nullptr || reps < 1) { set_last_error("plan_time_ops: bad arguments"); return -1; }
+  Plan* p = static_cast<Plan*>(plan);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const std::string list = std::string(",") + names + ",";
+  std::vector<size_t> sel;
+  double fl = 0.0;
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const std::string key = std::string(",") + p->notes[i].name + ",";
+    if (list.find(key) != std::string::npos) { sel.push_back(i); fl += p->notes[i].flops; }
+  }
+  *flops_per_rep = fl;
+  *launches_per_rep = static_cast<int>(sel.size());
+  *ms_per_rep = 0.f;
+  if (sel.empty()) return 0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int rc = 0;
+  launch_pdl(vqa_spin_kernel, dim3(1), dim3(1), 0, s, 2000000LL);   // let the host queue ahead of the device
+  for (size_t i : sel) { rc = p->ops[i](s); if (rc) break; }          // one untimed pass (caches, attributes)
+  cudaEventRecord(e0, s);
+  for (int r = 0; r < reps && rc == 0; ++r)
+    for (size_t i : sel) { rc = p->ops[i](s); if (rc) break; }
+  cudaEventRecord(e1, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (rc == 0 && e != cudaSuccess) { set_last_error("plan_time_ops: %s", cudaGetErrorString(e)); rc = static_cast<int>(e); }
+  if (rc == 0) { float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1); *ms_per_rep = ms / reps; }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return rc;
 }
 

@@ -73,6 +73,7 @@ SIGNATURES = {
     "vqa_plan_mark": (c_int, [_P]),
     "vqa_plan_wait": (c_int, [_P, c_int]),
     "vqa_plan_profile": (c_int, [_P, _P, _P, c_int]),
+    "vqa_plan_time_ops": (c_int, [_P, _P, ctypes.c_char_p, c_int, ctypes.POINTER(c_f), ctypes.POINTER(c_d), ctypes.POINTER(c_int)]),
     "vqa_plan_op_info": (c_int, [_P, c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_d),
                                  ctypes.POINTER(c_d)]),
     "vqa_gemm_bf16": (c_int, [_P, ctypes.POINTER(GemmArgs), _P]),

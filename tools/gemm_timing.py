@@ -2,6 +2,11 @@
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# needs the diagnostic build (python t5-resnet-vqa_b200/build.py --debug): the default library has no instrumentation
+_DBG = os.path.join(ROOT, "t5-resnet-vqa_b200", "libvqa_b200_dbg.so")
+if not os.path.exists(_DBG):
+    raise SystemExit("build the diagnostic library first: python t5-resnet-vqa_b200/build.py --debug")
+os.environ.setdefault("VQA_B200_LIB", _DBG)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import t5_resnet_vqa_b200 as pkg
 from util import Caller
