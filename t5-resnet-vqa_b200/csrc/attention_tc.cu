@@ -252,7 +252,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t bar_tma = sP + 2 * kTile, bar_mma = bar_tma + 8, slot = bar_mma + 8;
   uint8_t* Pg = gen + 3 * CH * kTile;
   const uint32_t* slot_ptr = reinterpret_cast<const uint32_t*>(gen + (3 * CH + 2) * kTile + 16);
-  const int t = threadIdx.x, warp = t >> 5;
+  const int t = threadIdx.x;
+  // lane-0 broadcast: ptxas then knows the warp index is warp-uniform (uniform branches / uniform registers below)
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
 
   VQA_STAMP(0);
   pdl_launch_dependents();
@@ -300,7 +302,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
   float4 bq[8];
   load_bias_row(bq, a.bias, rc, a.Lq, a.Lk);
-  if (t == 0) {
+  if (warp == 0) {   // whole warp, one elected lane issues (operands stay in uniform registers)
     mbar_wait_lean(bar_tma, 0);
     tc_fence_after();
     VQA_STAMP(3);
@@ -308,9 +310,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       const uint32_t off = (ks >> 2) * kTile + (ks & 3) * 32;
-      umma_bf16(tmem, umma_smem_desc(sQ + off, 16u, 1024u), umma_smem_desc(sK + off, 16u, 1024u), idesc, ks ? 1u : 0u);
+      umma_bf16_e<1>(tmem, umma_smem_desc(sQ + off, 16u, 1024u), umma_smem_desc(sK + off, 16u, 1024u), idesc, ks ? 1u : 0u);
     }
-    umma_commit(bar_mma);
+    umma_commit_e<1>(bar_mma);
   }
   __syncwarp();
 
@@ -362,16 +364,16 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   VQA_STAMP(7);
-  if (t == 0) {
+  if (warp == 0) {   // whole warp, one elected lane issues (operands stay in uniform registers)
     tc_fence_after();
     const uint32_t idesc = umma_idesc_bf16(128, HD, false, true);
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
       const uint64_t da = umma_smem_desc(sP + (ks >> 2) * kTile + (ks & 3) * 32, 16u, 1024u);
       const uint64_t db = umma_smem_desc(sV + ks * 2048, kTile, 1024u);
-      umma_bf16(tmem + 128, da, db, idesc, ks ? 1u : 0u);
+      umma_bf16_e<1>(tmem + 128, da, db, idesc, ks ? 1u : 0u);
     }
-    umma_commit(bar_mma);
+    umma_commit_e<1>(bar_mma);
   }
   __syncwarp();
   mbar_wait_lean(bar_mma, 1);
@@ -423,7 +425,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* Pdg = gen + 4 * CH * kTile;
   uint8_t* dSg = Pdg + 2 * kTile;
   const uint32_t* slot_ptr = reinterpret_cast<const uint32_t*>(gen + (4 * CH + 4) * kTile + 16);
-  const int t = threadIdx.x, warp = t >> 5;
+  const int t = threadIdx.x;
+  // lane-0 broadcast: ptxas then knows the warp index is warp-uniform (uniform branches / uniform registers below)
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
 
   VQA_STAMP(0);
   pdl_launch_dependents();
@@ -474,7 +478,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float2 st = *reinterpret_cast<const float2*>(a.stats + 2 * rc.prow);
     mx = st.x; inv = st.y;
   }
-  if (t == 0) {
+  if (warp == 0) {   // whole warp, one elected lane issues (operands stay in uniform registers)
     mbar_wait_lean(bar_tma, 0);
     tc_fence_after();
     VQA_STAMP(3);
@@ -482,15 +486,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {     // S = Q K^T
       const uint32_t off = (ks >> 2) * kTile + (ks & 3) * 32;
-      umma_bf16(tmem, umma_smem_desc(sQ + off, 16u, 1024u), umma_smem_desc(sK + off, 16u, 1024u), idesc, ks ? 1u : 0u);
+      umma_bf16_e<1>(tmem, umma_smem_desc(sQ + off, 16u, 1024u), umma_smem_desc(sK + off, 16u, 1024u), idesc, ks ? 1u : 0u);
     }
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {     // dP = dO V^T
       const uint32_t off = (ks >> 2) * kTile + (ks & 3) * 32;
-      umma_bf16(tmem + 128, umma_smem_desc(sdO + off, 16u, 1024u), umma_smem_desc(sV + off, 16u, 1024u), idesc,
+      umma_bf16_e<1>(tmem + 128, umma_smem_desc(sdO + off, 16u, 1024u), umma_smem_desc(sV + off, 16u, 1024u), idesc,
                 ks ? 1u : 0u);
     }
-    umma_commit(bar_mma);
+    umma_commit_e<1>(bar_mma);
   }
   __syncwarp();
 
@@ -560,26 +564,26 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   VQA_STAMP(7);
-  if (t == 0) {
+  if (warp == 0) {   // whole warp, one elected lane issues (operands stay in uniform registers)
     tc_fence_after();
     const uint32_t id_tt = umma_idesc_bf16(128, HD, true, true);
     const uint32_t id_nt = umma_idesc_bf16(128, HD, false, true);
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {      // dV[key, d] = sum_q Pd[q, key] dO[q, d]
-      umma_bf16(tmem + cDV, umma_smem_desc(sPd + ks * 2048, kTile, 1024u), umma_smem_desc(sdO + ks * 2048, kTile, 1024u),
+      umma_bf16_e<1>(tmem + cDV, umma_smem_desc(sPd + ks * 2048, kTile, 1024u), umma_smem_desc(sdO + ks * 2048, kTile, 1024u),
                 id_tt, ks ? 1u : 0u);
     }
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {      // dQ[q, d] = sum_key dS[q, key] K[key, d]
-      umma_bf16(tmem + cDQ, umma_smem_desc(sdS + (ks >> 2) * kTile + (ks & 3) * 32, 16u, 1024u),
+      umma_bf16_e<1>(tmem + cDQ, umma_smem_desc(sdS + (ks >> 2) * kTile + (ks & 3) * 32, 16u, 1024u),
                 umma_smem_desc(sK + ks * 2048, kTile, 1024u), id_nt, ks ? 1u : 0u);
     }
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {      // dK[key, d] = sum_q dS[q, key] Q[q, d]
-      umma_bf16(tmem + cDK, umma_smem_desc(sdS + ks * 2048, kTile, 1024u), umma_smem_desc(sQ + ks * 2048, kTile, 1024u),
+      umma_bf16_e<1>(tmem + cDK, umma_smem_desc(sdS + ks * 2048, kTile, 1024u), umma_smem_desc(sQ + ks * 2048, kTile, 1024u),
                 id_tt, ks ? 1u : 0u);
     }
-    umma_commit(bar_mma);
+    umma_commit_e<1>(bar_mma);
   }
   __syncwarp();
   mbar_wait_lean(bar_mma, 1);

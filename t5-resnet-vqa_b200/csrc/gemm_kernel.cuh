@@ -148,7 +148,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_slot = bar_base + 8u * C::NBARS;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + C::BAR_OFF + 8 * C::NBARS);
 
-  const int warp = threadIdx.x >> 5;
+  // broadcast from lane 0: tells ptxas the warp index is warp-uniform, so the role branches below are uniform branches
+  // and the role loops can keep their state in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   // cluster split-K (CTAS == 1 only): the KSP CTAs of a cluster share one output tile; CTA `krank` contracts k-slice
   // `krank`, hands the partial sums of the columns it does not own to their owners through p.ks_ws, and finishes
@@ -358,6 +360,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             next_ready = umma_kblock4_e<CTAS>(d_tmem, (static_cast<uint64_t>(da_hi) << 32) | la,
                                               (static_cast<uint64_t>(db_hi) << 32) | lb, a_k16, b_k16, idesc, i ? 1u : 0u,
                                               empty_bar(stage), full_bar(ns), ns == 0 ? (phase ^ 1u) : phase);
+            next_ready = __shfl_sync(0xffffffffu, next_ready, 0);   // warp-uniform by construction
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             if (dbg_on) { const long long c2 = clock64(); dbg_wait += c1 - c0; dbg_issue += c2 - c1; }
             continue;

@@ -367,41 +367,47 @@ __device__ __forceinline__ uint32_t umma_kblock4_e(uint32_t tmem_d, uint64_t da,
                                                    uint32_t b_step, uint32_t idesc, uint32_t accumulate,
                                                    uint32_t empty_bar, uint32_t next_full_bar, uint32_t next_parity) {
   uint32_t ready;
-  const uint64_t da1 = da + a_step, da2 = da + 2 * a_step, da3 = da + 3 * a_step;
-  const uint64_t db1 = db + b_step, db2 = db + 2 * b_step, db3 = db + 3 * b_step;
+  // the three further descriptor pairs are derived inside the block (uniform adds), so only the base pair and the
+  // steps have to be moved into uniform registers per k-block
   if (CTAS == 2) {
     asm volatile(
-        "{\n\t.reg .pred pe, pa, pt, pw;\n\t"
+        "{\n\t.reg .pred pe, pa, pt, pw;\n\t.reg .b64 a1, a2, a3, b1, b2, b3, sa, sb;\n\t"
         "elect.sync _|pe, 0xffffffff;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 pw, [%13], %14;\n\t"
-        "setp.ne.b32 pa, %11, 0;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 pw, [%9], %10;\n\t"
+        "cvt.u64.u32 sa, %4;\n\tcvt.u64.u32 sb, %5;\n\t"
+        "add.u64 a1, %2, sa;\n\tadd.u64 a2, a1, sa;\n\tadd.u64 a3, a2, sa;\n\t"
+        "add.u64 b1, %3, sb;\n\tadd.u64 b2, b1, sb;\n\tadd.u64 b3, b2, sb;\n\t"
+        "setp.ne.b32 pa, %7, 0;\n\t"
         "setp.eq.u32 pt, 0, 0;\n\t"
-        "@pe tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %6, %10, pa;\n\t"
-        "@pe tcgen05.mma.cta_group::2.kind::f16 [%1], %3, %7, %10, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::2.kind::f16 [%1], %4, %8, %10, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::2.kind::f16 [%1], %5, %9, %10, pt;\n\t"
-        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%12], %15;\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%1], %2, %3, %6, pa;\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%1], a1, b1, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%1], a2, b2, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::2.kind::f16 [%1], a3, b3, %6, pt;\n\t"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], %11;\n\t"
         "selp.u32 %0, 1, 0, pw;\n\t}\n"
         : "=r"(ready)
-        : "r"(tmem_d), "l"(da), "l"(da1), "l"(da2), "l"(da3), "l"(db), "l"(db1), "l"(db2), "l"(db3), "r"(idesc),
-          "r"(accumulate), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity), "h"(static_cast<uint16_t>(3))
+        : "r"(tmem_d), "l"(da), "l"(db), "r"(a_step), "r"(b_step), "r"(idesc), "r"(accumulate), "r"(empty_bar),
+          "r"(next_full_bar), "r"(next_parity), "h"(static_cast<uint16_t>(3))
         : "memory");
   } else {
     asm volatile(
-        "{\n\t.reg .pred pe, pa, pt, pw;\n\t"
+        "{\n\t.reg .pred pe, pa, pt, pw;\n\t.reg .b64 a1, a2, a3, b1, b2, b3, sa, sb;\n\t"
         "elect.sync _|pe, 0xffffffff;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 pw, [%13], %14;\n\t"
-        "setp.ne.b32 pa, %11, 0;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 pw, [%9], %10;\n\t"
+        "cvt.u64.u32 sa, %4;\n\tcvt.u64.u32 sb, %5;\n\t"
+        "add.u64 a1, %2, sa;\n\tadd.u64 a2, a1, sa;\n\tadd.u64 a3, a2, sa;\n\t"
+        "add.u64 b1, %3, sb;\n\tadd.u64 b2, b1, sb;\n\tadd.u64 b3, b2, sb;\n\t"
+        "setp.ne.b32 pa, %7, 0;\n\t"
         "setp.eq.u32 pt, 0, 0;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %6, %10, pa;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %7, %10, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], %4, %8, %10, pt;\n\t"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], %5, %9, %10, pt;\n\t"
-        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%12];\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %3, %6, pa;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], a1, b1, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], a2, b2, %6, pt;\n\t"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], a3, b3, %6, pt;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
         "selp.u32 %0, 1, 0, pw;\n\t}\n"
         : "=r"(ready)
-        : "r"(tmem_d), "l"(da), "l"(da1), "l"(da2), "l"(da3), "l"(db), "l"(db1), "l"(db2), "l"(db3), "r"(idesc),
-          "r"(accumulate), "r"(empty_bar), "r"(next_full_bar), "r"(next_parity)
+        : "r"(tmem_d), "l"(da), "l"(db), "r"(a_step), "r"(b_step), "r"(idesc), "r"(accumulate), "r"(empty_bar),
+          "r"(next_full_bar), "r"(next_parity)
         : "memory");
   }
   return ready;

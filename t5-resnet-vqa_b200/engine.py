@@ -135,6 +135,12 @@ class _Rec:
 
     def wgrad(self, dY, M, N, ldy, X, K, ldx, dW, **kw):
         """dW[N,K] (fp32) = dY[M,N]^T @ X[M,K]"""
+        if not kw:
+            # few output tiles, deep contraction over the tokens: split K over CTAs (fp32 red.add into a zeroed dW)
+            bn, split = pick_wgrad_split(N, K, M)
+            if split > 1:
+                self.memset_zero(dW, 4 * N * K)
+                kw = dict(bn=bn, split_k=split)
         self.gemm(N, K, M, dY, ldy, 1, X, ldx, 1, dW, K, 1, **kw)
 
     def conv(self, N, H, W, Cin, Cout, R, stride, pad, x, w, out, bias=None, residual=None, relu=1, stem7=0,
@@ -213,8 +219,8 @@ def _tile_cost(tiles, bn):
 # Launch-time model of the tcgen05 GEMM on B200 (microseconds; tools/gemm_bench.py, graph-replayed, L2-warm):
 # t = fixed(bn) + waves * k_blocks_per_CTA * per_kblock(bn) [+ exchange when a cluster splits K].  It reproduces the
 # measured best configuration of the step's 13 GEMM shapes to within 10 %.
-_GEMM_FIXED = {64: 3.6, 128: 3.8, 256: 4.7}
-_GEMM_KB = {64: 0.20, 128: 0.253, 256: 0.30}
+_GEMM_FIXED = {64: 3.2, 128: 3.3, 256: 4.0}
+_GEMM_KB = {64: 0.117, 128: 0.175, 256: 0.278}
 _GEMM_KSPLIT_EXCHANGE = 1.3
 
 
@@ -240,6 +246,34 @@ def pick_tile(M, N, K, allow_ksplit=True):
         for ks, cost in cands:
             if best is None or cost < best[0] - 1e-9:
                 best = (cost, bn, ks)
+    return best[1], best[2]
+
+
+def pick_wgrad_split(N, K, M):
+    """(tile width, split-K factor) for a weight gradient dW[N,K] over M tokens, or (None, 1) to leave the choice to
+    pick_tile.  Same launch model; the split variant also pays for zeroing dW (~0.5 us per MB + a graph node).
+    Opt-in (VQA_B200_WGRAD_SPLIT=1): the isolated launch gets faster, the step does not (5.63 vs 5.57 ms) - the weight
+    gradients run on the side lane, where a 36-CTA launch that leaves 112 SMs to the data-gradient chain is worth more
+    than a shorter 144-CTA one."""
+    if not _env_flag("VQA_B200_WGRAD_SPLIT", False):
+        return None, 1
+    kb = (M + 63) // 64
+    tn = (N + 127) // 128
+    unsplit, best = None, None
+    for bn in (128, 64):
+        if K % bn:
+            continue
+        tiles = tn * (K // bn)
+        base = _GEMM_FIXED[bn] + -(-tiles // N_SM) * kb * _GEMM_KB[bn]
+        unsplit = base if unsplit is None else min(unsplit, base)
+        for split in (2, 3, 4):
+            if tiles * split > N_SM or kb < 8 * split:
+                continue
+            cost = _GEMM_FIXED[bn] + -(-kb // split) * _GEMM_KB[bn] + 1.0 + 4.0 * N * K / 2.0e6
+            if best is None or cost < best[0]:
+                best = (cost, bn, split)
+    if best is None or unsplit is None or best[0] > unsplit - 1.0:
+        return None, 1
     return best[1], best[2]
 
 
