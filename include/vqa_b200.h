@@ -20,7 +20,7 @@
  *     synchronises the device.  Safe to call from the autograd engine's worker thread.
  *   - bf16 tensors are row-major with the innermost dimension contiguous; activations are NHWC /
  *     [tokens, features].
- *   - dropout: counter-based Philox4x32-10 keyed by the device pair rng = {seed, offset}; an element
+ *   - dropout: counter-based Philox4x32-7 keyed by the device pair rng = {seed, offset}; an element
  *     of stream `sid` at flat index i is dropped iff u16(philox(seed, offset, sid, i / 8), i % 8) <
  *     p * 65536, survivors are scaled by 1/(1-p).  Forward and backward regenerate the same mask.
  */
