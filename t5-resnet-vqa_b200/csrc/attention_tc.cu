@@ -416,15 +416,21 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   constexpr uint32_t cDV = (3 * HD <= 256) ? 0 : 256;
   constexpr uint32_t cDQ = (3 * HD <= 256) ? HD : 256 + HD;
   constexpr uint32_t cDK = (3 * HD <= 256) ? 2 * HD : 0;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sQ = base, sK = sQ + CH * kTile, sV = sK + CH * kTile, sdO = sV + CH * kTile;
-  const uint32_t sPd = sdO + CH * kTile, sdS = sPd + 2 * kTile;
-  const uint32_t bar_tma = sdS + 2 * kTile, bar_mma = bar_tma + 8, slot = bar_mma + 8;
-  uint8_t* Pdg = gen + 4 * CH * kTile;
+  // Shared memory: Q, K, dO, Pd (2 tiles), dS (2 tiles), V - where the SECOND dS tile IS V's first tile: V is dead
+  // once dP = dO V^T has completed, which every thread has waited for before it writes dS.  (4 CH + 3) tiles = 112 KB
+  // for the T5 head size, so two CTAs share an SM and the 192 CTAs of the step's launch are one wave instead of two.
+  // The dynamic shared memory of a kernel without static shared memory starts on a 1 KB boundary (checked below);
+  // asking for alignment slack would push two CTAs over the SM's 228 KB.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* gen = smem_raw;
+  const uint32_t sQ = base, sK = sQ + CH * kTile, sdO = sK + CH * kTile;
+  const uint32_t sPd = sdO + CH * kTile, sdS = sPd + 2 * kTile, sV = sdS + kTile;
+  const uint32_t bar_tma = sV + CH * kTile, bar_mma = bar_tma + 8, slot = bar_mma + 8;
+  uint8_t* Pdg = gen + 3 * CH * kTile;
   uint8_t* dSg = Pdg + 2 * kTile;
-  const uint32_t* slot_ptr = reinterpret_cast<const uint32_t*>(gen + (4 * CH + 4) * kTile + 16);
+  const uint32_t* slot_ptr = reinterpret_cast<const uint32_t*>(gen + (4 * CH + 3) * kTile + 16);
+  if ((base & 1023u) != 0u) __trap();
   const int t = threadIdx.x;
   // lane-0 broadcast: ptxas then knows the warp index is warp-uniform (uniform branches / uniform registers below)
   const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
@@ -442,7 +448,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tmem_alloc(slot, kCols);
     tmem_relinquish();
   }
-  for (int i = t; i < 4 * kTile / 16; i += kThreads) reinterpret_cast<uint4*>(Pdg)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // zero Pd (2 tiles) and the first dS tile now; the second dS tile is V's buffer and is zeroed after dP (below)
+  for (int i = t; i < 3 * kTile / 16; i += kThreads) reinterpret_cast<uint4*>(Pdg)[i] = make_uint4(0u, 0u, 0u, 0u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -525,6 +532,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   }
   // pass 2: dS = P (dP - rowdot); bias gradient; bf16 operands of the three output MMAs
+  {   // the second dS tile lives in V's buffer (dead since dP completed): clear this thread's row of it; its diagonal
+      // block, if it has one there, is written below by the same thread
+    uint4* vrow = reinterpret_cast<uint4*>(dSg + kTile + (t >> 3) * 1024 + (t & 7) * 128);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) vrow[j] = make_uint4(0u, 0u, 0u, 0u);
+  }
   float* dbrow = (a.dbias != nullptr && rc.row_ok) ? a.dbias + (static_cast<long long>(rc.h) * a.Lq + rc.i) * a.Lk : nullptr;
   const bool dbvec = dbrow != nullptr && (a.Lk & 3) == 0 && (reinterpret_cast<uintptr_t>(dbrow) & 15) == 0;
 #pragma unroll
@@ -608,7 +621,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 template <int HD> constexpr size_t fwd_smem_bytes() { return (3 * ((HD + 63) / 64) + 2) * kTile + 64 + 1024; }
-template <int HD> constexpr size_t bwd_smem_bytes() { return (4 * ((HD + 63) / 64) + 4) * kTile + 64 + 1024; }
+template <int HD> constexpr size_t bwd_smem_bytes() { return (4 * ((HD + 63) / 64) + 3) * kTile + 64; }
 
 template <typename K>
 int raise_smem(K kern, size_t bytes, const char* what) {

@@ -200,6 +200,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (CTAS == 2) { tmem_alloc_pair(tmem_slot, C::TMEM_COLS); tmem_relinquish_pair(); }
     else { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
   }
+  // the first tile's coordinates depend on launch parameters only: computed here, while barrier initialisation and
+  // the TMEM allocation are in flight, so the (cold) parameter reads are off the path to the first TMA load
+  const TileCoord tc_first = coord(unit);
   tc_fence_before();
   if (CTAS == 2 || (KS && KSP > 1)) cluster_sync_all();   // the peers' barriers must be initialised before anyone signals them
   else __syncthreads();
@@ -247,7 +250,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }                              \
     } while (0)
     for (int t = unit; t < total_tiles; t += nunits) {
-      const TileCoord tc = coord(t);
+      const TileCoord tc = t == unit ? tc_first : coord(t);
       const int nkb = tc.num_kb;
       if (VQA_DBG_MODE(p) >= 2 && VQA_DBG_MODE(p) <= 4) {   // bring-up: no loads at all (measures the MMA side alone)
         for (int i = 0; i < nkb; ++i) {
@@ -341,7 +344,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = unit; t < total_tiles; t += nunits) {
-        const TileCoord tc = coord(t);
+        const TileCoord tc = t == unit ? tc_first : coord(t);
         mbar_wait_lean(tmem_empty_bar(acc), acc_phase ^ 1u);   // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -401,7 +404,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int slot = 0;
       uint32_t phase = 0;
       for (int t = unit; t < total_tiles; t += nunits) {
-        const TileCoord tc = coord(t);
+        const TileCoord tc = t == unit ? tc_first : coord(t);
         if (tc.kb_begin != 0 && KSP == 1) continue;   // atomic split-K: the residual is added by the first k-slice only
         for (int pn = own_lo / 2; pn < own_hi / 2; ++pn) {
           const int n = tc.n0 + pn * 64;
@@ -445,7 +448,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int rslot = 0;                        // residual ring position
     uint32_t rphase = 0;
     for (int t = unit; t < total_tiles; t += nunits) {
-      const TileCoord tc = coord(t);
+      const TileCoord tc = t == unit ? tc_first : coord(t);
       const bool first_split = (tc.kb_begin == 0) || KSP > 1;   // cluster split-K: every CTA finishes its own columns
       const bool add_bias = p.bias != nullptr && first_split;
       const bool add_res = kRes != 0 && first_split;
