@@ -61,7 +61,7 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
   return p;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              float* __restrict__ vmax, __nv_bfloat16* __restrict__ shadow, long long n, AdamHyper h,
              const float* __restrict__ gnorm_sq) {
@@ -192,6 +192,15 @@ int vqa_adamw_amsgrad(void* plan, float* p, const float* g, float* m, float* v, 
   h.max_norm = max_norm; h.amsgrad = amsgrad;
   note_op("adamw", 0.0, (amsgrad ? 36.0 : 28.0) * static_cast<double>(n) + (shadow ? 2.0 * n : 0.0));
   return submit(plan, stream, [=](cudaStream_t s) {
+    // VQA_B200_ADAMW_GRID=<n>: n CTAs of 1024 threads instead (experiment: confine the HBM-bound pass to a subset of the
+    // SMs so that GEMM CTAs, which need a whole SM's register file, can run on the others)
+    static int wide = -1;
+    if (wide < 0) { const char* e = getenv("VQA_B200_ADAMW_GRID"); wide = e ? atoi(e) : 0; }
+    if (wide > 0) {
+      launch_pdl(adamw_kernel, dim3(wide), dim3(1024), 0, s, p, g, m, v, vmax, static_cast<__nv_bfloat16*>(shadow), n, h,
+                 gnorm_sq);
+      return launch_status("adamw");
+    }
     launch_pdl(adamw_kernel, dim3(adamw_grid((n >> 2) + 4, 256)), dim3(256), 0, s, p, g, m, v, vmax, static_cast<__nv_bfloat16*>(shadow), n, h,
                                                                 gnorm_sq);
     return launch_status("adamw");
