@@ -88,6 +88,10 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # the reference arm / CPU baseline: the oracle port of the reference step on the host cores
 # --------------------------------------------------------------------------------------------------
+WORKLOAD = ("ResNet50 + T5-base encoder + 3xSGA train step (fwd+bwd+clip+AdamW-amsgrad), batch %d per GPU, "
+            "224x224 images, 32-token questions, 170 answers, dropout on")
+
+
 def cpu_reference_steps(steps, warmup, batch=4):
     import torch
     from oracle import vqa_oracle as O
@@ -135,8 +139,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "train samples/s", "value": r["value"], "unit": "samples/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": max(warmup, 1), "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ResNet50+T5-base-encoder+3xSGA train step, 224x224, 32-token question, 170 answers; "
-                                   "CPU sample batch %d" % r["batch"]},
+            "config": {"workload": WORKLOAD % PER_GPU_BATCH, "global_batch": args.gpus * PER_GPU_BATCH,
+                       "parallelism": "cpu", "sample_batch": r["batch"],
+                       "note": "the reference's CPU fp32 path (oracle port) on a bounded sample of the same workload"},
             "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -426,8 +431,7 @@ def main():
         "metric": "train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "ResNet50 + T5-base encoder + 3xSGA train step (fwd+bwd+clip+AdamW-amsgrad), batch %d per GPU, "
-                               "224x224 images, 32-token questions, 170 answers, dropout on" % B,
+        "config": {"workload": WORKLOAD % B,
                    "global_batch": world * B, "parallelism": "dp%d" % world,
                    "l2": "working set per step (activations + 567 MB fp32 gradients + 2.3 GB optimizer state) exceeds the 126 MB L2",
                    "optimizer": type(opt).__name__, "cuda_graphs": bool(model._engine.use_graphs)},

@@ -137,10 +137,12 @@ __global__ void image_to_stem_kernel(const float* __restrict__ img, uint4* __res
   const long long total = static_cast<long long>(N) * H * Wp;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int wp = static_cast<int>(idx % Wp);
-    const long long t = idx / Wp;
-    const int h = static_cast<int>(t % H);
-    const int n = static_cast<int>(t / H);
+    // 32-bit index arithmetic (the host checks total < 2^31): 64-bit div / mod by run-time values is ~4x the instructions
+    const uint32_t i32 = static_cast<uint32_t>(idx);
+    const uint32_t t = i32 / static_cast<uint32_t>(Wp);
+    const int wp = static_cast<int>(i32 - t * static_cast<uint32_t>(Wp));
+    const int n = static_cast<int>(t / static_cast<uint32_t>(H));
+    const int h = static_cast<int>(t - static_cast<uint32_t>(n) * static_cast<uint32_t>(H));
     uint4 o = make_uint4(0, 0, 0, 0);
     const int w = wp - 3;
     if (w >= 0 && w < W) {
@@ -180,11 +182,13 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
   const long long total = static_cast<long long>(N) * Ho * Wo * C8;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int c8 = static_cast<int>(idx % C8);
-    long long t = idx / C8;
-    const int wo = static_cast<int>(t % Wo); t /= Wo;
-    const int ho = static_cast<int>(t % Ho);
-    const int n = static_cast<int>(t / Ho);
+    const uint32_t i32 = static_cast<uint32_t>(idx);      // total < 2^31 (checked by the host)
+    uint32_t t = i32 / static_cast<uint32_t>(C8);
+    const int c8 = static_cast<int>(i32 - t * static_cast<uint32_t>(C8));
+    uint32_t t2 = t / static_cast<uint32_t>(Wo);
+    const int wo = static_cast<int>(t - t2 * static_cast<uint32_t>(Wo));
+    const int n = static_cast<int>(t2 / static_cast<uint32_t>(Ho));
+    const int ho = static_cast<int>(t2 - static_cast<uint32_t>(n) * static_cast<uint32_t>(Ho));
     float m[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
@@ -325,6 +329,7 @@ int vqa_image_to_stem(void* plan, const float* img, void* out, int N, int H, int
   note_op("image_to_stem", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     const long long total = static_cast<long long>(N) * H * (W + 8);
+    if (total >= (1LL << 31)) { set_last_error("image_to_stem: more than 2^31 pixels"); return -1; }
     launch_pdl(image_to_stem_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, s, img, static_cast<uint4*>(out), N, H, W);
     return launch_status("image_to_stem");
   });
@@ -345,6 +350,7 @@ int vqa_maxpool3x3s2(void* plan, const void* x, void* out, int N, int H, int W, 
   return submit(plan, stream, [=](cudaStream_t s) {
     const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
     const long long total = static_cast<long long>(N) * Ho * Wo * (C / 8);
+    if (total >= (1LL << 31)) { set_last_error("maxpool: more than 2^31 output vectors"); return -1; }
     launch_pdl(maxpool3x3s2_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(x),
                                                                    static_cast<__nv_bfloat16*>(out), N, H, W, C, Ho, Wo);
     return launch_status("maxpool3x3s2");
