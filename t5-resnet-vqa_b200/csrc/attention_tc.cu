@@ -127,6 +127,41 @@ __device__ __forceinline__ void store_tmem_row(uint32_t taddr, __nv_bfloat16* ds
   }
 }
 
+// The same row drain, but written out by the whole warp: every thread parks its 32-column segment (64 B of bf16) in a
+// warp-private 2 KB scratch area (a dead operand tile), then lanes 4r..4r+3 write row r's segment, so one store instruction
+// covers eight rows x 64 contiguous bytes instead of 32 rows x 16 bytes (the thread-per-row stores were ~4 us of the
+// backward kernel's 16).  dst / ok are the calling thread's OWN row; the other rows' are fetched by shuffle.
+template <int NC>
+__device__ __forceinline__ void store_tmem_row_warp(uint32_t taddr, __nv_bfloat16* dst, bool ok, float mul,
+                                                    uint8_t* scratch, int lane) {
+#pragma unroll 1
+  for (int c = 0; c < NC / 32; ++c) {
+    uint32_t r[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tmem_ld_32x8(taddr + c * 32 + k * 8, r[k]);
+    tmem_ld_wait();
+    __syncwarp();                                  // the previous chunk has been read out of the scratch area
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint4 u;
+      u.x = pack_bf16x2(__uint_as_float(r[k][0]) * mul, __uint_as_float(r[k][1]) * mul);
+      u.y = pack_bf16x2(__uint_as_float(r[k][2]) * mul, __uint_as_float(r[k][3]) * mul);
+      u.z = pack_bf16x2(__uint_as_float(r[k][4]) * mul, __uint_as_float(r[k][5]) * mul);
+      u.w = pack_bf16x2(__uint_as_float(r[k][6]) * mul, __uint_as_float(r[k][7]) * mul);
+      *reinterpret_cast<uint4*>(scratch + lane * 64 + ((k ^ ((lane >> 1) & 3)) << 4)) = u;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = lane + 32 * j, row = idx >> 2, k = idx & 3;
+      const uint4 v = *reinterpret_cast<const uint4*>(scratch + row * 64 + ((k ^ ((row >> 1) & 3)) << 4));
+      const long long p = __shfl_sync(0xffffffffu, static_cast<long long>(reinterpret_cast<uintptr_t>(dst)), row);
+      const int okr = __shfl_sync(0xffffffffu, ok ? 1 : 0, row);
+      if (okr) reinterpret_cast<uint4*>(static_cast<uintptr_t>(p))[c * 4 + k] = v;
+    }
+  }
+}
+
 // 8 bf16 of row `row`, columns 32g + 8k .. +8, of a block-diagonal [128 x 128] K-major tile (two 64-column chunks of
 // 128 rows x 128 B, 128B swizzle)
 __device__ __forceinline__ void store_diag8(uint8_t* tile, int row, int g, int k, const float (&v)[8]) {
@@ -321,35 +356,33 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   VQA_STAMP(5);
   const uint32_t t_s = tmem + lane_base + warp * 32;     // this row's 32 scores (diagonal block of the pair)
-  // pass 1: row maximum
+  // the row's 32 scores come out of TMEM with ONE load (a round trip per 8 columns and per pass was most of this phase)
+  uint32_t accs[32];
+  tmem_ld_32x32(t_s, accs);
+  tmem_ld_wait();
+  float scs[32];
+  // pass 1: scores (scale, bias, key mask) and the row maximum
   float mx = -INFINITY;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (k * 8 >= a.Lk) break;
-    uint32_t acc[8];
-    tmem_ld_32x8(t_s + k * 8, acc);
-    tmem_ld_wait();
-    float sc[8];
-    score8(sc, acc, k, rc.visible, a.scale, bq[2 * k], bq[2 * k + 1]);
+    score8(*reinterpret_cast<float(*)[8]>(&scs[8 * k]), *reinterpret_cast<const uint32_t(*)[8]>(&accs[8 * k]), k, rc.visible,
+           a.scale, bq[2 * k], bq[2 * k + 1]);
     const uint32_t inr = rc.in_range >> (k * 8);
 #pragma unroll
     for (int e = 0; e < 8; ++e)
-      if ((inr >> e) & 1u) mx = fmaxf(mx, sc[e]);
+      if ((inr >> e) & 1u) mx = fmaxf(mx, scs[8 * k + e]);
   }
   // pass 2: exp, row sum, dropout, bf16 P (unnormalised: the 1/sum goes onto O, flash style)
   float sum = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (k * 8 >= a.Lk) break;
-    uint32_t acc[8];
-    tmem_ld_32x8(t_s + k * 8, acc);
-    tmem_ld_wait();
     float sc[8];
-    score8(sc, acc, k, rc.visible, a.scale, bq[2 * k], bq[2 * k + 1]);
     const uint32_t inr = rc.in_range >> (k * 8), kp = keep >> (k * 8);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float ex = ((inr >> e) & 1u) ? __expf(sc[e] - mx) : 0.f;
+      const float ex = ((inr >> e) & 1u) ? __expf(scs[8 * k + e] - mx) : 0.f;
       sum += ex;
       sc[e] = ((kp >> e) & 1u) ? ex : 0.f;
     }
@@ -380,7 +413,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   VQA_STAMP(8);
   __nv_bfloat16* op = a.out + (static_cast<long long>(rc.b) * a.Lq + rc.i) * a.ldo + rc.h * HD;
-  store_tmem_row<HD>(tmem + lane_base + 128, op, rc.row_ok, inv * dc.scale);
+  store_tmem_row_warp<HD>(tmem + lane_base + 128, op, rc.row_ok, inv * dc.scale, gen + warp * 2048, t & 31);   // scratch: Q's tile (dead)
 
   VQA_STAMP(9);
   tc_fence_before();
@@ -512,22 +545,27 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t t_s = tmem + lane_base + warp * 32;          // S block of this row
   const uint32_t t_dp = tmem + lane_base + 128 + warp * 32;   // dP block of this row
   // rows that do not exist (i >= Lq, pair beyond B*H) get P = 0 so they add nothing to dK / dV
+  // S and dP rows: ONE 32-column TMEM load each (a round trip per 8 columns and per pass was ~2 us of this kernel); the
+  // probabilities and the masked, rescaled dP values then stay in registers for pass 2
+  uint32_t accs[32], accd[32];
+  tmem_ld_32x32(t_s, accs);
+  tmem_ld_32x32(t_dp, accd);
+  tmem_ld_wait();
+  float pjs[32], dps[32];
   // pass 1: rowdot = sum_j P_j dP_j (dP through the dropout mask)
   float rowdot = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (k * 8 >= a.Lk) break;
-    uint32_t acc[8], dacc[8];
-    tmem_ld_32x8(t_s + k * 8, acc);
-    tmem_ld_32x8(t_dp + k * 8, dacc);
-    tmem_ld_wait();
     float sc[8];
-    score8(sc, acc, k, rc.visible, a.scale, bq[2 * k], bq[2 * k + 1]);
+    score8(sc, *reinterpret_cast<const uint32_t(*)[8]>(&accs[8 * k]), k, rc.visible, a.scale, bq[2 * k], bq[2 * k + 1]);
     const uint32_t inr = rc.row_ok ? (rc.in_range >> (k * 8)) : 0u, kp = keep >> (k * 8);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float pj = ((inr >> e) & 1u) ? __expf(sc[e] - mx) * inv : 0.f;
-      const float dp = ((kp >> e) & 1u) ? __uint_as_float(dacc[e]) * dc.scale : 0.f;
+      const float dp = ((kp >> e) & 1u) ? __uint_as_float(accd[8 * k + e]) * dc.scale : 0.f;
+      pjs[8 * k + e] = pj;
+      dps[8 * k + e] = dp;
       rowdot = fmaf(pj, dp, rowdot);
     }
   }
@@ -543,19 +581,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (k * 8 >= a.Lk) break;
-    uint32_t acc[8], dacc[8];
-    tmem_ld_32x8(t_s + k * 8, acc);
-    tmem_ld_32x8(t_dp + k * 8, dacc);
-    tmem_ld_wait();
     float sc[8], ds[8];
-    score8(sc, acc, k, rc.visible, a.scale, bq[2 * k], bq[2 * k + 1]);
-    const uint32_t inr = rc.row_ok ? (rc.in_range >> (k * 8)) : 0u, kp = keep >> (k * 8);
+    const uint32_t kp = keep >> (k * 8);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float pj = ((inr >> e) & 1u) ? __expf(sc[e] - mx) * inv : 0.f;
-      const float m = ((kp >> e) & 1u) ? dc.scale : 0.f;
-      ds[e] = pj * (__uint_as_float(dacc[e]) * m - rowdot);
-      sc[e] = pj * m;                      // dropped probabilities (operand of dV)
+      const float pj = pjs[8 * k + e];
+      // dps already carries the dropout mask and its 1/(1-p): dropped keys contribute -P * rowdot, as before
+      ds[e] = pj * (dps[8 * k + e] - rowdot);
+      sc[e] = ((kp >> e) & 1u) ? pj * dc.scale : 0.f;   // dropped probabilities (operand of dV)
     }
     if (dbrow != nullptr) {
       if (dbvec) {
@@ -604,12 +637,15 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   VQA_STAMP(8);
   {
     __nv_bfloat16* qp = a.dq + (static_cast<long long>(rc.b) * a.Lq + rc.i) * a.lddq + rc.h * HD;
-    store_tmem_row<HD>(tmem + lane_base + cDQ, qp, rc.row_ok, 1.f);
+    // scratch: this warp's 2 KB of the Q tile (every operand tile is dead once the three output MMAs have completed)
+    uint8_t* scratch = gen + warp * 2048;
+    const int lane = t & 31;
+    store_tmem_row_warp<HD>(tmem + lane_base + cDQ, qp, rc.row_ok, 1.f, scratch, lane);
     const bool key_ok = rc.pair_ok && rc.i < a.Lk;
     __nv_bfloat16* kp = a.dk + (static_cast<long long>(rc.b) * a.Lk + rc.i) * a.lddk + rc.h * HD;
-    store_tmem_row<HD>(tmem + lane_base + cDK, kp, key_ok, 1.f);
+    store_tmem_row_warp<HD>(tmem + lane_base + cDK, kp, key_ok, 1.f, scratch, lane);
     __nv_bfloat16* vp = a.dv + (static_cast<long long>(rc.b) * a.Lk + rc.i) * a.lddv + rc.h * HD;
-    store_tmem_row<HD>(tmem + lane_base + cDV, vp, key_ok, 1.f);
+    store_tmem_row_warp<HD>(tmem + lane_base + cDV, vp, key_ok, 1.f, scratch, lane);
   }
   VQA_STAMP(9);
   tc_fence_before();
