@@ -67,7 +67,8 @@ struct Cfg {
   static constexpr int STG_BYTES = 4 * kPanelBytes;
   static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
   static constexpr int NBARS = 2 * STAGES + 9;  // full[], empty[], tmem_full[2], tmem_empty[2], res_full[2], res_empty[2], ksplit
-  static constexpr int SMEM_BYTES = BAR_OFF + NBARS * 8 + 16 + 1024;
+  static constexpr int BIAS_OFF = (BAR_OFF + NBARS * 8 + 16 + 15) & ~15;   // the tile's bias columns, double-buffered
+  static constexpr int SMEM_BYTES = BIAS_OFF + 2 * 256 * 4 + 1024;
   static constexpr int TMEM_COLS = 2 * BN;      // two accumulator stages (128, 256 or 512 columns)
 };
 
@@ -447,6 +448,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int buf = 0;                          // staging double buffer
     int rslot = 0;                        // residual ring position
     uint32_t rphase = 0;
+    int tile_it = 0;
     for (int t = unit; t < total_tiles; t += nunits) {
       const TileCoord tc = t == unit ? tc_first : coord(t);
       const bool first_split = (tc.kb_begin == 0) || KSP > 1;   // cluster split-K: every CTA finishes its own columns
@@ -504,6 +506,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         VQA_GSTAMP(11);
       }
 
+      // the tile's bias columns go to shared memory while the main loop is still running (a per-chunk global load
+      // exposed an L2 round trip per chunk: ~0.7 us of a 5 us launch)
+      float* bias_s = reinterpret_cast<float*>(smem_gen + C::BIAS_OFF) + (tile_it & 1) * 256;
+      ++tile_it;
+      if (add_bias) {
+        const int col = static_cast<int>(threadIdx.x) - 64;   // epilogue thread 0..255
+        if (col < BN) bias_s[col] = (tc.n0 + col < p.N) ? __ldg(p.bias + tc.n0 + col) : 0.f;
+      }
+      uint4 rres_n[8];
+      uint4 rmsk_n[4];
+      auto load_direct = [&](int cc, uint4 (&rr)[8], uint4 (&rm)[4]) {
+        const int nn = tc.n0 + cc * 32;
+        const bool act = kOutF32 ? (nn < p.N) : ((nn & ~63) < p.N);
+        if (kRes == 2 && act && add_res && row_ok) {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) + grow * p.ldr + nn);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) rr[k] = __ldg(rp + k);
+        }
+        if (kMask && act && row_ok) {
+          const uint4* mp = reinterpret_cast<const uint4*>(p.relu_mask + grow * p.ldm + nn);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rm[k] = __ldg(mp + k);
+        }
+      };
+      if (own_lo + half < own_hi) load_direct(own_lo + half, rres_n, rmsk_n);
+      // cluster split-K has already waited for the accumulator (phase 1); otherwise the wait sits inside the chunk loop,
+      // after the second chunk's operand loads have been requested
+      if (waited && add_bias) named_bar_sync(4, 32 * kEpiWarps);
 #pragma unroll 1
       for (int c = own_lo + half; c < own_hi; c += 2) {
         const int n = tc.n0 + c * 32;
@@ -511,18 +541,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // uniform over the barrier group: fp32 panels are one chunk wide, bf16 panels two (one per column half)
         const bool active = kOutF32 ? (n < p.N) : ((n & ~63) < p.N);
         float v[32];
-        // ---- directly read operands of this chunk are requested before the accumulator is waited for ----
+        // ---- directly read operands (fp32 residual, ReLU mask): this chunk's were requested one chunk ago (the first
+        // chunk's before the accumulator was waited for); the NEXT chunk's are requested now, so their L2 round trip
+        // runs under this chunk's TMEM read, arithmetic and store instead of being waited for ----
         uint4 rres[8];
         uint4 rmsk[4];
-        if (kRes == 2 && active && add_res && row_ok) {
-          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) + grow * p.ldr + n);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) rres[k] = __ldg(rp + k);
-        }
-        if (kMask && active && row_ok) {
-          const uint4* mp = reinterpret_cast<const uint4*>(p.relu_mask + grow * p.ldm + n);
+        for (int k = 0; k < 8; ++k) rres[k] = rres_n[k];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) rmsk[k] = __ldg(mp + k);
+        for (int k = 0; k < 4; ++k) rmsk[k] = rmsk_n[k];
+        if (c + 2 < own_hi) load_direct(c + 2, rres_n, rmsk_n);
+        if (!waited) {
+          mbar_wait_lean(tmem_full_bar(acc), acc_phase);
+          tc_fence_after();
+          waited = true;
+          if (t == unit) VQA_GSTAMP(5);
+          if (add_bias) named_bar_sync(4, 32 * kEpiWarps);   // every epilogue thread's bias column is in shared memory
         }
         float4 pks[8];
         if (KS && KSP > 1 && active) {   // first peer's partial sums of this chunk
@@ -530,12 +564,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                               ((static_cast<size_t>(unit) * KSP + (krank + 1) % KSP) * NCH + c) * (8 * 128) + row;
 #pragma unroll
           for (int k = 0; k < 8; ++k) pks[k] = __ldcg(src + k * 128);
-        }
-        if (!waited) {
-          mbar_wait_lean(tmem_full_bar(acc), acc_phase);
-          tc_fence_after();
-          waited = true;
-          if (t == unit) VQA_GSTAMP(5);
         }
         if (active) {
           uint32_t accr[32];
@@ -582,17 +610,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         if (active) {
-          if (add_bias) {
-            if (n + 32 <= p.N) {
+          if (add_bias) {   // staged in shared memory at the top of the tile (zeros beyond N)
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n) + k);
-                v[4 * k] += b4.x; v[4 * k + 1] += b4.y; v[4 * k + 2] += b4.z; v[4 * k + 3] += b4.w;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (n + i < p.N) v[i] += __ldg(p.bias + n + i);
+            for (int k = 0; k < 8; ++k) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + 4 * k);
+              v[4 * k] += b4.x; v[4 * k + 1] += b4.y; v[4 * k + 2] += b4.z; v[4 * k + 3] += b4.w;
             }
           }
           if (kRes == 1 && add_res) {
