@@ -9,6 +9,7 @@ parameter / gradient / bf16-shadow buffers, so a step replays with two host call
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -457,7 +458,8 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     r.rmsnorm_bwd(dText, 1, hid[nblk], eng.mp(t5.final_layer_norm.weight), rstd_f, None, dH,
                   eng.gp(t5.final_layer_norm.weight), M, D, p_t5, sid_final, rng,
                   g_bf, p_t5, saved_t5[nblk - 1]["sid_f"])
-    blocks_per_seg = 3
+    # T5 blocks per backward segment (= per gradient all-reduce bucket under data parallelism)
+    blocks_per_seg = max(1, int(os.environ.get("VQA_B200_DDP_BLOCKS_PER_SEG", "3")))
     seg_lo = o[id(proj.weight)]
     for bi in reversed(range(nblk)):
         blk, sv = blocks[bi], saved_t5[bi]
