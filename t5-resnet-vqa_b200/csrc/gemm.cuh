@@ -77,7 +77,6 @@ struct GemmParams {
   int ksplit;                  // > 1: cluster split-K: `ksplit` CTAs (one cluster) share an output tile, each contracts a
                                // k-slice, exchanges partial accumulators through ks_ws and finishes a column range
   float* ks_ws;                // workspace: clusters x ksplit x (bn/32) x 128 x 32 fp32
-  int split_producer;          // 1: B tiles are issued by a second thread (see gemm_kernel.cuh)
   int dbg_mode;                // bring-up: 1 = skip the MMAs, 2 = skip the loads (VQA_B200_GEMM_DBG)
   long long* dbg_clk;          // bring-up: clock64 stamps of CTA 0 (vqa_debug_gemm_timing), else null
   int dbg_a_lbo, dbg_a_sbo, dbg_b_lbo, dbg_b_sbo;  // bring-up overrides of the MN-major descriptor strides (0 = default)

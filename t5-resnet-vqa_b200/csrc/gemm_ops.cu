@@ -301,11 +301,6 @@ int gemm_op_run(const GemmOp* op, cudaStream_t stream) {
   p.fd_tiles_w = make_fastdiv(p.tiles_w); p.fd_tiles_h = make_fastdiv(p.tiles_h);
   p.fd_bx_w = make_fastdiv(p.bx_w); p.fd_bx_h = make_fastdiv(p.bx_h);
   p.dbg_clk = g_dbg_clk;
-  {
-    static int mode = -1;   // VQA_B200_SPLIT_PRODUCER=0 falls back to one issuing thread (measured slower on the whole step)
-    if (mode < 0) { const char* e = getenv("VQA_B200_SPLIT_PRODUCER"); mode = (e && e[0] == '0') ? 0 : 1; }
-    p.split_producer = mode;
-  }
   { static int dm = -1; if (dm < 0) { const char* e = getenv("VQA_B200_GEMM_DBG"); dm = e ? atoi(e) : 0; } p.dbg_mode = dm; }
   p.dbg_a_lbo = g_dbg[0]; p.dbg_a_sbo = g_dbg[1]; p.dbg_b_lbo = g_dbg[2]; p.dbg_b_sbo = g_dbg[3];
   int r = launch_gemm(op->tmA, op->tmB, op->tmOut, op->tmRes, p, op->bn, op->split_k, op->ctas, stream);
