@@ -642,3 +642,34 @@ def test_plan_replay_and_graph(C, pkg):
         side.synchronize()
     assert rel_fro(acc, 2 * (X.float() @ W.float().t())) < 2e-5
     lib.vqa_plan_destroy(plan)
+
+
+def test_plan_time_ops_selects_a_kernel_family(C, pkg):
+    """bench.py's roofline timing: only the named ops are replayed (back to back), flops and launch counts come from
+    the recorded notes, and the per-launch profile of the same plan still covers every op."""
+    from t5_resnet_vqa_b200.engine import _Rec
+    lib = pkg.lib.load()
+    plan = lib.vqa_plan_create()
+    r = _Rec(lib, plan, None)
+    M, N, K = 512, 256, 384
+    X, W = rnd(M, K, seed=1, dtype=BF), rnd(N, K, seed=2, dtype=BF)
+    y = torch.zeros(M, N, device="cuda")
+    acc = torch.zeros(M, N, device="cuda")
+    for _ in range(3):
+        r.linear(X, M, K, K, W, N, y, N, out_fp32=1, bn=128)
+        r.axpy_f32(acc, y, 1.0, M * N)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        sp = ctypes.c_void_p(side.cuda_stream)
+        ms, fl, n = ctypes.c_float(), ctypes.c_double(), ctypes.c_int()
+        pkg.lib.check(lib.vqa_plan_time_ops(plan, sp, b"gemm", 4, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n)))
+        assert n.value == 3 and fl.value == 3 * 2.0 * M * N * K and 0.0 < ms.value < 50.0
+        assert float(acc.abs().max()) == 0.0            # the axpy ops were not part of the replay
+        pkg.lib.check(lib.vqa_plan_time_ops(plan, sp, b"conv,nothing", 2, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n)))
+        assert n.value == 0 and ms.value == 0.0
+        per = (ctypes.c_float * 6)()
+        pkg.lib.check(lib.vqa_plan_profile(plan, sp, per, 100))
+        side.synchronize()
+        assert all(p > 0.0 for p in per)
+    assert rel_fro(acc, 3 * (X.float() @ W.float().t())) < 2e-5
+    lib.vqa_plan_destroy(plan)
