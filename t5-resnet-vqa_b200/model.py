@@ -13,6 +13,9 @@ from . import modules as M
 from .engine import Engine
 
 
+_DIRECT_GRADS = os.environ.get("VQA_B200_DIRECT_GRADS", "1") != "0"
+
+
 class _StepFunction(torch.autograd.Function):
     """One autograd node for the whole model: forward replays the forward plan, backward the backward plan.
     Gradients come back as views of the engine's flat fp32 gradient buffer (no per-parameter copies)."""
@@ -39,6 +42,20 @@ class _StepFunction(torch.autograd.Function):
                 if p.grad is not None:
                     p.grad = p.grad.clone()
         eng.backward(st, gloss, glogp)
+        if _DIRECT_GRADS and not any(p._backward_hooks or getattr(p, "_post_accumulate_grad_hooks", None) for p in params):
+            # Host fast path: hand out the engine's cached gradient views directly instead of returning 180 fresh views
+            # for autograd's AccumulateGrad nodes (~1 ms of host time per step, which the end-to-end step - host inputs,
+            # loss read back every step - cannot hide).  Same result: `.grad` is a view of the flat gradient buffer, or,
+            # when a gradient already exists (accumulation over micro-batches), that gradient plus this step's.
+            # Parameters with hooks keep the autograd path below.
+            for p, v in zip(params, eng.grad_views()):
+                if v is None:
+                    continue
+                if p.grad is None:
+                    p.grad = v
+                else:
+                    p.grad = p.grad + v
+            return (None, None, None) + (None,) * len(params)
         grads = []
         g = eng.grad
         for p in params:

@@ -117,11 +117,19 @@ class VQAFusedAdamW(torch.optim.Optimizer):
         return sd
 
     def _signature(self):
+        """What the contiguous-range table depends on.  Gradients handed out by an Engine are cached view objects
+        (engine.grad_views), recognised by identity: the id of such a view pins both the parameter's and the gradient's
+        place in the flat buffers, and 180 `data_ptr()` calls per step (~0.3 ms of host time) are avoided."""
         sig = []
         for group in self.param_groups:
             for p in group["params"]:
                 g = p.grad
-                sig.append((p.data_ptr(), g.data_ptr() if g is not None else 0))
+                if g is None:
+                    sig.append((id(p), 0))
+                elif getattr(g, "_vqa_flat_view", False):
+                    sig.append((id(p), id(g)))
+                else:
+                    sig.append((p.data_ptr(), g.data_ptr()))
         return tuple(sig)
 
     @torch.no_grad()
@@ -200,6 +208,22 @@ _torch_clip_grad_norm_ = torch.nn.utils.clip_grad_norm_
 def _engine_holding_all_grads(params):
     """The Engine whose flat gradient buffer holds EVERY gradient in `params` (and nothing else), or None."""
     eng, n = None, 0
+    # fast path: every gradient is one of an engine's cached views (identity check, no pointer arithmetic)
+    with_grad = [p for p in params if p.grad is not None]      # frozen parameters (the backbone) have none
+    p0 = with_grad[0] if with_grad else None
+    if p0 is not None and getattr(p0.grad, "_vqa_flat_view", False) and p0.is_cuda:
+        cand = engine_for_ptr(p0.data_ptr())
+        if cand is not None and len(with_grad) == len(cand.params):
+            views = cand.grad_views()
+            index = cand.param_index
+            ok = True
+            for p in with_grad:
+                i = index.get(id(p))
+                if i is None or p.grad is not views[i]:
+                    ok = False
+                    break
+            if ok:
+                return cand
     for p in params:
         g = p.grad
         if g is None:
