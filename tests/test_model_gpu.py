@@ -267,3 +267,34 @@ def test_clip_grad_norm_fast_path(pkg, cuda):
     w = torch.randn(10, 10, device=cuda, requires_grad=True)
     w.grad = torch.ones_like(w)
     assert abs(float(torch.nn.utils.clip_grad_norm_([w], 1.0)) - 10.0) < 1e-4
+
+
+def test_gradient_accumulation_and_hooks_keep_autograd_semantics(pkg, cuda):
+    """Two backward passes without zero_grad add up (micro-batch accumulation), the first pass's gradients are views of the
+    engine's flat buffer, and a parameter hook (which forces the autograd AccumulateGrad path) sees the same gradient."""
+    from oracle import vqa_oracle as O
+    sd = O.random_state_dict("resnet18", 170, seed=0)
+    batch = O.synthetic_batch(2, 16, 64, 64, 170, seed=1)
+    m = build(pkg, "resnet18", sd, cuda, train=False)
+    _, loss = run(m, batch, cuda)
+    loss.backward()
+    eng = m._engine
+    w = m.classification_layer.weight
+    assert w.grad.data_ptr() == eng.gp(w)                      # a view of the flat gradient buffer, no copy
+    assert all(p.grad is None for p in m.vision_model.parameters())
+    g1 = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    _, loss = run(m, batch, cuda)
+    loss.backward()                                            # no zero_grad in between
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            assert torch.allclose(p.grad, 2 * g1[k], rtol=1e-5, atol=1e-7), k
+    # hooks: the step falls back to returning gradients through autograd, so the hook fires with the same values
+    seen = {}
+    h = w.register_hook(lambda g: seen.setdefault("g", g.detach().clone()))
+    for p in m.parameters():
+        p.grad = None
+    _, loss = run(m, batch, cuda)
+    loss.backward()
+    h.remove()
+    assert "g" in seen and torch.allclose(seen["g"], g1["classification_layer.weight"], rtol=1e-5, atol=1e-7)
+    assert torch.allclose(w.grad, g1["classification_layer.weight"], rtol=1e-5, atol=1e-7)
