@@ -1,23 +1,27 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a:  D[M,N] = epilogue( A[M,K] * B[N,K]^T ), bf16 in, fp32 accumulate.
 //
-// Persistent kernel, one CTA per SM, 352 threads, static round-robin tile scheduler over 128 x BN output tiles
-// (n-tile fastest so CTAs running side by side share the A tile in L2; split-K slices are extra tiles):
-//   warp 0      TMA producer   (one elected lane; STAGES-deep ring of 128x64 A and BNx64 B tiles, runs ahead
-//                               across tile boundaries)
-//   warp 1      TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma into one of TWO accumulator
-//                               stages of BN columns, so tile i+1 is multiplied while tile i is drained)
+// Persistent kernel, one CTA per SM, 384 threads (12 warps), static round-robin tile scheduler over 128 x BN output
+// tiles (n-tile fastest so CTAs running side by side share the A tile in L2; split-K slices are extra tiles).  The warp
+// index is broadcast from lane 0, which makes the role branches warp-uniform for ptxas: the producer and MMA loops are run
+// by the WHOLE warp with their state in uniform registers, and one elected lane issues from inside the asm blocks.
+//   warp 0      A-operand TMA producer (STAGES-deep ring of 128x64 A and BNx64 B tiles, runs ahead across tiles;
+//                               coordinates advance incrementally: no division or parameter reload per k-block)
+//   warp 11     B-operand TMA producer (same ring, same barriers: the A producer announces the bytes of both)
+//   warp 1      TMEM allocator + MMA issuer: one instruction group per k-block (non-blocking poll of the next stage,
+//                               four tcgen05.mma of K = 16, commit) into one of TWO accumulator stages of BN columns, so
+//                               tile i+1 is multiplied while tile i is drained
 //   warps 2..9  epilogue       (8 warps; warp w owns TMEM lanes 32*(w%4).. and every other 32-column chunk.  A thread
 //                               owns ONE output row: tcgen05.ld gives it 32 consecutive fp32 columns, which it runs
-//                               through bias / ReLU / ReLU-mask / dropout / residual in registers, packs, and writes
-//                               into a 128-byte-swizzled staging panel in shared memory; one elected thread per
-//                               panel then issues a TMA tensor store (or fp32 reduce-add for split-K / accumulate),
-//                               double-buffered so stores drain while the next panel is computed.  TMA clips ragged
-//                               M / N edges and maps convolution pixel boxes back to NHWC, so the epilogue has no
-//                               per-row address arithmetic at all.)
+//                               through bias (staged in shared memory during the main loop) / ReLU / ReLU-mask / dropout
+//                               / residual in registers, packs, and writes into a 128-byte-swizzled staging panel in
+//                               shared memory; one elected thread per panel then issues a TMA tensor store (or fp32
+//                               reduce-add for split-K / accumulate), double-buffered so stores drain while the next
+//                               panel is computed.  TMA clips ragged M / N edges and maps convolution pixel boxes back to
+//                               NHWC.  fp32 residuals / ReLU masks are read directly, one chunk ahead of their use.)
 //   warp 10     residual producer (bf16 residual tiles of the ResNet block tails, TMA-loaded panel by panel into a
-//                               two-slot ring so the HBM latency of the epilogue's reads is covered by bytes in flight,
-//                               not by registers; fp32 residuals / ReLU masks of the token GEMMs are L2-resident and
-//                               are read directly, one full 128-byte line per thread)
+//                               two-slot ring so the HBM latency of the epilogue's reads is covered by bytes in flight)
+// CTAS = 2: a CTA pair (cluster of two, cta_group::2) runs one 256-row MMA, each CTA staging half of the B tile.
+// KS: cluster split-K instantiations (a cluster per tile, k-slices per CTA, partial sums through an L2 workspace).
 // Operands may be K-major or MN-major in global memory (instruction-descriptor transpose bits), so
 // forward (X W^T), dgrad (dY W) and wgrad (dY^T X) all run on this kernel without any transposed copy.
 // A may also be an implicit-GEMM convolution operand: NHWC activations read through a 4-D tensor map,
