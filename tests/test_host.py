@@ -154,3 +154,22 @@ def test_gradient_averaging_two_ranks_gloo(pkg):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_tile_model_agrees_with_the_measured_table(pkg):
+    """The launch-time model behind pick_tile is fitted to profiles/r1_gemm_bench.txt (B200, graph-replayed): for every
+    measured GEMM shape its choice among the single-CTA tile widths must be within 12 % of the fastest measured one."""
+    import re
+    from t5_resnet_vqa_b200 import engine as E
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r1_gemm_bench.txt")
+    rows = []
+    for line in open(path):
+        m = re.match(r"(fwd|dgrad|wgrad)\s+M(\d+)\s+N(\d+)\s+K(\d+)\s+([\d.]+)\s+([\d.]+)\s+([\d.]+)", line)
+        if m:
+            rows.append((m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4)),
+                         {64: float(m.group(5)), 128: float(m.group(6)), 256: float(m.group(7))}))
+    assert len(rows) >= 12
+    for kind, M, N, K, t in rows:
+        bn, ks = E.pick_tile(M, N, K)
+        assert ks == 1
+        assert t[bn] <= 1.12 * min(t.values()), (kind, M, N, K, bn, t)
