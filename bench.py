@@ -12,7 +12,10 @@ replicas of that per-GPU batch (weak scaling; N=8 is BASELINE's global batch 512
 
 `value`  : device-resident inputs, K steps timed with CUDA events, max over ranks.
 `e2e`    : the same step called with PINNED HOST tensors (H2D copies inside the timed region) plus the
-           trainer's per-step `loss.item()` device->host read.
+           trainer's per-step `loss.item()` device->host read.  Images travel as uint8 RGB [B,H,W,3] (what cv2 hands the
+           reference's collate before ToTensor; the /255 runs in the stem-packing kernel); `e2e_fp32_chw` is the same
+           measurement with the collate's float [B,3,H,W] tensors.
+--global-batch G: fixed global batch split over the ranks (512 -> 256/128/64 per GPU), "strong".
 `roofline`: every launch of the forward/backward plans is timed live with CUDA events (vqa_plan_profile);
            the dominant kernel family is the tcgen05 GEMM / implicit-GEMM conv kernel; achieved = its
            algorithmic FLOPs per step / its summed launch durations; peak from MEASURED_PEAKS.json.
@@ -90,6 +93,8 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 WORKLOAD = ("ResNet50 + T5-base encoder + 3xSGA train step (fwd+bwd+clip+AdamW-amsgrad), batch %d per GPU, "
             "224x224 images, 32-token questions, 170 answers, dropout on")
+CPU_WORKLOAD = ("ResNet50 + T5-base encoder + 3xSGA train step (fwd+bwd+clip+AdamW-amsgrad), batch %d, 224x224 images, "
+                "32-token questions, 170 answers, dropout off (oracle port of the reference, fp32, torch CPU)")
 
 
 def cpu_reference_steps(steps, warmup, batch=4):
@@ -139,9 +144,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "train samples/s", "value": r["value"], "unit": "samples/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": max(warmup, 1), "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD % PER_GPU_BATCH, "global_batch": args.gpus * PER_GPU_BATCH,
+            "config": {"workload": CPU_WORKLOAD % r["batch"], "global_batch": r["batch"],
                        "parallelism": "cpu", "sample_batch": r["batch"],
-                       "note": "the reference's CPU fp32 path (oracle port) on a bounded sample of the same workload"},
+                       "note": "the reference's CPU fp32 path (oracle port) on a bounded sample (batch %d, dropout off) of "
+                               "the GPU arm's workload (%s)" % (r["batch"], WORKLOAD % PER_GPU_BATCH)},
             "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
                              "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -253,6 +259,16 @@ def time_adamw(pkg, n_params, reps=5):
     return ms, 38.0 * n_params
 
 
+def dram_traffic():
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernels from the committed `ncu --set full`
+    capture of this same step (profiles/r2_dram_traffic.json, written by tools/ncu_summary.py); {} when absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -260,6 +276,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE: 64)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="fixed GLOBAL batch split over the ranks (BASELINE.md section 5: 512); overrides --batch, strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default=None, help="write the per-launch timing table here")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-phase device/host time breakdown")
@@ -289,6 +307,10 @@ def main():
     model = pkg.ResnetVQAModel(VISION, "t5-base", answer_spaces=ANSWERS)
     model.to(dev).train()
     B = args.batch
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch must be a multiple of the number of ranks")
+        B = args.global_batch // world
     g = torch.Generator().manual_seed(1 + rank)
     host = dict(
         question_input_ids=torch.randint(2, 32100, (B, L_TEXT), generator=g).pin_memory(),
@@ -298,6 +320,9 @@ def main():
         annotation_ids=torch.randint(0, ANSWERS, (B,), generator=g).pin_memory(),
         image_tensors=torch.rand(B, 3, IMG, IMG, generator=g).pin_memory())
     devb = {k: (v.to(dev) if v is not None else None) for k, v in host.items()}
+    # input edge: the same images as cv2 leaves them (uint8 RGB, HWC) - a quarter of the bytes over PCIe
+    host_u8 = dict(host, image_tensors=(host["image_tensors"] * 255.0).round().clamp(0, 255).to(torch.uint8)
+                   .permute(0, 2, 3, 1).contiguous().pin_memory())
     total_steps = 2 * (warmup + args.steps) + 16
     opt, sched = build_trainer_objects(model, total_steps)
 
@@ -367,22 +392,31 @@ def main():
         print(json.dumps({"breakdown_device_ms": acc_d, "breakdown_host_enqueue_ms": acc_h}), file=sys.stderr)
 
     # ---- timed: end to end from pinned host memory, loss read back every step ----
-    for _ in range(2):
-        train_one_step(model, opt, sched, host, read_loss=True)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        train_one_step(model, opt, sched, host, read_loss=True)
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
+    def time_e2e(hb):
+        for _ in range(3):     # first call records the plan of this image format
+            train_one_step(model, opt, sched, hb, read_loss=True)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            train_one_step(model, opt, sched, hb, read_loss=True)
+        f1.record()
+        barrier()
+        return f0.elapsed_time(f1)
+    ms_e2e_f32 = time_e2e(host)
+    ms_e2e = time_e2e(host_u8)
     clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
 
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, ms_e2e_f32], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(t[0]), float(t[1])
+    ms_total, ms_e2e, ms_e2e_f32 = float(t[0]), float(t[1]), float(t[2])
+
+    ddp_eq = None
+    if world > 1:
+        # N-rank step == 1-rank step on the concatenated batch (small configuration; all ranks take part)
+        from tools import ddp_check
+        ddp_eq = ddp_check.check(dev, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -403,10 +437,13 @@ def main():
     # the dominant kernel's duration as it runs in the step: its launches replayed back to back between one event pair
     t_ms, t_fl, t_n = time_family(pkg, model, st, "gemm,conv,conv_wgrad")
     achieved_tf = t_fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
+    traffic = dram_traffic()
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all %d GEMM / implicit-GEMM conv launches of one step)" % t_n,
-                "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / pk["tf_sustained"], "traffic": None,
-                "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                "achieved": achieved_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                "frac": achieved_tf / pk["tf_burst"], "frac_of_sustained": achieved_tf / pk["tf_sustained"],
+                "traffic": traffic.get("gemm_family_bytes_per_step"), "traffic_source": traffic.get("source"),
+                "peak_source": pk["source"] + ", burst figure: the family is replayed on its own (~20 ms), not inside a long "
+                               "step; frac_of_sustained uses the 4-second back-to-back figure",
                 "flops_per_step": t_fl, "ms_per_step_in_kernel": t_ms, "launches_per_step": t_n,
                 "timing": "all launches of the kernel in one step replayed back to back on one stream, 5 passes between "
                           "one pair of CUDA events (vqa_plan_time_ops)",
@@ -416,7 +453,7 @@ def main():
     a_ms, a_bytes = time_adamw(pkg, int(model._engine.total))
     roofline_hbm = {"bound": "hbm", "kernel": "adamw_kernel (fused AdamW-amsgrad + bf16 shadow, %d parameters)" % model._engine.total,
                     "achieved": a_bytes / (a_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": a_bytes / (a_ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
+                    "frac": a_bytes / (a_ms * 1e-3) / 1e9 / pk["hbm"], "traffic": traffic.get("adamw_bytes_per_launch"),
                     "bytes_per_launch": a_bytes, "ms_per_launch": a_ms, "peak_source": pk["source"]}
     if args.profile_json:
         with open(args.profile_json, "w") as f:
@@ -425,18 +462,23 @@ def main():
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1000.0)
     e2e_value = world * B / (ms_e2e / args.steps / 1000.0)
-    h2d = sum(v.numel() * v.element_size() for v in host.values() if v is not None)
+    h2d = sum(v.numel() * v.element_size() for v in host_u8.values() if v is not None)
+    h2d_f32 = sum(v.numel() * v.element_size() for v in host.values() if v is not None)
     launches_per_step = st.n_fwd_launches + st.n_bwd_launches + n_opt_launches + 2  # + shadow prep, rng advance
     line = {
         "metric": "train samples/s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD % B,
                    "global_batch": world * B, "parallelism": "dp%d" % world,
                    "l2": "working set per step (activations + 567 MB fp32 gradients + 2.3 GB optimizer state) exceeds the 126 MB L2",
                    "optimizer": type(opt).__name__, "cuda_graphs": bool(model._engine.use_graphs)},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "images": "uint8 RGB [B,H,W,3], /255 on the device"},
+        "e2e_fp32_chw": {"value": world * B / (ms_e2e_f32 / args.steps / 1000.0), "unit": "samples/s",
+                         "h2d_bytes_per_step": h2d_f32, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e_f32 / args.steps,
+                         "images": "float32 [B,3,H,W] (the reference collate's ToTensor output)"},
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,
         "roofline": roofline,
@@ -445,6 +487,8 @@ def main():
         "clocks": clocks,
         "loss": last_loss,
     }
+    if ddp_eq is not None:
+        line["ddp_equivalence"] = ddp_eq
     if "adamw" in fam or True:
         line["kernel_families"] = {k: {"launches": v["launches"], "ms": round(v["ms"], 4)}
                                    for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:12]}

@@ -99,6 +99,14 @@ typedef struct {
   void* ks_ws;   /* device workspace, >= vqa_gemm_ksplit_workspace(M, N, bn, ksplit) bytes, 16-byte aligned; must not be
                     shared by launches that can run concurrently (other streams / plan lanes) */
   long long ks_ws_bytes;
+  /* Two-term operand split (a forward GEMM whose bf16 rounding must not be seen: the early T5 blocks, DESIGN.md
+     "Parity").  B_lo: bf16 [N,K] (ldb) holding bf16(W - bf16(W)) of the fp32 weight whose bf16(W) is B; the launch
+     then contracts A*B^T + A*B_lo^T in one k-loop (fp32 accumulation in TMEM).  a_lo_col > 0: A carries its own
+     low-order half in columns [a_lo_col, a_lo_col + K) of the same rows (lda >= a_lo_col + K) and the term
+     A_lo*B^T is added as well.  Needs K % 64 == 0, K-major operands, no split_k / accumulate / ksplit and no bf16
+     residual.  NULL / 0: plain bf16 GEMM. */
+  const void* B_lo;
+  long long a_lo_col;
 } vqa_gemm_args;
 long long vqa_gemm_ksplit_workspace(int M, int N, int bn, int ksplit);
 int vqa_gemm_bf16(void* plan, const vqa_gemm_args* a, void* stream);
@@ -133,6 +141,9 @@ int vqa_conv2d_wgrad_bf16(void* plan, const vqa_conv_wgrad_args* a, void* stream
 
 /* ---- layout / precision plumbing (weight preparation, input formatting) ------------------------- */
 int vqa_cast_f32_bf16(void* plan, const float* src, void* dst, long long n, void* stream);
+int vqa_cast_bf16_f32(void* plan, const void* src, float* dst, long long n, void* stream);
+/* dst[i] = bf16(src[i] - float(bf16(src[i]))): the low-order half of the two-term split of an fp32 weight range */
+int vqa_split_lo_bf16(void* plan, const float* src, void* dst, long long n, void* stream);
 int vqa_memset_zero(void* plan, void* ptr, long long bytes, void* stream);
 int vqa_axpy_f32(void* plan, float* y, const float* x, float a, long long n, void* stream); /* y += a*x */
 /* Conv2d weight [O,I,R,S] fp32 (+ eval BatchNorm gamma/beta/mean/var, may be NULL) -> bf16
@@ -147,6 +158,9 @@ int vqa_convT_weight_prep(void* plan, const float* w, void* w_out, int Cin, int 
 int vqa_convT_wgrad_unprep(void* plan, const float* dw_conv, float* dw, int Cin, int Cout, void* stream);
 /* images fp32 [N,3,H,W] -> bf16 [N,H,W+8,8] (stem layout); bf16 NHWC -> fp32 NCHW feature map */
 int vqa_image_to_stem(void* plan, const float* img, void* out, int N, int H, int W, void* stream);
+/* input edge: uint8 RGB [N,H,W,3] as cv2 produces it (dataset_utils/resnet_vqa_daquar_dataset.py:153-171)
+ * -> the same stem layout with transforms.ToTensor()'s /255 folded in: a quarter of the fp32 CHW upload */
+int vqa_image_u8_to_stem(void* plan, const uint8_t* img, void* out, int N, int H, int W, void* stream);
 int vqa_nhwc_to_nchw_f32(void* plan, const void* x, float* out, int N, int H, int W, int C, void* stream);
 /* MaxPool2d(3, stride 2, pad 1) on bf16 NHWC (tv:200) */
 int vqa_maxpool3x3s2(void* plan, const void* x, void* out, int N, int H, int W, int C, void* stream);
@@ -162,6 +176,10 @@ int vqa_embedding_bwd(void* plan, const long long* ids, const float* dout, float
 int vqa_rmsnorm_fwd(void* plan, const float* x, const float* w, void* y_bf16, float* y_f32,
                     float* rstd, int M, int D, float eps, float drop_p, uint32_t sid,
                     const uint64_t* rng, void* stream);
+/* Same normalisation written as a two-term bf16 split: y_hilo is bf16 [M, 2*D], columns [0,D) = bf16(y),
+ * columns [D,2D) = bf16(y - bf16(y)) (the A operand of a vqa_gemm_bf16 launch with a_lo_col = D). */
+int vqa_rmsnorm_fwd_split(void* plan, const float* x, const float* w, void* y_hilo, float* rstd, int M, int D,
+                          float eps, void* stream);
 /* g_out (bf16 [M,D], may be NULL): dropout-masked copy of dx under stream g_sid / probability g_drop_p, i.e.
  * the gradient entering the next residual branch, produced here instead of by a separate vqa_dropout_cast. */
 int vqa_rmsnorm_bwd(void* plan, const void* dy, int dy_fp32, const float* x, const float* w,

@@ -26,6 +26,10 @@ CASES = {
     "r50_b2_masked": dict(vision="resnet50", B=2, L=32, H=224, W=224, masked_tail=10),
     # the reference's native collate shapes: 256x256 images (64 vision tokens), 16-token questions
     "r18_b2_256_l16": dict(vision="resnet18", B=2, L=16, H=256, W=256, masked_tail=3),
+    # BASELINE.json configs[1] (the config every bench number is quoted on): ResNet50, batch 64, 224x224, 32 tokens,
+    # all-ones mask, and the same with a padded tail of 10 tokens
+    "r50_b64": dict(vision="resnet50", B=64, L=32, H=224, W=224, masked_tail=0),
+    "r50_b64_masked": dict(vision="resnet50", B=64, L=32, H=224, W=224, masked_tail=10),
 }
 
 

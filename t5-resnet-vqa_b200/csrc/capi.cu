@@ -10,7 +10,7 @@ using namespace vqa;
 extern "C" {
 
 const char* vqa_last_error(void) { return get_last_error(); }
-int vqa_version(void) { return 100; }
+int vqa_version(void) { return 101; }
 int vqa_debug_set_umma(int a_lbo, int a_sbo, int b_lbo, int b_sbo) {
   gemm_debug_set_umma(a_lbo, a_sbo, b_lbo, b_sbo);
   return 0;
@@ -36,6 +36,7 @@ int vqa_gemm_bf16(void* plan, const vqa_gemm_args* a, void* stream) {
   e.residual = a->residual; e.ldr = a->ldr; e.res_fp32 = a->res_fp32; e.res_first = a->res_first;
   e.alpha = a->alpha; e.accumulate = a->accumulate;
   e.ksplit = a->ksplit; e.ks_ws = static_cast<float*>(a->ks_ws); e.ks_ws_bytes = static_cast<size_t>(a->ks_ws_bytes);
+  e.b_lo = a->B_lo; e.a_lo_col = a->a_lo_col;
   GemmOp op;
   int r = gemm_op_init(&op, a->M, a->N, a->K, a->A, a->lda, a->a_mn, a->B, a->ldb, a->b_mn, a->out,
                        a->ldo, a->out_fp32, e, a->bn, a->split_k, a->cta_pair ? 2 : 1);

@@ -35,6 +35,39 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
   }
 }
 
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  pdl_grid_sync();
+  const long long nvec = n >> 3;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float f[8];
+    load_bf16x8(src + i * 8, f);
+    store_f32x8(dst + i * 8, f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const long long i = (nvec << 3) + threadIdx.x;
+    dst[i] = __bfloat162float(src[i]);
+  }
+}
+
+// low-order half of the two-term bf16 split of an fp32 range: dst = bf16(src - float(bf16(src)))
+__global__ void split_lo_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  pdl_grid_sync();
+  const long long nvec = n >> 3;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float f[8];
+    load_f32x8(src + i * 8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] -= __bfloat162float(__float2bfloat16_rn(f[k]));
+    store_bf16x8(dst + i * 8, f);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const long long i = (nvec << 3) + threadIdx.x;
+    dst[i] = __float2bfloat16_rn(src[i] - __bfloat162float(__float2bfloat16_rn(src[i])));
+  }
+}
+
 __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, long long n) {
   pdl_grid_sync();
   const long long nvec = n >> 2;
@@ -150,6 +183,29 @@ __global__ void image_to_stem_kernel(const float* __restrict__ img, uint4* __res
       const float* p = img + (static_cast<long long>(n) * 3) * plane + static_cast<long long>(h) * W + w;
       o.x = pack_bf16x2(p[0], p[plane]);
       o.y = pack_bf16x2(p[2 * plane], 0.f);
+    }
+    out[idx] = o;
+  }
+}
+
+// uint8 RGB [N, H, W, 3] (what cv2 hands the reference's collate before ToTensor, dataset_utils/resnet_vqa_daquar_dataset.py:
+// 153-171) -> the same stem layout; the /255 of transforms.ToTensor() is folded in (IEEE division, so the bf16 values equal
+// those of the fp32 path bit for bit)
+__global__ void image_u8_to_stem_kernel(const uint8_t* __restrict__ img, uint4* __restrict__ out, int N, int H, int W) {
+  pdl_grid_sync();
+  const int Wp = W + 8;
+  const long long total = static_cast<long long>(N) * H * Wp;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const uint32_t i32 = static_cast<uint32_t>(idx);
+    const uint32_t t = i32 / static_cast<uint32_t>(Wp);          // = n * H + h
+    const int wp = static_cast<int>(i32 - t * static_cast<uint32_t>(Wp));
+    uint4 o = make_uint4(0, 0, 0, 0);
+    const int w = wp - 3;
+    if (w >= 0 && w < W) {
+      const uint8_t* p = img + (static_cast<long long>(t) * W + w) * 3;
+      o.x = pack_bf16x2(static_cast<float>(p[0]) / 255.f, static_cast<float>(p[1]) / 255.f);
+      o.y = pack_bf16x2(static_cast<float>(p[2]) / 255.f, 0.f);
     }
     out[idx] = o;
   }
@@ -275,6 +331,30 @@ int vqa_cast_f32_bf16(void* plan, const float* src, void* dst, long long n, void
   });
 }
 
+int vqa_cast_bf16_f32(void* plan, const void* src, float* dst, long long n, void* stream) {
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) {
+    set_last_error("cast: pointers must be 16-byte aligned");
+    return -1;
+  }
+  note_op("cast_bf16_f32", 0.0, 6.0 * static_cast<double>(n));
+  return submit(plan, stream, [=](cudaStream_t s) {
+    launch_pdl(cast_bf16_f32_kernel, dim3(grid_for((n >> 3) + 8, 256)), dim3(256), 0, s, static_cast<const __nv_bfloat16*>(src), dst, n);
+    return launch_status("cast_bf16_f32");
+  });
+}
+
+int vqa_split_lo_bf16(void* plan, const float* src, void* dst, long long n, void* stream) {
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15)) {
+    set_last_error("split_lo: pointers must be 16-byte aligned");
+    return -1;
+  }
+  note_op("split_lo_bf16", 0.0, 6.0 * static_cast<double>(n));
+  return submit(plan, stream, [=](cudaStream_t s) {
+    launch_pdl(split_lo_bf16_kernel, dim3(grid_for((n >> 3) + 8, 256)), dim3(256), 0, s, src, static_cast<__nv_bfloat16*>(dst), n);
+    return launch_status("split_lo_bf16");
+  });
+}
+
 int vqa_memset_zero(void* plan, void* ptr, long long bytes, void* stream) {
   note_op("memset", 0.0, static_cast<double>(bytes));
   return submit(plan, stream, [=](cudaStream_t s) {
@@ -332,6 +412,16 @@ int vqa_image_to_stem(void* plan, const float* img, void* out, int N, int H, int
     if (total >= (1LL << 31)) { set_last_error("image_to_stem: more than 2^31 pixels"); return -1; }
     launch_pdl(image_to_stem_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, s, img, static_cast<uint4*>(out), N, H, W);
     return launch_status("image_to_stem");
+  });
+}
+
+int vqa_image_u8_to_stem(void* plan, const uint8_t* img, void* out, int N, int H, int W, void* stream) {
+  note_op("image_to_stem", 0.0, 0.0);
+  return submit(plan, stream, [=](cudaStream_t s) {
+    const long long total = static_cast<long long>(N) * H * (W + 8);
+    if (total >= (1LL << 31)) { set_last_error("image_u8_to_stem: more than 2^31 pixels"); return -1; }
+    launch_pdl(image_u8_to_stem_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, s, img, static_cast<uint4*>(out), N, H, W);
+    return launch_status("image_u8_to_stem");
   });
 }
 

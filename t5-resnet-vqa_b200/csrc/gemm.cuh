@@ -77,6 +77,10 @@ struct GemmParams {
   int ksplit;                  // > 1: cluster split-K: `ksplit` CTAs (one cluster) share an output tile, each contracts a
                                // k-slice, exchanges partial accumulators through ks_ws and finishes a column range
   float* ks_ws;                // workspace: clusters x ksplit x (bn/32) x 128 x 32 fp32
+  // two-term operand split (plain K-major GEMMs only): the k-loop runs nseg segments of kseg k-blocks each over the SAME
+  // output tile: (A, B), [(A_lo, B),] (A, B_lo).  A_lo = columns [a_lo_col, a_lo_col + K) of A's rows; B_lo is read
+  // through the residual tensor map (a split launch has no bf16 residual).  nseg <= 1: off.
+  int nseg, kseg, a_lo_col;
   int dbg_mode;                // bring-up: 1 = skip the MMAs, 2 = skip the loads (VQA_B200_GEMM_DBG)
   long long* dbg_clk;          // bring-up: clock64 stamps of CTA 0 (vqa_debug_gemm_timing), else null
   int dbg_a_lbo, dbg_a_sbo, dbg_b_lbo, dbg_b_sbo;  // bring-up overrides of the MN-major descriptor strides (0 = default)

@@ -199,7 +199,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     mbar_fence_init();
   } else if (warp == 2 && lane < 4) {
     const CUtensorMap* tm = lane == 0 ? &tmA : (lane == 1 ? &tmB : (lane == 2 ? &tmOut : &tmRes));
-    if (lane < 3 || kRes == 1) tma_prefetch_desc(tm);
+    if (lane < 3 || kRes == 1 || p.nseg > 1) tma_prefetch_desc(tm);
   }
   if (warp == 1) {
     if (CTAS == 2) { tmem_alloc_pair(tmem_slot, C::TMEM_COLS); tmem_relinquish_pair(); }
@@ -267,8 +267,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (do_a) {
         if (a_mode == LOAD_2D && !a_mn) {
-          int k0 = tc.kb_begin * BK;
-          for (int i = 0; i < nkb; ++i, k0 += BK) VQA_PRODUCE(load2(sa, &tmA, fb, k0, tc.m0));
+          if (p.nseg > 1) {   // two-term operand split: segments (A, B), [(A_lo, B),] (A, B_lo) over the same tile
+            const int nseg = p.nseg, kseg = p.kseg;
+            for (int sgm = 0; sgm < nseg; ++sgm) {
+              int k0 = (sgm == 1 && nseg == 3) ? p.a_lo_col : 0;
+              for (int i = 0; i < kseg; ++i, k0 += BK) VQA_PRODUCE(load2(sa, &tmA, fb, k0, tc.m0));
+            }
+          } else {
+            int k0 = tc.kb_begin * BK;
+            for (int i = 0; i < nkb; ++i, k0 += BK) VQA_PRODUCE(load2(sa, &tmA, fb, k0, tc.m0));
+          }
         } else if (a_mode == LOAD_2D) {
           int k0 = tc.kb_begin * BK;
           for (int i = 0; i < nkb; ++i, k0 += BK)
@@ -299,8 +307,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       } else {
         const int nb0 = tc.n0 + rank * (BN / CTAS);   // first B-tile row / column staged by this CTA
         if (b_mode == LOAD_2D && !b_mn) {
-          int k0 = tc.kb_begin * BK;
-          for (int i = 0; i < nkb; ++i, k0 += BK) VQA_PRODUCE(load2(sb, &tmB, fb, k0, nb0));
+          if (p.nseg > 1) {   // the last segment reads the low-order half of B (residual tensor map)
+            const int nseg = p.nseg, kseg = p.kseg;
+            for (int sgm = 0; sgm < nseg; ++sgm) {
+              const CUtensorMap* mb = sgm == nseg - 1 ? &tmRes : &tmB;
+              int k0 = 0;
+              for (int i = 0; i < kseg; ++i, k0 += BK) VQA_PRODUCE(load2(sb, mb, fb, k0, nb0));
+            }
+          } else {
+            int k0 = tc.kb_begin * BK;
+            for (int i = 0; i < nkb; ++i, k0 += BK) VQA_PRODUCE(load2(sb, &tmB, fb, k0, nb0));
+          }
         } else if (b_mode == LOAD_2D) {
           int k0 = tc.kb_begin * BK;
           for (int i = 0; i < nkb; ++i, k0 += BK) {

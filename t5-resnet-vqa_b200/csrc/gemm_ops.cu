@@ -152,8 +152,26 @@ int gemm_op_init(GemmOp* op, int M, int N, int K, const void* A, long long lda, 
   p.out = out; p.ldo = ldo; p.out_fp32 = out_fp32; p.out_pixels = 0;
   p.atomic_out = (split_k > 1 || epi.accumulate) ? 1 : 0;
   fill_epilogue(p, epi);
+  const bool split = epi.b_lo != nullptr;
+  if (split) {
+    if (a_mn || b_mn || split_k > 1 || epi.accumulate || epi.ksplit > 1 || (K % 64) || epi.a_lo_col < 0 ||
+        (epi.a_lo_col % 8) || (epi.residual != nullptr && !epi.res_fp32) ||
+        (reinterpret_cast<uintptr_t>(epi.b_lo) & 15)) {
+      set_last_error("gemm: the two-term operand split needs K-major operands, K %% 64 == 0, no split_k / accumulate / "
+                     "ksplit and no bf16 residual");
+      return -1;
+    }
+    if (epi.a_lo_col > 0 && (epi.a_lo_col < K || lda < epi.a_lo_col + K)) {
+      set_last_error("gemm: a_lo_col must be >= K with lda >= a_lo_col + K");
+      return -1;
+    }
+    p.nseg = epi.a_lo_col > 0 ? 3 : 2;
+    p.kseg = K / 64;
+    p.a_lo_col = static_cast<int>(epi.a_lo_col);
+    p.kb_total = p.nseg * p.kseg;
+  }
   int r;
-  if (!a_mn) r = make_tmap_2d(&op->tmA, A, M, K, lda, 64, 128);
+  if (!a_mn) r = make_tmap_2d(&op->tmA, A, M, split && epi.a_lo_col > 0 ? epi.a_lo_col + K : K, lda, 64, 128);
   else       r = make_tmap_2d(&op->tmA, A, K, M, lda, 64, 64);
   if (r) return r;
   if (!b_mn) r = make_tmap_2d(&op->tmB, B, N, K, ldb, 64, bn / ctas);
@@ -161,6 +179,10 @@ int gemm_op_init(GemmOp* op, int M, int N, int K, const void* A, long long lda, 
   if (r) return r;
   r = finish_output_maps(op, false, 0, 0, 0);
   if (r) return r;
+  if (split) {   // the low-order half of B travels in the (otherwise unused) residual tensor map
+    r = make_tmap_2d(&op->tmRes, epi.b_lo, N, K, ldb, 64, bn / ctas);
+    if (r) return r;
+  }
   r = check_ksplit(op, epi, bn, split_k, ctas);
   if (r) return r;
   op->bn = bn; op->split_k = split_k < 1 ? 1 : split_k; op->ctas = ctas;

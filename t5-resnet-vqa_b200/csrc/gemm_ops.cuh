@@ -21,6 +21,8 @@ struct Epilogue {
   int ksplit = 1;      // > 1: cluster split-K over `ksplit` CTAs per output tile (needs ks_ws; see gemm.cuh)
   float* ks_ws = nullptr;
   size_t ks_ws_bytes = 0;
+  const void* b_lo = nullptr;   // two-term operand split (see vqa_gemm_args.B_lo / a_lo_col)
+  long long a_lo_col = 0;
 };
 
 struct GemmOp {

@@ -39,7 +39,7 @@ template <int NC>
 __global__ void __launch_bounds__(kThreads)
 rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y_bf16,
                    float* __restrict__ y_f32, float* __restrict__ rstd, int M, float eps, float drop_p,
-                   uint32_t sid, const unsigned long long* __restrict__ rng) {
+                   uint32_t sid, const unsigned long long* __restrict__ rng, int split) {
   // parameters are only written by optimizer kernels, which are full (event) dependencies of the plan: they may be
   // read before the programmatic-dependency wait, which only guards the previous kernel's activations
   pdl_launch_dependents();
@@ -70,6 +70,16 @@ rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __n
       for (int i = 0; i < 8; ++i) o[i] = wv[c][i] * (xv[c][i] * r);
       const long long col = (c * 32 + lane) * 8;
       drop8(dc, static_cast<unsigned long long>(row) * D + col, o);
+      if (split) {
+        // two-term split for the GEMMs of the early T5 blocks: [row, 0:D) = bf16(y), [row, D:2D) = bf16(y - bf16(y))
+        __nv_bfloat16* yr = y_bf16 + static_cast<long long>(row) * (2 * D) + col;
+        float lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) lo[i] = o[i] - __bfloat162float(__float2bfloat16_rn(o[i]));
+        store_bf16x8(yr, o);
+        store_bf16x8(yr + D, lo);
+        continue;
+      }
       if (y_bf16 != nullptr) store_bf16x8(y_bf16 + static_cast<long long>(row) * D + col, o);
       if (y_f32 != nullptr) store_f32x8(y_f32 + static_cast<long long>(row) * D + col, o);
     }
@@ -315,8 +325,20 @@ int vqa_rmsnorm_fwd(void* plan, const float* x, const float* w, void* y_bf16, fl
   note_op("rmsnorm_fwd", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     DISPATCH_NC(D, (launch_pdl(rmsnorm_fwd_kernel<NC>, dim3(norm_grid(M)), dim3(kThreads), 0, s, x, w, static_cast<__nv_bfloat16*>(y_bf16), y_f32, rstd, M, eps, drop_p, sid,
-                       reinterpret_cast<const unsigned long long*>(rng))));
+                       reinterpret_cast<const unsigned long long*>(rng), 0)));
     return launch_status("rmsnorm_fwd");
+  });
+}
+
+int vqa_rmsnorm_fwd_split(void* plan, const float* x, const float* w, void* y_hilo, float* rstd, int M, int D,
+                          float eps, void* stream) {
+  if (check_d(D, "rmsnorm_fwd_split")) return -1;
+  if (y_hilo == nullptr) { set_last_error("rmsnorm_fwd_split: null output"); return -1; }
+  note_op("rmsnorm_fwd", 0.0, 0.0);
+  return submit(plan, stream, [=](cudaStream_t s) {
+    DISPATCH_NC(D, (launch_pdl(rmsnorm_fwd_kernel<NC>, dim3(norm_grid(M)), dim3(kThreads), 0, s, x, w, static_cast<__nv_bfloat16*>(y_hilo),
+                       static_cast<float*>(nullptr), rstd, M, eps, 0.f, 0u, static_cast<const unsigned long long*>(nullptr), 1)));
+    return launch_status("rmsnorm_fwd_split");
   });
 }
 

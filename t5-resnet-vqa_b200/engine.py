@@ -102,9 +102,10 @@ class _Rec:
     # ---- contractions ----
     def gemm(self, M, N, K, A, lda, a_mn, B, ldb, b_mn, out, ldo, out_fp32, bias=None, relu=0, relu_mask=None,
              ldm=0, drop_p=0.0, sid=0, rng=None, residual=None, ldr=0, res_fp32=1, alpha=1.0, accumulate=0,
-             bn=None, split_k=1, pair=None, ksplit=None):
+             bn=None, split_k=1, pair=None, ksplit=None, b_lo=None, a_lo_col=0):
+        nseg = 1 if b_lo is None else (3 if a_lo_col else 2)   # two-term operand split: the k-loop is nseg times as long
         if bn is None:
-            bn, ks = pick_tile(M, N, K, allow_ksplit=not accumulate and split_k == 1 and not pair)
+            bn, ks = pick_tile(M, N, K * nseg, allow_ksplit=not accumulate and split_k == 1 and not pair and nseg == 1)
             if ksplit is None:
                 ksplit = ks
         ksplit = int(ksplit or 1)
@@ -123,6 +124,7 @@ class _Rec:
         if ksplit > 1:
             ws = self._ks_workspace()
             a.ks_ws, a.ks_ws_bytes = ws.data_ptr(), ws.numel()
+        a.B_lo, a.a_lo_col = L.ptr(b_lo), int(a_lo_col)
         L.check(self.lib.vqa_gemm_bf16(self.plan, ctypes.byref(a), self._s()), "gemm")
 
     def linear(self, X, M, K, ldx, W, N, out, ldo, out_fp32=0, **kw):
@@ -309,7 +311,13 @@ class Engine:
         self.vision_sig = None
         self.param_sig = None
         self.shadow_fresh = False
+        self.shadow_stale = True    # the bf16 shadow must be re-cast from the fp32 master before the next forward
         self.proj_dirty = True
+        self.lo_fresh = False       # low-order halves of the split-precision T5 blocks' weights are current
+        # T5 blocks 0..n-1 run their forward GEMMs with two-term (hi + lo bf16) operands: their weights' and normalised
+        # inputs' bf16 rounding is what pulls the deepest tensors' gradient cosine below the 0.999 bar
+        # (tools/precision_probe.py).  0 = plain bf16 everywhere.
+        self.t5_split_blocks = int(os.environ.get("VQA_B200_T5_SPLIT_BLOCKS", "4"))
         self._ddp = None
         self.fused_opt = None       # weakref to a VQAFusedAdamW that updates every parameter of this engine
         self.pending_clip = None    # max_norm of a clip_grad_norm_ whose scaling the fused optimizer will apply
@@ -374,13 +382,38 @@ class Engine:
         self.device = device
         self.param_sig = None
         self.shadow_fresh = False
+        self.shadow_stale = True
+        self.proj_dirty = True
+        self.lo_fresh = False
+        # low-order bf16 halves of the split-precision blocks' GEMM weights: T5 blocks n-1 .. 0 are the LAST entries of
+        # `big` (reverse execution order), so they form one contiguous range of the flat buffers
+        blocks = list(self.model.lang_model.block)
+        nsplit = max(0, min(self.t5_split_blocks, len(blocks)))
+        self.t5_split_blocks = nsplit
+        self.lo_range = None
+        self.shadow_lo = None
+        if nsplit > 0:
+            lo0 = offs[id(blocks[nsplit - 1].layer[0].SelfAttention.q.weight)]
+            self.lo_range = (lo0, self.n_big)
+            self.shadow_lo = torch.zeros(self.n_big - lo0, dtype=torch.bfloat16, device=device)
         self.plans = {}
         self.rng = torch.zeros(2, dtype=torch.int64, device=device)
-        seed = int(os.environ.get("VQA_B200_SEED", torch.initial_seed() & 0x7FFFFFFFFFFFFFFF))
-        self.rng[0] = seed
+        self._seed_src = None
+        self._reseed()
         # vision caches are rebuilt whenever the frozen weights change
         self.vision_sig = None
         _REGISTRY[self.master.data_ptr()] = self
+
+    def _reseed(self):
+        """Dropout seed = torch's global seed (so a later torch.manual_seed is honoured), mixed with the data-parallel rank (each
+        replica draws its own masks); VQA_B200_SEED pins it.  The Philox offset restarts at 0."""
+        src = (torch.initial_seed(), getattr(self, "_seed_rank", 0))
+        if src == self._seed_src:
+            return
+        self._seed_src = src
+        seed = int(os.environ.get("VQA_B200_SEED", src[0]))
+        seed = (seed ^ (src[1] * 0x9E3779B97F4A7C15)) & 0x7FFFFFFFFFFFFFFF
+        self.rng.copy_(torch.tensor([seed, 0], dtype=torch.int64))
 
     def _params_on(self, device):
         p0 = self.model.classification_layer.weight
@@ -396,6 +429,13 @@ class Engine:
 
     def sp(self, p):
         return self.shadow.data_ptr() + 2 * self.offs[id(p)]
+
+    def lp(self, p):
+        """Low-order bf16 half (bf16(w - bf16(w))) of a split-precision weight."""
+        o = self.offs[id(p)]
+        if self.lo_range is None or not (self.lo_range[0] <= o < self.lo_range[1]):
+            raise RuntimeError("parameter is not in the split-precision range")
+        return self.shadow_lo.data_ptr() + 2 * (o - self.lo_range[0])
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -446,15 +486,38 @@ class Engine:
     def _param_signature(self):
         return tuple(p._version for p in self.params)
 
+    def _note_param_changes(self):
+        """Host-side check, made BEFORE anything of a forward is enqueued: did something other than the fused optimizer
+        (torch.optim.*, load_state_dict, an in-place edit) change the parameters since the last forward?  Then the bf16
+        shadow, the projection's conv-layout weights and the low-order halves are all stale.  (Writes through `p.data`
+        do not move the version counter; call `invalidate()` after such edits.)"""
+        sig = self._param_signature()
+        if not (self.shadow_fresh and sig == self.param_sig):
+            self.shadow_stale = True
+            self.proj_dirty = True
+            self.lo_fresh = False
+        self.param_sig = sig
+
+    def invalidate(self):
+        """Declare every derived weight cache stale (bf16 shadow, folded backbone, projection layout, low-order halves):
+        for callers that edit parameters or BatchNorm statistics through `.data`, which no version counter sees."""
+        self.shadow_fresh = False
+        self.shadow_stale = True
+        self.proj_dirty = True
+        self.lo_fresh = False
+        self.vision_sig = None
+
     def _refresh_shadow(self):
         """bf16 copies of the fp32 master weights (what the GEMMs read), on the current stream.  Only needed when
         something other than the fused optimizer changed the parameters (it writes the shadow itself)."""
-        sig = self._param_signature()
-        if not (self.shadow_fresh and sig == self.param_sig):
+        if self.shadow_stale:
             self.rec(None).cast_f32_bf16(self.master, self.shadow, self.total)
-            self.proj_dirty = True
-        self.param_sig = sig
+            self.shadow_stale = False
         self.shadow_fresh = True
+        if self.lo_range is not None and not self.lo_fresh:
+            lo0, lo1 = self.lo_range
+            self.rec(None).split_lo_bf16(self.master.data_ptr() + 4 * lo0, self.shadow_lo, lo1 - lo0)
+            self.lo_fresh = True
 
     def _refresh_projection(self):
         """The ConvTranspose2d weight re-expressed as the equivalent 3x3 conv weight (current stream)."""
@@ -488,6 +551,7 @@ class Engine:
     def note_fused_update(self, covered):
         """Called by VQAFusedAdamW after it updated `covered` of this engine's parameters in place (raw
         pointers, so no version counters moved) and wrote their bf16 shadow itself."""
+        self.lo_fresh = False
         if covered == len(self.params):
             self.proj_dirty = True
         else:
@@ -507,6 +571,7 @@ class Engine:
             self._flatten(device)
             proj = self.model._projection()
             self.proj_w = torch.empty(proj.weight.numel(), dtype=torch.bfloat16, device=device)
+            self.proj_dirty = True
             from .ddp import maybe_enable
             maybe_enable(self)
 
@@ -515,8 +580,8 @@ class Engine:
         inside forward(), after the optimizer)."""
         self._prepare_vision()
 
-    def get_plan(self, B, Lt, H, W, training, has_labels, want_features):
-        key = (B, Lt, H, W, bool(training), bool(has_labels), bool(want_features))
+    def get_plan(self, B, Lt, H, W, training, has_labels, want_features, u8_images=False):
+        key = (B, Lt, H, W, bool(training), bool(has_labels), bool(want_features), bool(u8_images))
         st = self.plans.get(key)
         if st is None:
             from .plan_builder import build_state
@@ -531,6 +596,7 @@ class Engine:
         """Copy the inputs into the plans' static buffers and replay the four forward plans: the vision branch on
         its own stream (the backbone does not wait for the optimizer), the text branch on the caller's stream."""
         main = torch.cuda.current_stream(self.device)
+        self._note_param_changes()      # sets proj_dirty before the vision-stream block below reads it
         if self.use_lanes:
             if self.s_vis is None:
                 self.s_vis = torch.cuda.Stream(device=self.device)
@@ -566,6 +632,11 @@ class Engine:
             st.labels.copy_(labels, non_blocking=True)
         self.wait_optimizer(main)
         self._refresh_shadow()
+        if st.training:
+            # one dropout stream position per TRAINING forward: its backward (and a second backward under retain_graph)
+            # regenerates the masks from the same {seed, offset}, a forward without backward does not repeat them
+            self._reseed()
+            self.rec(None).rng_advance(self.rng)
         if not self.use_lanes:
             self.run_plan(st.fwd_vis)
             self._refresh_projection()
@@ -613,8 +684,6 @@ class Engine:
         else:
             for seg in st.bwd_segments:
                 self.run_plan(seg.plan)
-        if st.training:
-            self.rec(None).rng_advance(self.rng)
 
     def __del__(self):
         try:

@@ -20,7 +20,8 @@ class GemmArgs(ctypes.Structure):
                 ("drop_p", c_f), ("drop_sid", c_u32), ("rng", c_vp),
                 ("residual", c_vp), ("ldr", c_ll), ("res_fp32", c_int), ("res_first", c_int),
                 ("alpha", c_f), ("accumulate", c_int), ("bn", c_int), ("split_k", c_int), ("cta_pair", c_int),
-                ("ksplit", c_int), ("ks_ws", c_vp), ("ks_ws_bytes", c_ll)]
+                ("ksplit", c_int), ("ks_ws", c_vp), ("ks_ws_bytes", c_ll),
+                ("B_lo", c_vp), ("a_lo_col", c_ll)]
 
 
 class ConvArgs(ctypes.Structure):
@@ -80,17 +81,21 @@ SIGNATURES = {
     "vqa_conv2d_bf16": (c_int, [_P, ctypes.POINTER(ConvArgs), _P]),
     "vqa_conv2d_wgrad_bf16": (c_int, [_P, ctypes.POINTER(ConvWgradArgs), _P]),
     "vqa_cast_f32_bf16": (c_int, [_P, _P, _P, c_ll, _P]),
+    "vqa_cast_bf16_f32": (c_int, [_P, _P, _P, c_ll, _P]),
+    "vqa_split_lo_bf16": (c_int, [_P, _P, _P, c_ll, _P]),
     "vqa_memset_zero": (c_int, [_P, _P, c_ll, _P]),
     "vqa_axpy_f32": (c_int, [_P, _P, _P, c_f, c_ll, _P]),
     "vqa_fold_conv_bn": (c_int, [_P, _P, _P, _P, _P, _P, c_f, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "vqa_convT_weight_prep": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "vqa_convT_wgrad_unprep": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "vqa_image_to_stem": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "vqa_image_u8_to_stem": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "vqa_nhwc_to_nchw_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "vqa_maxpool3x3s2": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "vqa_embedding_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_f, c_u32, _P, _P]),
     "vqa_embedding_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_f, c_u32, _P, _P]),
     "vqa_rmsnorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_f, c_f, c_u32, _P, _P]),
+    "vqa_rmsnorm_fwd_split": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_f, _P]),
     "vqa_rmsnorm_bwd": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_f, c_u32, _P, _P, c_f, c_u32,
                                 _P]),
     "vqa_t5_bias_build": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),

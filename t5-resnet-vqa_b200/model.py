@@ -35,14 +35,22 @@ class _StepFunction(torch.autograd.Function):
         eng = model._engine
         params = eng.params
         # gradient accumulation across steps: an existing .grad that aliases our flat buffer must be detached
-        # from it before the buffer is overwritten
-        p0 = params[0]
-        if p0.grad is not None and p0.grad.data_ptr() == eng.gp(p0):
-            for p in params:
-                if p.grad is not None:
-                    p.grad = p.grad.clone()
+        # from it before the buffer is overwritten (checked per parameter: any of them may be frozen or cleared)
+        views = eng.grad_views()
+        for p, v in zip(params, views):
+            g = p.grad
+            if g is not None and v is not None and (g is v or g.data_ptr() == v.data_ptr()):
+                p.grad = g.clone()
         eng.backward(st, gloss, glogp)
-        if _DIRECT_GRADS and not any(p._backward_hooks or getattr(p, "_post_accumulate_grad_hooks", None) for p in params):
+        # The fast path assigns .grad itself, so it is only taken when autograd would do exactly that for every parameter
+        # (loss.backward(), no hooks).  torch.autograd.grad(loss, some_params) / backward(inputs=some_params) set
+        # needs_input_grad only for the requested tensors and expect the gradients to be RETURNED: they take the autograd
+        # path below.  (Asking torch.autograd.grad for ALL parameters at once cannot be told apart from backward() here:
+        # set VQA_B200_DIRECT_GRADS=0 for that; INTEGRATION.md.)
+        wanted = ctx.needs_input_grad[3:]
+        direct = (_DIRECT_GRADS and all(w == p.requires_grad for w, p in zip(wanted, params))
+                  and not any(p._backward_hooks or getattr(p, "_post_accumulate_grad_hooks", None) for p in params))
+        if direct:
             # Host fast path: hand out the engine's cached gradient views directly instead of returning 180 fresh views
             # for autograd's AccumulateGrad nodes (~1 ms of host time per step, which the end-to-end step - host inputs,
             # loss read back every step - cannot hide).  Same result: `.grad` is a view of the flat gradient buffer, or,
@@ -151,10 +159,21 @@ class ResnetVQAModel(nn.Module):
         eng._ensure(dev)
         self.vision_model.eval()  # side effect of the reference forward (model/resnet_vqa_model.py:116,127)
         B, Lt = question_input_ids.shape
-        H, W = image_tensors.shape[2], image_tensors.shape[3]
+        # Two image formats: float [B,3,H,W] in 0..1 (the reference collate: cv2 -> ToTensor, dataset_utils/
+        # resnet_vqa_daquar_dataset.py:153-171) or, for the input edge, the uint8 RGB [B,H,W,3] array cv2 produced BEFORE
+        # ToTensor - a quarter of the upload, the /255 and the layout change happen in the stem-packing kernel.
+        u8 = image_tensors.dtype == torch.uint8
+        if u8:
+            if image_tensors.shape[3] != 3:
+                raise ValueError("uint8 image_tensors must be [B, H, W, 3] (RGB, as cv2 produces them)")
+            H, W = image_tensors.shape[1], image_tensors.shape[2]
+        else:
+            if image_tensors.shape[1] != 3:
+                raise ValueError("float image_tensors must be [B, 3, H, W]")
+            H, W = image_tensors.shape[2], image_tensors.shape[3]
         has_labels = annotation_ids is not None
         eng.prepare()
-        st = eng.get_plan(B, Lt, H, W, self.training, has_labels, want_features)
+        st = eng.get_plan(B, Lt, H, W, self.training, has_labels, want_features, u8)
         eng.forward(st, question_input_ids, question_attention_masks, annotation_ids, image_tensors)
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in eng.params)
         if needs_grad:

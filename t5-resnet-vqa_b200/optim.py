@@ -116,6 +116,12 @@ class VQAFusedAdamW(torch.optim.Optimizer):
                        for k, v in sd["state"].items()}
         return sd
 
+    def load_state_dict(self, state_dict):
+        """torch semantics; the flat moment buffers are re-adopted from the loaded per-parameter state at the next step()."""
+        super().load_state_dict(state_dict)
+        self._sig = None
+        self._ranges = None
+
     def _signature(self):
         """What the contiguous-range table depends on.  Gradients handed out by an Engine are cached view objects
         (engine.grad_views), recognised by identity: the id of such a view pins both the parameter's and the gradient's

@@ -40,7 +40,7 @@ class _Alloc:
         return t
 
 
-def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
+def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images=False):
     m = eng.model
     dev = eng.device
     lib = eng.lib
@@ -73,7 +73,8 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     st.ids = al(B, Lt, dtype=i64, zero=True)
     st.mask = al(B, Lt, dtype=i64, zero=True)
     st.labels = al(B, dtype=i64, zero=True)
-    st.images = al(B, 3, H, W, dtype=f32, zero=True)
+    # fp32 [B,3,H,W] in 0..1 (the reference collate's ToTensor output) or uint8 [B,H,W,3] (input edge: /255 on the device)
+    st.images = al(B, H, W, 3, dtype=torch.uint8, zero=True) if u8_images else al(B, 3, H, W, dtype=f32, zero=True)
     st.logp = al(B, A, dtype=f32, zero=True)
     st.loss = al(1, dtype=f32, zero=True)
     st.gloss = al(1, dtype=f32, zero=True)
@@ -97,7 +98,10 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     two_lanes = eng.use_lanes
     vm = m.vision_model
     stem_in = al(B, H, W + 8, 8)
-    r.image_to_stem(st.images, stem_in, B, H, W)
+    if u8_images:
+        r.image_u8_to_stem(st.images, stem_in, B, H, W)
+    else:
+        r.image_to_stem(st.images, stem_in, B, H, W)
     H1, W1 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
     c1 = al(B, H1, W1, 64)
     r.conv(B, H, W, 8, 64, 7, 2, 3, stem_in, eng.vw["stem"], c1, bias=eng.vb["stem"], relu=1, stem7=1)
@@ -177,27 +181,44 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
     pos_bias = al(nH, Lt, Lt, dtype=f32)
     r.t5_bias_build(eng.mp(relw), bucket, pos_bias, nH, Lt, cfg["num_buckets"])
     saved_t5 = []
+    nsplit = eng.t5_split_blocks
     for bi, blk in enumerate(blocks):
         att, ff = blk.layer[0], blk.layer[1]
         sa, dd = att.SelfAttention, ff.DenseReluDense
         t5_probs, t5_stats = attn_save(nH, Lt, Lt)
-        sv = dict(y1=al(M, D), rstd1=al(M, dtype=f32), qkv=al(M, 3 * inner), probs=t5_probs, stats=t5_stats,
-                  ctx=al(M, inner), hmid=al(M, D, dtype=f32), y2=al(M, D), rstd2=al(M, dtype=f32), h=al(M, dff),
-                  sid_p=new_sid(), sid_o=new_sid(), sid_h=new_sid(), sid_f=new_sid())
-        r.rmsnorm_fwd(hid[bi], eng.mp(att.layer_norm.weight), sv["y1"], None, sv["rstd1"], M, D, eps_t5, 0.0, 0, None)
+        # Blocks 0..nsplit-1 contract two-term (hi + lo bf16) operands in their forward GEMMs: the normalised inputs are
+        # written as [M, 2D] = hi | lo, the weights' low-order halves come from the engine (engine.lp), and one k-loop adds
+        # x_hi W_hi + x_lo W_hi + x_hi W_lo (o / wo: their bf16 inputs have no low half, two terms).  The backward still
+        # uses the plain bf16 operands (backward rounding does not move the gradient cosine, tools/precision_probe.py).
+        split = bi < nsplit
+        ldy = 2 * D if split else D
+        sv = dict(y1=al(M, ldy), rstd1=al(M, dtype=f32), qkv=al(M, 3 * inner), probs=t5_probs, stats=t5_stats,
+                  ctx=al(M, inner), hmid=al(M, D, dtype=f32), y2=al(M, ldy), rstd2=al(M, dtype=f32), h=al(M, dff),
+                  ldy=ldy, sid_p=new_sid(), sid_o=new_sid(), sid_h=new_sid(), sid_f=new_sid())
+
+        def norm(x, w, y, rstd):
+            if split:
+                r.rmsnorm_fwd_split(x, eng.mp(w), y, rstd, M, D, eps_t5)
+            else:
+                r.rmsnorm_fwd(x, eng.mp(w), y, None, rstd, M, D, eps_t5, 0.0, 0, None)
+
+        def lo(w, with_a):
+            return dict(b_lo=eng.lp(w), a_lo_col=D if with_a else 0) if split else {}
+        norm(hid[bi], att.layer_norm.weight, sv["y1"], sv["rstd1"])
         # fused q|k|v projection: the three [768,768] weights are adjacent in the flat bf16 shadow
-        r.linear(sv["y1"], M, D, D, eng.sp(sa.q.weight), 3 * inner, sv["qkv"], 3 * inner)
+        r.linear(sv["y1"], M, D, ldy, eng.sp(sa.q.weight), 3 * inner, sv["qkv"], 3 * inner, **lo(sa.q.weight, True))
         qkv = sv["qkv"]
         r.attn_fwd(B, nH, Lt, Lt, dkv, qkv, 3 * inner, qkv.data_ptr() + 2 * inner, 3 * inner,
                    qkv.data_ptr() + 4 * inner, 3 * inner, sv["ctx"], inner, sv["probs"], pos_bias, st.mask, 1.0,
                    p_t5, sv["sid_p"], rng, stats=sv["stats"])
         r.linear(sv["ctx"], M, inner, inner, eng.sp(sa.o.weight), D, sv["hmid"], D, out_fp32=1,
-                 drop_p=p_t5, sid=sv["sid_o"], rng=rng, residual=hid[bi], ldr=D, res_fp32=1)
-        r.rmsnorm_fwd(sv["hmid"], eng.mp(ff.layer_norm.weight), sv["y2"], None, sv["rstd2"], M, D, eps_t5, 0.0, 0, None)
-        r.linear(sv["y2"], M, D, D, eng.sp(dd.wi.weight), dff, sv["h"], dff, relu=1, drop_p=p_t5, sid=sv["sid_h"],
-                 rng=rng)
+                 drop_p=p_t5, sid=sv["sid_o"], rng=rng, residual=hid[bi], ldr=D, res_fp32=1, **lo(sa.o.weight, False))
+        norm(sv["hmid"], ff.layer_norm.weight, sv["y2"], sv["rstd2"])
+        r.linear(sv["y2"], M, D, ldy, eng.sp(dd.wi.weight), dff, sv["h"], dff, relu=1, drop_p=p_t5, sid=sv["sid_h"],
+                 rng=rng, **lo(dd.wi.weight, True))
         r.linear(sv["h"], M, dff, dff, eng.sp(dd.wo.weight), D, hid[bi + 1], D, out_fp32=1,
-                 drop_p=p_t5, sid=sv["sid_f"], rng=rng, residual=sv["hmid"], ldr=D, res_fp32=1)
+                 drop_p=p_t5, sid=sv["sid_f"], rng=rng, residual=sv["hmid"], ldr=D, res_fp32=1,
+                 **lo(dd.wo.weight, False))
         saved_t5.append(sv)
     text_f32, text_bf16, rstd_f = al(M, D, dtype=f32), al(M, D), al(M, dtype=f32)
     sid_final = new_sid()
@@ -470,7 +491,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
         side.before_write(dpre)
         r.dgrad(g_bf, M, D, D, eng.sp(dd.wo.weight), dff, dpre, dff, relu_mask=sv["h"], ldm=dff, drop_p=p_t5,
                 sid=sv["sid_h"], rng=rng)
-        side.leaf([dpre], lambda: r.wgrad(dpre, M, dff, dff, sv["y2"], D, D, eng.gp(dd.wi.weight)))
+        side.leaf([dpre], lambda: r.wgrad(dpre, M, dff, dff, sv["y2"], D, sv["ldy"], eng.gp(dd.wi.weight)))
         r.dgrad(dpre, M, dff, dff, eng.sp(dd.wi.weight), D, dsm, D)
         g_bf = next_g()
         side.before_write(g_bf)
@@ -485,7 +506,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features):
                    qkv.data_ptr() + 4 * inner, 3 * inner, sv["probs"], dsm, inner,
                    dqkv, 3 * inner, dqkv.data_ptr() + 2 * inner, 3 * inner, dqkv.data_ptr() + 4 * inner, 3 * inner,
                    dbias_pos, 1.0, p_t5, sv["sid_p"], rng, stats=sv["stats"], bias=pos_bias, key_mask=st.mask)
-        side.leaf([dqkv], lambda: r.wgrad(dqkv, M, 3 * inner, 3 * inner, sv["y1"], D, D, eng.gp(sa.q.weight)))
+        side.leaf([dqkv], lambda: r.wgrad(dqkv, M, 3 * inner, 3 * inner, sv["y1"], D, sv["ldy"], eng.gp(sa.q.weight)))
         r.dgrad(dqkv, M, 3 * inner, 3 * inner, eng.sp(sa.q.weight), D, dsm, D)
         if bi > 0:
             g_bf = next_g()

@@ -138,6 +138,16 @@ def _ddp_worker(rank, world, port, out):
         ok = False
     except RuntimeError:
         pass
+    # bf16 wire format: cast down, average the staging range, cast back; every rank ends with the SAME fp32 values, equal to
+    # the mean of the ranks' bf16-rounded gradients
+    flat2, stage = mine.clone(), torch.zeros(total, dtype=torch.bfloat16)
+    for lo, hi in ranges:
+        ddp.average_range_via(flat2, stage, lo, hi, lambda src, dst: dst.copy_(src), lambda src, dst: dst.copy_(src))
+    want2 = (sum(o.bfloat16() for o in others) / world).float()
+    ok = ok and torch.allclose(flat2, want2, atol=2e-2, rtol=1e-2) and torch.allclose(flat2, want, atol=3e-2)
+    gathered = [torch.zeros_like(flat2) for _ in range(world)]
+    dist.all_gather(gathered, flat2)
+    ok = ok and all(torch.equal(gathered[0], t) for t in gathered)
     out.put((rank, bool(ok)))
     dist.destroy_process_group()
 

@@ -93,6 +93,77 @@ def test_wgrad(C, M, N, K, bn):
 
 
 # ------------------------------------------------------------------------------------------------
+# two-term operand split (hi + lo bf16): the early T5 blocks' forward GEMMs (vqa_gemm_args.B_lo / a_lo_col)
+# ------------------------------------------------------------------------------------------------
+def _split(x):
+    hi = x.to(BF)
+    lo = (x - hi.float()).to(BF)
+    return hi, lo
+
+
+@pytest.mark.parametrize("M,N,K,bn,a_split,pair", [(2048, 2304, 768, 256, True, None), (2048, 3072, 768, 128, True, None),
+                                                   (2048, 768, 768, 64, False, None), (2048, 768, 3072, 128, False, None),
+                                                   (200, 192, 128, 64, True, None), (2048, 3072, 768, 256, True, 1)])
+def test_linear_two_term_split(C, M, N, K, bn, a_split, pair):
+    """x_hi W_hi + [x_lo W_hi +] x_hi W_lo in one k-loop: against the fp32 product of the fp32 operands the error must be far
+    below a plain bf16 GEMM's (2^-9 per operand), and it must equal the fp32 sum of the same bf16 terms."""
+    Xf, Wf = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
+    Xh, Xl = _split(Xf)
+    Wh, Wl = _split(Wf)
+    X2 = torch.cat([Xh, Xl], dim=1).contiguous() if a_split else Xh.contiguous()
+    out = torch.zeros(M, N, device="cuda")
+    C.linear(X2, M, K, X2.shape[1], Wh, N, out, N, out_fp32=1, bn=bn, b_lo=Wl, a_lo_col=K if a_split else 0, pair=pair)
+    terms = Xh.float() @ Wh.float().t() + Xh.float() @ Wl.float().t()
+    if a_split:
+        terms = terms + Xl.float() @ Wh.float().t()
+    assert rel_fro(out, terms) < 2e-5
+    exact = (Xf.double() @ Wf.double().t()).float()
+    plain = torch.zeros(M, N, device="cuda")
+    C.linear(Xh.contiguous(), M, K, K, Wh, N, plain, N, out_fp32=1, bn=bn)
+    err_split, err_plain = rel_fro(out, exact), rel_fro(plain, exact)
+    assert err_plain > 1e-3                                   # the plain bf16 product really is at bf16 precision
+    assert err_split < (3e-5 if a_split else 0.75 * err_plain)   # both operands split: ~2^-16; weights only: x's rounding remains
+
+
+def test_linear_two_term_split_epilogues(C):
+    """The split k-loop under the epilogues the T5 blocks use: bf16 out + ReLU + dropout (wi), fp32 out + fp32 residual (o/wo)."""
+    M, N, K = 2048, 3072, 768
+    Xf, Wf = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5)
+    Xh, Xl = _split(Xf)
+    Wh, Wl = _split(Wf)
+    X2 = torch.cat([Xh, Xl], dim=1).contiguous()
+    out = torch.zeros(M, N, dtype=BF, device="cuda")
+    C.linear(X2, M, K, 2 * K, Wh, N, out, N, relu=1, b_lo=Wl, a_lo_col=K, bn=128)
+    ref = F.relu((Xh.float() + Xl.float()) @ (Wh.float() + Wl.float()).t())
+    assert rel_fro(out, ref) < 4e-3
+    R = rnd(M, 768, seed=3)
+    W2f = rnd(768, N, seed=4, scale=N ** -0.5)
+    W2h, W2l = _split(W2f)
+    o2 = torch.zeros(M, 768, device="cuda")
+    C.linear(out, M, N, N, W2h, 768, o2, 768, out_fp32=1, residual=R, ldr=768, res_fp32=1, b_lo=W2l, bn=64)
+    ref2 = out.float() @ (W2h.float() + W2l.float()).t() + R
+    assert rel_fro(o2, ref2) < 2e-5
+
+
+def test_rmsnorm_split_and_weight_lo(C):
+    M, D = 2048, 768
+    x, w = rnd(M, D, seed=1, scale=3.0), 0.75 + 0.5 * torch.rand(D, device="cuda")
+    y2, rstd = torch.zeros(M, 2 * D, dtype=BF, device="cuda"), torch.zeros(M, device="cuda")
+    C.rmsnorm_fwd_split(x, w, y2, rstd, M, D, 1e-6)
+    ref = w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6))
+    hi, lo = y2[:, :D].float(), y2[:, D:].float()
+    assert rel_fro(hi, ref) < 4e-3
+    assert rel_fro(hi + lo, ref) < 3e-5
+    y1 = torch.zeros(M, D, dtype=BF, device="cuda")
+    C.rmsnorm_fwd(x, w, y1, None, rstd, M, D, 1e-6, 0.0, 0, None)
+    assert torch.equal(y1, y2[:, :D])
+    W = rnd(3000, 769, seed=5)
+    Wl = torch.zeros_like(W, dtype=BF)
+    C.split_lo_bf16(W, Wl, W.numel())
+    assert torch.equal(Wl, (W - W.to(BF).float()).to(BF))
+
+
+# ------------------------------------------------------------------------------------------------
 # cluster split-K: a thread-block cluster per output tile, k-slices per CTA, partial sums exchanged through a
 # workspace, every CTA finishing (bias / ReLU / dropout / residual / store) a column range of the tile
 # ------------------------------------------------------------------------------------------------

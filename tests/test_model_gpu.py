@@ -15,14 +15,11 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 LOGP_REL, LOSS_REL, TOP1, GRAD_COS = 2e-2, 1e-3, 0.99, 0.999
-# What bf16 operands allow on these random-init weights (DESIGN.md "Parity", tools/noise_probe*.py): rounding
-# ONLY the weights to bf16 and computing everything else in fp32 on the CPU oracle already flips 1 of 64 top-1
-# answers (98.4 %) and drops the deepest T5 tensors' gradient cosine to 0.9982 (ReLU kinks under forward
-# perturbation).  So the two statistical bars are asserted in the form bf16 can meet, and the measured values are
-# written to gpurun_out/parity.jsonl next to the north-star numbers:
-#   top-1: 100 % on samples whose reference margin exceeds the log-prob tolerance, >= TOP1_FLOOR overall
-#   gradient cosine: >= GRAD_COS on >= 90 % of the tensors, median >= 0.9998, every tensor >= GRAD_COS_FLOOR
-TOP1_FLOOR, GRAD_COS_FLOOR = 0.95, 0.998
+# All four bars are asserted as stated.  The gradient-cosine bar holds on EVERY tensor because the first T5 blocks run
+# their forward GEMMs with two-term (hi + lo bf16) operands (engine.t5_split_blocks, tools/precision_probe.py: with plain
+# bf16 operands the deepest tensors - block 0/1 wi, q, k, layer_norm - sit at 0.9982..0.9989 from ReLU kinks and softmax
+# rows moved by the forward rounding).  Top-1 is resolved over 512 samples (one flip = 0.2 %); on the small golden batches
+# every sample whose reference margin exceeds the log-prob tolerance must agree.
 
 
 def build(pkg, vision, sd, device, train=False):
@@ -48,16 +45,17 @@ def report(name, **kv):
         f.write(json.dumps(dict(name=name, **kv)) + "\n")
 
 
-def check_outputs(logp, loss, ref_logp, ref_loss, name="", strict_top1=False):
+def check_outputs(logp, loss, ref_logp, ref_loss, name=""):
     logp, loss = logp.detach().float().cpu(), float(loss.detach())
     rel = float((logp - ref_logp).norm() / ref_logp.norm())
     # element-wise too: log-probs are O(5); bound the worst element relative to its magnitude
     worst = float(((logp - ref_logp).abs() / ref_logp.abs().clamp_min(1.0)).max())
     lrel = abs(loss - float(ref_loss)) / abs(float(ref_loss))
     same = logp.argmax(1) == ref_logp.argmax(1)
-    # a random-init model has near-flat answers: a top-1 flip only counts when the reference's own margin
-    # between its best two answers is larger than the log-prob tolerance (otherwise the reference itself
-    # would flip under an fp32 re-ordering); the >= 99 % bar is enforced on the 64-sample case below
+    # a random-init model has near-flat answers: on a batch too small to resolve 99 % a top-1 flip only counts when the
+    # reference's own margin between its best two answers is larger than the log-prob tolerance (otherwise the
+    # reference itself would flip under an fp32 re-ordering); from 64 samples on the >= 99 % bar is enforced as stated
+    # on batches of >= 100 samples, and test_top1_agreement_512 resolves it properly
     top2 = ref_logp.topk(2, dim=1).values
     decisive = (top2[:, 0] - top2[:, 1]) > LOGP_REL * top2[:, 0].abs()
     agree = float(same.float().mean())
@@ -67,11 +65,12 @@ def check_outputs(logp, loss, ref_logp, ref_loss, name="", strict_top1=False):
     assert worst <= LOGP_REL, "worst log-prob element rel err %.3e" % worst
     assert lrel <= LOSS_REL, "loss rel err %.3e" % lrel
     assert bool(same[decisive].all())
-    if strict_top1:
-        assert agree >= TOP1_FLOOR, agree
+    if logp.shape[0] >= 100:
+        assert agree >= TOP1, agree
+    return agree
 
 
-@pytest.mark.parametrize("case", ["r34_b4", "r50_b2_masked", "r18_b2_256_l16"])
+@pytest.mark.parametrize("case", ["r34_b4", "r50_b2_masked", "r18_b2_256_l16", "r50_b64", "r50_b64_masked"])
 def test_parity_with_reference_golden_and_oracle(pkg, cuda, case):
     from oracle import vqa_oracle as O
     gold = torch.load(os.path.join(GOLD, case + ".pt"), weights_only=False)
@@ -110,8 +109,8 @@ def test_parity_with_reference_golden_and_oracle(pkg, cuda, case):
     assert not bad, bad[:10]
     frac = sum(1 for c_, _ in cos if c_ >= GRAD_COS) / len(cos)
     report(case + ":grad_cosine_summary", frac_ge_0p999=frac, worst=cos[0][0], median=cos[len(cos) // 2][0])
-    assert cos[0][0] >= GRAD_COS_FLOOR, cos[:5]
-    assert frac >= 0.90 and cos[len(cos) // 2][0] >= 0.9998, (frac, cos[len(cos) // 2])
+    assert cos[0][0] >= GRAD_COS, cos[:5]            # the north-star bar, on every tensor
+    assert cos[len(cos) // 2][0] >= 0.9998, cos[len(cos) // 2]
 
 
 def test_generate_answers_features_and_eval_determinism(pkg, cuda):
@@ -134,18 +133,32 @@ def test_generate_answers_features_and_eval_determinism(pkg, cuda):
     check_outputs(logp2, loss2, o_logp.detach(), o_loss.detach(), "generate_answers")
 
 
-def test_top1_agreement_batch64(pkg, cuda):
-    """Top-1 answer agreement on BASELINE's per-GPU batch (64 samples) against the fp32 oracle (see the note on
-    TOP1_FLOOR above: 100 % is required wherever the reference's own margin is decisive)."""
+def test_top1_agreement_512(pkg, cuda):
+    """Top-1 answer agreement >= 99 % (north_star) on BASELINE configs[1] (ResNet50, 64 per batch, 224x224, 32 tokens), resolved
+    over 512 samples = 8 batches.  The fp32 oracle runs on the GPU here (torch fp32, TF32 off: the reference's own eager
+    path) so that 512 ResNet50 samples take seconds; the first batch is cross-checked against the CPU oracle."""
     from oracle import vqa_oracle as O
-    sd = O.random_state_dict("resnet34", 170, seed=0)
-    batch = O.synthetic_batch(64, 32, 224, 224, 170, seed=5)
-    m = build(pkg, "resnet34", sd, cuda)
-    with torch.no_grad():
-        logp, loss = run(m, batch, cuda)
-        o_logp, o_loss = O.forward(sd, "resnet34", batch["question_input_ids"], batch["question_attention_masks"],
-                                   batch["annotation_ids"], batch["image_tensors"])
-    check_outputs(logp, loss, o_logp, o_loss, "top1_b64", strict_top1=True)
+    sd = O.random_state_dict("resnet50", 170, seed=0)
+    sd_gpu = {k: v.to(cuda) for k, v in sd.items()}
+    m = build(pkg, "resnet50", sd, cuda)
+    same, total, rels = 0, 0, []
+    for chunk in range(8):
+        batch = O.synthetic_batch(64, 32, 224, 224, 170, seed=100 + chunk, masked_tail=10 if chunk % 2 else 0)
+        kw = {k: v.to(cuda) for k, v in batch.items()}
+        with torch.no_grad():
+            logp, loss = run(m, batch, cuda)
+            o_logp, o_loss = O.forward(sd_gpu, "resnet50", kw["question_input_ids"], kw["question_attention_masks"],
+                                       kw["annotation_ids"], kw["image_tensors"])
+            if chunk == 0:
+                c_logp, _ = O.forward(sd, "resnet50", batch["question_input_ids"], batch["question_attention_masks"],
+                                      batch["annotation_ids"], batch["image_tensors"])
+                assert float((o_logp.cpu() - c_logp).abs().max()) < 1e-4
+        o_logp = o_logp.cpu()
+        check_outputs(logp, loss, o_logp, o_loss.cpu(), "top1_512:%d" % chunk)
+        same += int((logp.cpu().argmax(1) == o_logp.argmax(1)).sum())
+        total += 64
+    report("top1_512", agree=same / total, same=same, n=total)
+    assert same / total >= TOP1, (same, total)
 
 
 def test_train_mode_dropout_and_fused_optimizer_step(pkg, cuda):
@@ -298,3 +311,107 @@ def test_gradient_accumulation_and_hooks_keep_autograd_semantics(pkg, cuda):
     h.remove()
     assert "g" in seen and torch.allclose(seen["g"], g1["classification_layer.weight"], rtol=1e-5, atol=1e-7)
     assert torch.allclose(w.grad, g1["classification_layer.weight"], rtol=1e-5, atol=1e-7)
+
+
+def test_weight_caches_follow_non_fused_updates_after_idle_forwards(pkg, cuda):
+    """torch.optim.AdamW (the reference config's default "type") and load_state_dict change the parameters behind the engine's
+    back; after two forwards without any change (validation epoch) the next update must still reach the bf16 shadow, the
+    projection's conv-layout weights and the split-precision low halves: same result as a fresh model on the same weights."""
+    from oracle import vqa_oracle as O
+    sd = O.random_state_dict("resnet18", 170, seed=0)
+    batch = O.synthetic_batch(2, 16, 64, 64, 170, seed=1)
+    m = build(pkg, "resnet18", sd, cuda)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-2, weight_decay=0.1, amsgrad=True)
+    _, loss = run(m, batch, cuda)
+    loss.backward()
+    with torch.no_grad():
+        a, _ = run(m, batch, cuda)
+        b, _ = run(m, batch, cuda)
+    assert torch.equal(a, b)
+    opt.step()                                   # in-place update of every trainable tensor, projection included
+    with torch.no_grad():
+        after, _ = run(m, batch, cuda)
+    assert not torch.equal(after, a)
+    fresh = build(pkg, "resnet18", {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}, cuda)
+    with torch.no_grad():
+        want, _ = run(fresh, batch, cuda)
+    assert torch.equal(after, want)
+    # load_state_dict after idle forwards, and an edit through .data followed by invalidate()
+    with torch.no_grad():
+        run(m, batch, cuda)
+    m.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        back, _ = run(m, batch, cuda)
+    assert torch.equal(back, a)
+    m.upscale_layer.weight.data.mul_(1.5)
+    m._engine.invalidate()
+    with torch.no_grad():
+        scaled, _ = run(m, batch, cuda)
+    assert not torch.equal(scaled, a)
+
+
+def test_dropout_stream_and_fused_optimizer_state_reload(pkg, cuda):
+    """Train mode: every forward draws new masks (also without a backward in between), a second backward on the same forward
+    (retain_graph) regenerates the forward's masks, a new torch.manual_seed restarts the stream; VQAFusedAdamW.load_state_dict
+    after a step adopts the loaded moments."""
+    from oracle import vqa_oracle as O
+    sd = O.random_state_dict("resnet18", 170, seed=0)
+    batch = O.synthetic_batch(2, 16, 64, 64, 170, seed=1)
+    torch.manual_seed(11)
+    m = build(pkg, "resnet18", sd, cuda, train=True)
+    with torch.no_grad():
+        l1, _ = run(m, batch, cuda)
+        l2, _ = run(m, batch, cuda)
+    assert not torch.equal(l1, l2)
+    _, loss = run(m, batch, cuda)
+    loss.backward(retain_graph=True)
+    g1 = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+    loss.backward()
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            assert torch.allclose(p.grad, 2 * g1[k], rtol=1e-5, atol=1e-7), k
+    assert int(m._engine.rng[0]) == 11 and int(m._engine.rng[1]) == 3      # three training forwards so far
+    torch.manual_seed(12)                                                    # a later re-seed is honoured
+    with torch.no_grad():
+        run(m, batch, cuda)
+    assert int(m._engine.rng[0]) == 12 and int(m._engine.rng[1]) == 1
+    # optimizer state reload after a step
+    opt = torch.optim.VQAFusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.1, amsgrad=True)
+    opt.step()
+    import copy
+    saved = copy.deepcopy(opt.state_dict())
+    opt.step()
+    opt.load_state_dict(saved)
+    opt.step()
+    w = m.classification_layer.weight
+    assert float(opt.state[w]["step"]) == 2.0          # 1 (loaded) + 1, not 3: the loaded state was adopted
+
+
+def test_uint8_nhwc_images_equal_the_float_path(pkg, cuda):
+    """Input edge: uint8 RGB [B,H,W,3] images (cv2's output before ToTensor) give bit-identical log-probs,
+    loss and gradients to the reference format float [B,3,H,W] = uint8 / 255, from device or pinned host memory."""
+    from oracle import vqa_oracle as O
+    sd = O.random_state_dict("resnet34", 170, seed=0)
+    batch = O.synthetic_batch(4, 32, 224, 224, 170, seed=1)
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (4, 224, 224, 3), dtype=torch.uint8, generator=g)
+    batch["image_tensors"] = u8.permute(0, 3, 1, 2).float().div(255.0).contiguous()      # transforms.ToTensor()
+    m = build(pkg, "resnet34", sd, cuda)
+    logp_f, loss_f = run(m, batch, cuda)
+    loss_f.backward()
+    gf = m.upscale_layer.weight.grad.detach().clone()
+    o_logp, o_loss, _ = O.forward_backward(sd, "resnet34", batch)
+    check_outputs(logp_f, loss_f, o_logp, o_loss, "uint8_edge:float")
+    for p in m.parameters():
+        p.grad = None
+    for images in (u8.to(cuda), u8.pin_memory()):
+        b2 = dict(batch, image_tensors=images)
+        kw = {k: (v.to(cuda) if k != "image_tensors" else v) for k, v in b2.items()}
+        logp_u, loss_u = m(question_input_ids=kw["question_input_ids"], question_attention_masks=kw["question_attention_masks"],
+                           annotation_ids=kw["annotation_ids"], image_tensors=kw["image_tensors"])
+        assert torch.equal(logp_u, logp_f) and torch.equal(loss_u, loss_f)
+    loss_u.backward()
+    assert torch.equal(m.upscale_layer.weight.grad, gf)
+    with pytest.raises(ValueError):
+        m(question_input_ids=kw["question_input_ids"], question_attention_masks=kw["question_attention_masks"],
+          annotation_ids=kw["annotation_ids"], image_tensors=u8.permute(0, 3, 1, 2).contiguous().to(cuda))

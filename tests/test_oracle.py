@@ -8,7 +8,7 @@ import torch
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("case", ["r34_b4", "r18_b2_256_l16", "r50_b2_masked"])
+@pytest.mark.parametrize("case", ["r34_b4", "r18_b2_256_l16", "r50_b2_masked", "r50_b64"])
 def test_oracle_matches_reference_golden(case):
     from oracle import vqa_oracle as O
     gold = torch.load(os.path.join(GOLD, case + ".pt"), weights_only=False)
