@@ -318,6 +318,9 @@ class Engine:
         # inputs' bf16 rounding is what pulls the deepest tensors' gradient cosine below the 0.999 bar
         # (tools/precision_probe.py).  0 = plain bf16 everywhere.
         self.t5_split_blocks = int(os.environ.get("VQA_B200_T5_SPLIT_BLOCKS", "4"))
+        # the SGA stack's and the classifier's forward GEMMs add the weights' low-order term (x W_hi + x W_lo): the log-probs
+        # of the flat random-init classifier then agree with fp32 closely enough for >= 99 % top-1 agreement with margin
+        self.split_head = _env_flag("VQA_B200_SPLIT_HEAD", True)
         self._ddp = None
         self.fused_opt = None       # weakref to a VQAFusedAdamW that updates every parameter of this engine
         self.pending_clip = None    # max_norm of a clip_grad_norm_ whose scaling the fused optimizer will apply
@@ -385,17 +388,17 @@ class Engine:
         self.shadow_stale = True
         self.proj_dirty = True
         self.lo_fresh = False
-        # low-order bf16 halves of the split-precision blocks' GEMM weights: T5 blocks n-1 .. 0 are the LAST entries of
-        # `big` (reverse execution order), so they form one contiguous range of the flat buffers
+        # low-order bf16 halves of the split-precision GEMM weights, at the same offsets as the bf16 shadow.  Two contiguous
+        # ranges of `big`: classifier + SGA stack (its head), and T5 blocks n-1 .. 0 (its tail: reverse execution order)
         blocks = list(self.model.lang_model.block)
         nsplit = max(0, min(self.t5_split_blocks, len(blocks)))
         self.t5_split_blocks = nsplit
-        self.lo_range = None
-        self.shadow_lo = None
+        self.lo_ranges = []
+        if self.split_head:
+            self.lo_ranges.append((0, offs[id(self.model._projection().weight)]))
         if nsplit > 0:
-            lo0 = offs[id(blocks[nsplit - 1].layer[0].SelfAttention.q.weight)]
-            self.lo_range = (lo0, self.n_big)
-            self.shadow_lo = torch.zeros(self.n_big - lo0, dtype=torch.bfloat16, device=device)
+            self.lo_ranges.append((offs[id(blocks[nsplit - 1].layer[0].SelfAttention.q.weight)], self.n_big))
+        self.shadow_lo = torch.zeros(self.n_big, dtype=torch.bfloat16, device=device) if self.lo_ranges else None
         self.plans = {}
         self.rng = torch.zeros(2, dtype=torch.int64, device=device)
         self._seed_src = None
@@ -433,9 +436,9 @@ class Engine:
     def lp(self, p):
         """Low-order bf16 half (bf16(w - bf16(w))) of a split-precision weight."""
         o = self.offs[id(p)]
-        if self.lo_range is None or not (self.lo_range[0] <= o < self.lo_range[1]):
-            raise RuntimeError("parameter is not in the split-precision range")
-        return self.shadow_lo.data_ptr() + 2 * (o - self.lo_range[0])
+        if not any(lo0 <= o < lo1 for lo0, lo1 in self.lo_ranges):
+            raise RuntimeError("parameter is not in a split-precision range")
+        return self.shadow_lo.data_ptr() + 2 * o
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -472,15 +475,26 @@ class Engine:
         if sig == self.vision_sig:
             return
         r = self.rec(None)
-        self.vw, self.vb = {}, {}
+        # Re-folded IN PLACE: the recorded plans hold raw pointers to these tensors.  Only a backbone of another shape (or
+        # device) gets new buffers, and then every recorded plan is dropped.
+        if not hasattr(self, "vw"):
+            self.vw, self.vb = {}, {}
+        realloc = False
         for name, c, b in convs:
             O, I, R, S = c.weight.shape
             Sp, Ip = (8, 8) if name == "stem" else (S, I)
-            w = torch.empty(O * R * Sp * Ip, dtype=torch.bfloat16, device=self.device)
-            bias = torch.empty(O, dtype=torch.float32, device=self.device)
+            w, bias = self.vw.get(name), self.vb.get(name)
+            if w is None or w.numel() != O * R * Sp * Ip or w.device != self.device:
+                w = torch.empty(O * R * Sp * Ip, dtype=torch.bfloat16, device=self.device)
+                bias = torch.empty(O, dtype=torch.float32, device=self.device)
+                self.vw[name], self.vb[name] = w, bias
+                realloc = True
             r.fold_conv_bn(c.weight.detach().float().contiguous(), b.weight.detach(), b.bias.detach(),
                            b.running_mean, b.running_var, float(b.eps), w, bias, O, I, R, S, Sp, Ip)
-            self.vw[name], self.vb[name] = w, bias
+        if realloc and self.plans:
+            for st in self.plans.values():
+                st.destroy(self.lib)
+            self.plans = {}
         self.vision_sig = sig
 
     def _param_signature(self):
@@ -514,9 +528,9 @@ class Engine:
             self.rec(None).cast_f32_bf16(self.master, self.shadow, self.total)
             self.shadow_stale = False
         self.shadow_fresh = True
-        if self.lo_range is not None and not self.lo_fresh:
-            lo0, lo1 = self.lo_range
-            self.rec(None).split_lo_bf16(self.master.data_ptr() + 4 * lo0, self.shadow_lo, lo1 - lo0)
+        if self.lo_ranges and not self.lo_fresh:
+            for lo0, lo1 in self.lo_ranges:
+                self.rec(None).split_lo_bf16(self.master.data_ptr() + 4 * lo0, self.shadow_lo.data_ptr() + 2 * lo0, lo1 - lo0)
             self.lo_fresh = True
 
     def _refresh_projection(self):

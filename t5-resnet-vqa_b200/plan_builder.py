@@ -232,6 +232,9 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
     scale = 1.0 / math.sqrt(hd)
     sgas = list(m.sga_modules)
     saved_sga = []
+
+    def hlo(w):   # low-order weight term of the SGA / classifier forward GEMMs (engine.split_head)
+        return dict(b_lo=eng.lp(w)) if eng.split_head else {}
     y_bf16, Ly = y0, Ty
     out_f32 = None
     for li, sga in enumerate(sgas):
@@ -250,34 +253,35 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
                   sid_r3=new_sid())
         # mhatt1(v=x, k=x, q=x): fused v|k|q projection
         r.linear(text_bf16, M, D, D, eng.sp(m1.linear_v.weight), 3 * D, sv["qkv1"], 3 * D,
-                 bias=eng.mp(m1.linear_v.bias))
+                 bias=eng.mp(m1.linear_v.bias), **hlo(m1.linear_v.weight))
         q1 = sv["qkv1"]
         r.attn_fwd(B, Hs, Lt, Lt, hd, q1.data_ptr() + 4 * D, 3 * D, q1.data_ptr() + 2 * D, 3 * D, q1, 3 * D,
                    sv["ctx1"], D, sv["probs1"], None, None, scale, p_sga, sv["sid_p1"], rng, stats=sv["stats1"])
         r.linear(sv["ctx1"], M, D, D, eng.sp(m1.linear_merge.weight), D, sv["z1"], D, out_fp32=1,
                  bias=eng.mp(m1.linear_merge.bias), drop_p=p_sga, sid=sv["sid_r1"], rng=rng, residual=text_f32,
-                 ldr=D, res_fp32=1)
+                 ldr=D, res_fp32=1, **hlo(m1.linear_merge.weight))
         r.layernorm_fwd(sv["z1"], eng.mp(sga.norm1.norm.weight), eng.mp(sga.norm1.norm.bias), sv["x1b"], sv["x1f"],
                         sv["mean1"], sv["rstd1"], M, D, float(sga.norm1.norm.eps))
         # mhatt2(v=y, k=y, q=x1)
-        r.linear(sv["x1b"], M, D, D, eng.sp(m2.linear_q.weight), D, sv["q2"], D, bias=eng.mp(m2.linear_q.bias))
+        r.linear(sv["x1b"], M, D, D, eng.sp(m2.linear_q.weight), D, sv["q2"], D, bias=eng.mp(m2.linear_q.bias),
+                 **hlo(m2.linear_q.weight))
         if li == 0:
             r = eng.rec(st.fwd_fuse, st.ks_store)    # the vision tokens (vision stream) are needed from here on
         r.linear(y_bf16, Myl, D, D, eng.sp(m2.linear_v.weight), 2 * D, sv["vk2"], 2 * D,
-                 bias=eng.mp(m2.linear_v.bias))
+                 bias=eng.mp(m2.linear_v.bias), **hlo(m2.linear_v.weight))
         vk = sv["vk2"]
         r.attn_fwd(B, Hs, Lt, Ly, hd, sv["q2"], D, vk.data_ptr() + 2 * D, 2 * D, vk, 2 * D, sv["ctx2"], D,
                    sv["probs2"], None, None, scale, p_sga, sv["sid_p2"], rng, stats=sv["stats2"])
         r.linear(sv["ctx2"], M, D, D, eng.sp(m2.linear_merge.weight), D, sv["z2"], D, out_fp32=1,
                  bias=eng.mp(m2.linear_merge.bias), drop_p=p_sga, sid=sv["sid_r2"], rng=rng, residual=sv["x1f"],
-                 ldr=D, res_fp32=1)
+                 ldr=D, res_fp32=1, **hlo(m2.linear_merge.weight))
         r.layernorm_fwd(sv["z2"], eng.mp(sga.norm2.norm.weight), eng.mp(sga.norm2.norm.bias), sv["x2b"], sv["x2f"],
                         sv["mean2"], sv["rstd2"], M, D, float(sga.norm2.norm.eps))
         # FFN
         r.linear(sv["x2b"], M, D, D, eng.sp(mlp.fc1.weight), D, sv["hm"], D, bias=eng.mp(mlp.fc1.bias), relu=1,
-                 drop_p=p_sga, sid=sv["sid_h"], rng=rng)
+                 drop_p=p_sga, sid=sv["sid_h"], rng=rng, **hlo(mlp.fc1.weight))
         r.linear(sv["hm"], M, D, D, eng.sp(mlp.fc2.weight), D, sv["z3"], D, out_fp32=1, bias=eng.mp(mlp.fc2.bias),
-                 drop_p=p_sga, sid=sv["sid_r3"], rng=rng, residual=sv["x2f"], ldr=D, res_fp32=1)
+                 drop_p=p_sga, sid=sv["sid_r3"], rng=rng, residual=sv["x2f"], ldr=D, res_fp32=1, **hlo(mlp.fc2.weight))
         r.layernorm_fwd(sv["z3"], eng.mp(sga.norm3.norm.weight), eng.mp(sga.norm3.norm.bias), sv["ob"], sv["of"],
                         sv["mean3"], sv["rstd3"], M, D, float(sga.norm3.norm.eps))
         saved_sga.append(sv)
@@ -291,7 +295,8 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
     pool_w, pooled_b = al(B, Lt, dtype=f32), al(B, D)
     r.pooler_fwd(out_f32, eng.mp(pl.weight), eng.mp(pl.bias), pool_w, None, pooled_b, B, Lt, D)
     logits = al(B, Apad, dtype=f32, zero=True)
-    r.linear(pooled_b, B, D, D, eng.sp(cls.weight), A, logits, Apad, out_fp32=1, bias=eng.mp(cls.bias), bn=64)
+    r.linear(pooled_b, B, D, D, eng.sp(cls.weight), A, logits, Apad, out_fp32=1, bias=eng.mp(cls.bias), bn=64,
+             **hlo(cls.weight))
     r.logsoftmax_nll_fwd(logits, Apad, st.labels if has_labels else None, st.logp,
                          st.loss if has_labels else None, B, A)
     st.n_fwd_launches = sum(lib.vqa_plan_size(p) for p in st.fwd_plans)

@@ -125,8 +125,8 @@ def test_trainer_drives_three_steps(pkg, cuda):
         results[opt_type] = (losses, {k: p.detach().float().cpu().clone() for k, p in model.named_parameters()})
         assert all(g is None for g in (p.grad for p in model.vision_model.parameters()))
     la, lb = results["AdamW"][0], results["VQAFusedAdamW"][0]
-    assert la[0] == lb[0]                                     # step 0 runs at lr = 0 from identical weights
-    assert la[1] != la[0]                                     # ... and step 1 has moved them
+    assert la[0] == lb[0] and la[1] == la[0] and lb[1] == lb[0]    # the warm-up's step 0 runs at lr = 0: nothing moves yet
+    assert la[2] != la[0] and lb[2] != lb[0]                       # step 1 (lr > 0) has moved the weights
     assert max(abs(a - b) for a, b in zip(la, lb)) < 2e-3 * abs(la[0])
     pa, pb = results["AdamW"][1], results["VQAFusedAdamW"][1]
     # same update, tensor by tensor (element-exact equality of the kernel with torch.optim.AdamW on the SAME gradients is
