@@ -1,4 +1,4 @@
-// Flash-style tcgen05 attention for short sequences (Lq, Lk <= 32): T5 self-attention (hf:308-334: no 1/sqrt(d),
+// Flash-style tcgen05 attention for short sequences (Lq, Lk <= 64): T5 self-attention (hf:308-334: no 1/sqrt(d),
 // relative-position bias, key-padding mask) and the SGA self / guided attention over the 32 text tokens
 // (model/multi_head_vision_text_attn.py:73-86: 1/sqrt(96) scale), forward and backward.
 //
@@ -13,7 +13,10 @@
 // recomputes S = Q K^T and P with one more MMA, then  dP = dO V^T,  dS = P (dP - rowsum(P dP)),
 // dV = Pd^T dO,  dQ = scale dS K,  dK = scale dS^T Q  as three more MMAs over the same shared-memory tiles
 // (transposes are free: the MN-major descriptor bit).
-// Operands arrive by TMA (2-D boxes of 64 columns x 32 rows per pair and 64-column chunk, 128B swizzle).
+// Operands arrive by TMA (2-D boxes of 64 columns x SLOT rows per pair and 64-column chunk, 128B swizzle).
+// SLOT = 32 (four pairs per CTA) when Lq, Lk <= 32; SLOT = 64 (two pairs per CTA, diagonal blocks of 64 x 64: the guided
+// attention over the 49 / 64 vision tokens, model/multi_head_vision_text_attn.py:147-149 with y = vision) otherwise: a thread
+// then walks its row's scores in two 32-column halves.
 #include "../../include/vqa_b200.h"
 #include "common.cuh"
 #include "ptx.cuh"
@@ -25,10 +28,11 @@ using namespace vqa;
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int kPairs = 4;                 // (batch, head) pairs per CTA
-constexpr int kSlot = 32;                 // query rows / keys per pair
 constexpr int kTile = 128 * 128;          // bytes of one 64-column chunk: 128 rows x 128 B
-constexpr int kBox = kSlot * 128;         // bytes one TMA box delivers (32 rows x 64 bf16)
+// SLOT = query rows / keys per (batch, head) pair inside the 128-row tile (32 or 64); 128 / SLOT pairs per CTA;
+// one TMA box delivers SLOT rows x 64 bf16 = SLOT * 128 bytes
+template <int SLOT> struct MaskT { using type = uint32_t; };
+template <> struct MaskT<64> { using type = unsigned long long; };
 constexpr float kMaskedScore = -3.4028234663852886e38f;  // torch.finfo(float32).min (hf additive mask)
 
 // phase stamps are compiled only into the diagnostic library (build.py --debug), as in gemm_kernel.cuh
@@ -53,9 +57,10 @@ __device__ __forceinline__ uint32_t philox_u16(const Philox8& r, uint32_t e) {
 
 // Bit j = probability j of the row starting at flat index `base` survives dropout.  Same stream convention as the
 // SIMT kernel (attention.cu: philox group = flat index / 8, 16-bit lane = flat index % 8).
-__device__ __forceinline__ uint32_t keep_bits(const DropCtx& dc, unsigned long long base, int Lk) {
-  if (!dc.on) return 0xFFFFFFFFu;
-  uint32_t keep = 0;
+template <typename M>
+__device__ __forceinline__ M keep_bits(const DropCtx& dc, unsigned long long base, int Lk) {
+  if (!dc.on) return ~static_cast<M>(0);
+  M keep = 0;
   if ((Lk & 7) == 0) {
 #pragma unroll 1
     for (int g = 0; g * 8 < Lk; ++g) {   // rolled on purpose: run-once straight-line code is instruction-fetch bound
@@ -63,7 +68,7 @@ __device__ __forceinline__ uint32_t keep_bits(const DropCtx& dc, unsigned long l
       uint32_t m = 0;
 #pragma unroll
       for (int e = 0; e < 8; ++e) m |= (r.u16(e) >= dc.thresh ? 1u : 0u) << e;
-      keep |= m << (g * 8);
+      keep |= static_cast<M>(m) << (g * 8);
     }
   } else {
     unsigned long long cur = ~0ull;
@@ -73,26 +78,10 @@ __device__ __forceinline__ uint32_t keep_bits(const DropCtx& dc, unsigned long l
     for (int j = 0; j < Lk; ++j) {
       const unsigned long long idx = base + j;
       if ((idx >> 3) != cur) { cur = idx >> 3; r = philox8(dc.seed, dc.offset, dc.sid, cur); }
-      keep |= (philox_u16(r, static_cast<uint32_t>(idx & 7)) >= dc.thresh ? 1u : 0u) << j;
+      keep |= static_cast<M>(philox_u16(r, static_cast<uint32_t>(idx & 7)) >= dc.thresh ? 1u : 0u) << j;
     }
   }
   return keep;
-}
-
-// Write 32 fp32 values as bf16 into row `row` of a block-diagonal [128 x 128] K-major tile (two 64-column chunks of
-// 128 rows x 128 B, 128B swizzle): pair `g` owns columns 32g .. 32g+31.
-__device__ __forceinline__ void store_diag_row(uint8_t* tile, int row, int g, const float (&v)[32]) {
-  uint8_t* rowp = tile + (g >> 1) * kTile + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    uint4 u;
-    u.x = pack_bf16x2(v[8 * k + 0], v[8 * k + 1]);
-    u.y = pack_bf16x2(v[8 * k + 2], v[8 * k + 3]);
-    u.z = pack_bf16x2(v[8 * k + 4], v[8 * k + 5]);
-    u.w = pack_bf16x2(v[8 * k + 6], v[8 * k + 7]);
-    const int unit = ((g & 1) * 4 + k) ^ (row & 7);
-    *reinterpret_cast<uint4*>(rowp + unit * 16) = u;
-  }
 }
 
 // 32 lanes x 8 consecutive fp32 columns (thread t of the warp gets lane base + t)
@@ -162,98 +151,84 @@ __device__ __forceinline__ void store_tmem_row_warp(uint32_t taddr, __nv_bfloat1
   }
 }
 
-// 8 bf16 of row `row`, columns 32g + 8k .. +8, of a block-diagonal [128 x 128] K-major tile (two 64-column chunks of
-// 128 rows x 128 B, 128B swizzle)
-__device__ __forceinline__ void store_diag8(uint8_t* tile, int row, int g, int k, const float (&v)[8]) {
-  uint8_t* rowp = tile + (g >> 1) * kTile + (row >> 3) * 1024 + (row & 7) * 128;
+// 8 bf16 of row `row`, columns col0 .. col0 + 8 (col0 a multiple of 8), of a [128 x 128] K-major tile (two 64-column chunks
+// of 128 rows x 128 B, 128B swizzle).  The block-diagonal P / dS tiles: pair g owns columns SLOT*g .. SLOT*g + SLOT - 1.
+__device__ __forceinline__ void store_diag8(uint8_t* tile, int row, int col0, const float (&v)[8]) {
+  uint8_t* rowp = tile + (col0 >> 6) * kTile + (row >> 3) * 1024 + (row & 7) * 128;
   uint4 u;
   u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
   u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-  *reinterpret_cast<uint4*>(rowp + ((((g & 1) * 4 + k) ^ (row & 7)) << 4)) = u;
+  *reinterpret_cast<uint4*>(rowp + ((((col0 & 63) >> 3) ^ (row & 7)) << 4)) = u;
 }
 
+template <int SLOT>
 struct RowCtx {
-  int b, h, i;
+  using M = typename MaskT<SLOT>::type;
+  int b, h, i, g;
   bool pair_ok, row_ok;
   long long prow;        // (b*H + h)*Lq + i
-  uint32_t in_range;     // bit j: key j < Lk
-  uint32_t visible;      // bit j: key j not masked by key_mask
+  M in_range;            // bit j: key j < Lk
+  M visible;             // bit j: key j not masked by key_mask
 };
 
-__device__ __forceinline__ RowCtx row_ctx(int B, int H, int Lq, int Lk, const long long* key_mask) {
-  RowCtx c;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+template <int SLOT>
+__device__ __forceinline__ RowCtx<SLOT> row_ctx(int B, int H, int Lq, int Lk, const long long* key_mask) {
+  using M = typename MaskT<SLOT>::type;
+  RowCtx<SLOT> c;
+  const int t = threadIdx.x, lane = t & 31;
   const int npairs = B * H;
-  const int pr = blockIdx.x * kPairs + warp;
+  c.g = t / SLOT;
+  c.i = t - c.g * SLOT;
+  const int pr = blockIdx.x * (128 / SLOT) + c.g;
   c.pair_ok = pr < npairs;
   const int prc = c.pair_ok ? pr : npairs - 1;
   c.b = prc / H;
   c.h = prc - c.b * H;
-  c.i = lane;
-  c.row_ok = c.pair_ok && lane < Lq;
-  c.prow = (static_cast<long long>(c.b) * H + c.h) * Lq + lane;
-  c.in_range = Lk >= 32 ? 0xFFFFFFFFu : ((1u << Lk) - 1u);
-  bool vis = lane < Lk;
-  if (vis && key_mask != nullptr) vis = key_mask[static_cast<long long>(c.b) * Lk + lane] != 0;
-  c.visible = __ballot_sync(0xffffffffu, vis);
+  c.row_ok = c.pair_ok && c.i < Lq;
+  c.prow = (static_cast<long long>(c.b) * H + c.h) * Lq + c.i;
+  c.in_range = Lk >= SLOT ? ~static_cast<M>(0) : ((static_cast<M>(1) << Lk) - 1);
+  // every warp builds the whole key mask of its pair itself: lane l looks at key l (and key l + 32)
+  M vis_all = 0;
+#pragma unroll
+  for (int hlf = 0; hlf < SLOT / 32; ++hlf) {
+    const int key = hlf * 32 + lane;
+    bool vis = key < Lk;
+    if (vis && key_mask != nullptr) vis = key_mask[static_cast<long long>(c.b) * Lk + key] != 0;
+    vis_all |= static_cast<M>(__ballot_sync(0xffffffffu, vis)) << (hlf * 32);
+  }
+  c.visible = vis_all;
   return c;
 }
 
-// scores of one row: acc * scale + bias, masked keys -> finfo.min, keys >= Lk left untouched (never used)
-__device__ __forceinline__ void finish_scores(float (&s)[32], const uint32_t (&acc)[32], const RowCtx& c, float scale,
-                                              const float* bias, int Lq, int Lk) {
-  const float* brow = bias != nullptr ? bias + (static_cast<long long>(c.h) * Lq + (c.i < Lq ? c.i : 0)) * Lk : nullptr;
-  const bool vec = brow != nullptr && (Lk & 3) == 0 && (reinterpret_cast<uintptr_t>(brow) & 15) == 0;
-#pragma unroll
-  for (int q4 = 0; q4 < 8; ++q4) {
-    float bv[4] = {0.f, 0.f, 0.f, 0.f};
-    if (brow != nullptr && q4 * 4 < Lk) {
-      if (vec) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(brow) + q4);
-        bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (q4 * 4 + e < Lk) bv[e] = __ldg(brow + q4 * 4 + e);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int j = q4 * 4 + e;
-      float v = __uint_as_float(acc[j]) * scale + bv[e];
-      if (!((c.visible >> j) & 1u)) v = kMaskedScore;
-      s[j] = v;
-    }
-  }
-}
-
-// The row's 32 bias values, fetched BEFORE the score MMA is waited for (L2 latency off the critical path).
-__device__ __forceinline__ void load_bias_row(float4 (&bq)[8], const float* bias, const RowCtx& c, int Lq, int Lk) {
+// 32 of the row's bias values (keys 32*hlf .. 32*hlf + 31); for the first half fetched BEFORE the score MMA is waited for
+// (L2 latency off the critical path).
+__device__ __forceinline__ void load_bias_row(float4 (&bq)[8], const float* bias, int h, int i, int Lq, int Lk, int hlf = 0) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) bq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (bias == nullptr) return;
-  const float* brow = bias + (static_cast<long long>(c.h) * Lq + (c.i < Lq ? c.i : 0)) * Lk;
+  const float* brow = bias + (static_cast<long long>(h) * Lq + (i < Lq ? i : 0)) * Lk;
+  const int j0 = hlf * 32;
   if ((Lk & 3) == 0 && (reinterpret_cast<uintptr_t>(brow) & 15) == 0) {
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-      if (q * 4 < Lk) bq[q] = __ldg(reinterpret_cast<const float4*>(brow) + q);
+      if (j0 + q * 4 < Lk) bq[q] = __ldg(reinterpret_cast<const float4*>(brow + j0) + q);
   } else {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (q * 4 + e < Lk) v[e] = __ldg(brow + q * 4 + e);
+        if (j0 + q * 4 + e < Lk) v[e] = __ldg(brow + j0 + q * 4 + e);
       bq[q] = make_float4(v[0], v[1], v[2], v[3]);
     }
   }
 }
 
-// scores of columns 8k .. 8k+7 of one row: acc * scale + bias, masked keys -> finfo.min (keys >= Lk: caller ignores)
-__device__ __forceinline__ void score8(float (&s)[8], const uint32_t (&acc)[8], int k, uint32_t visible, float scale,
+// scores of 8 consecutive keys of one row: acc * scale + bias, masked keys -> finfo.min (keys >= Lk: caller ignores).
+// vis: bit e = key e of the group is visible.
+__device__ __forceinline__ void score8(float (&s)[8], const uint32_t (&acc)[8], uint32_t vis, float scale,
                                        const float4& b0, const float4& b1) {
   const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-  const uint32_t vis = visible >> (k * 8);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const float v = __uint_as_float(acc[e]) * scale + bv[e];
@@ -273,10 +248,12 @@ struct FwdP {
   long long* dbg;   // bring-up: clock64 stamps of CTA 0 (vqa_debug_attn_timing), else null
 };
 
-template <int HD>
+template <int HD, int SLOT>
 __global__ void __launch_bounds__(kThreads)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const FwdP a) {
+  using M = typename MaskT<SLOT>::type;
+  constexpr int kPairs = 128 / SLOT, kBox = SLOT * 128, NH = SLOT / 32;
   constexpr int CH = (HD + 63) / 64;   // 64-column chunks per operand row
   constexpr int KS = HD / 16;          // UMMA k-steps over the head dim
   constexpr uint32_t kCols = 256;      // TMEM: S [0,128), O [128, 128 + HD)
@@ -331,12 +308,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   __syncwarp();
   // per-row context (mask ballot, dropout bits, bias row) is computed while the TMA loads are in flight
-  const RowCtx rc = row_ctx(a.B, a.H, a.Lq, a.Lk, a.key_mask);
+  const RowCtx<SLOT> rc = row_ctx<SLOT>(a.B, a.H, a.Lq, a.Lk, a.key_mask);
   const DropCtx dc = drop_ctx(a.drop_p, a.sid, a.rng);
-  const uint32_t keep = keep_bits(dc, static_cast<unsigned long long>(rc.prow) * a.Lk, a.Lk);
+  const M keep = keep_bits<M>(dc, static_cast<unsigned long long>(rc.prow) * a.Lk, a.Lk);
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
   float4 bq[8];
-  load_bias_row(bq, a.bias, rc, a.Lq, a.Lk);
+  load_bias_row(bq, a.bias, rc.h, rc.i, a.Lq, a.Lk, 0);
   if (warp == 0) {   // whole warp, one elected lane issues (operands stay in uniform registers)
     mbar_wait_lean(bar_tma, 0);
     tc_fence_after();
@@ -355,38 +332,44 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   mbar_wait_lean(bar_mma, 0);
   tc_fence_after();
   VQA_STAMP(5);
-  const uint32_t t_s = tmem + lane_base + warp * 32;     // this row's 32 scores (diagonal block of the pair)
-  // the row's 32 scores come out of TMEM with ONE load (a round trip per 8 columns and per pass was most of this phase)
-  uint32_t accs[32];
-  tmem_ld_32x32(t_s, accs);
-  tmem_ld_wait();
-  float scs[32];
-  // pass 1: scores (scale, bias, key mask) and the row maximum
+  const uint32_t t_s = tmem + lane_base + rc.g * SLOT;     // this row's SLOT scores (diagonal block of the pair)
+  float scs[SLOT];
+  // pass 1: scores (scale, bias, key mask) and the row maximum; a row's scores come out of TMEM 32 columns per load
   float mx = -INFINITY;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (k * 8 >= a.Lk) break;
-    score8(*reinterpret_cast<float(*)[8]>(&scs[8 * k]), *reinterpret_cast<const uint32_t(*)[8]>(&accs[8 * k]), k, rc.visible,
-           a.scale, bq[2 * k], bq[2 * k + 1]);
-    const uint32_t inr = rc.in_range >> (k * 8);
+  for (int hf = 0; hf < NH; ++hf) {
+    if (hf * 32 >= a.Lk) break;
+    uint32_t accs[32];
+    tmem_ld_32x32(t_s + hf * 32, accs);
+    if (hf > 0) load_bias_row(bq, a.bias, rc.h, rc.i, a.Lq, a.Lk, hf);
+    tmem_ld_wait();
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if ((inr >> e) & 1u) mx = fmaxf(mx, scs[8 * k + e]);
+    for (int k = 0; k < 4; ++k) {
+      const int j0 = hf * 32 + k * 8;
+      if (j0 >= a.Lk) break;
+      score8(*reinterpret_cast<float(*)[8]>(&scs[j0]), *reinterpret_cast<const uint32_t(*)[8]>(&accs[8 * k]),
+             static_cast<uint32_t>(rc.visible >> j0), a.scale, bq[2 * k], bq[2 * k + 1]);
+      const uint32_t inr = static_cast<uint32_t>(rc.in_range >> j0);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if ((inr >> e) & 1u) mx = fmaxf(mx, scs[j0 + e]);
+    }
   }
   // pass 2: exp, row sum, dropout, bf16 P (unnormalised: the 1/sum goes onto O, flash style)
   float sum = 0.f;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (k * 8 >= a.Lk) break;
+  for (int kk = 0; kk < SLOT / 8; ++kk) {
+    const int j0 = kk * 8;
+    if (j0 >= a.Lk) break;
     float sc[8];
-    const uint32_t inr = rc.in_range >> (k * 8), kp = keep >> (k * 8);
+    const uint32_t inr = static_cast<uint32_t>(rc.in_range >> j0), kp = static_cast<uint32_t>(keep >> j0);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float ex = ((inr >> e) & 1u) ? __expf(scs[8 * k + e] - mx) : 0.f;
+      const float ex = ((inr >> e) & 1u) ? __expf(scs[j0 + e] - mx) : 0.f;
       sum += ex;
       sc[e] = ((kp >> e) & 1u) ? ex : 0.f;
     }
-    store_diag8(Pg, t, warp, k, sc);
+    store_diag8(Pg, t, rc.g * SLOT + j0, sc);
   }
   const float inv = 1.f / sum;
   if (rc.row_ok && a.stats != nullptr) {
@@ -438,10 +421,12 @@ struct BwdP {
   long long* dbg;
 };
 
-template <int HD>
+template <int HD, int SLOT>
 __global__ void __launch_bounds__(kThreads)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const BwdP a) {
+  using M = typename MaskT<SLOT>::type;
+  constexpr int kPairs = 128 / SLOT, kBox = SLOT * 128, NH = SLOT / 32;
   constexpr int CH = (HD + 63) / 64;
   constexpr int KS = HD / 16;
   // TMEM: S [0,128), dP [128,256); once both are in registers their columns are recycled for the outputs
@@ -507,12 +492,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   }
   __syncwarp();
-  const RowCtx rc = row_ctx(a.B, a.H, a.Lq, a.Lk, a.key_mask);
+  const RowCtx<SLOT> rc = row_ctx<SLOT>(a.B, a.H, a.Lq, a.Lk, a.key_mask);
   const DropCtx dc = drop_ctx(a.drop_p, a.sid, a.rng);
-  const uint32_t keep = keep_bits(dc, static_cast<unsigned long long>(rc.prow) * a.Lk, a.Lk);
+  const M keep = keep_bits<M>(dc, static_cast<unsigned long long>(rc.prow) * a.Lk, a.Lk);
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
   float4 bq[8];
-  load_bias_row(bq, a.bias, rc, a.Lq, a.Lk);
+  load_bias_row(bq, a.bias, rc.h, rc.i, a.Lq, a.Lk, 0);
   float mx = 0.f, inv = 0.f;
   if (rc.row_ok) {
     const float2 st = *reinterpret_cast<const float2*>(a.stats + 2 * rc.prow);
@@ -542,31 +527,38 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   mbar_wait_lean(bar_mma, 0);
   tc_fence_after();
   VQA_STAMP(5);
-  const uint32_t t_s = tmem + lane_base + warp * 32;          // S block of this row
-  const uint32_t t_dp = tmem + lane_base + 128 + warp * 32;   // dP block of this row
+  const uint32_t t_s = tmem + lane_base + rc.g * SLOT;          // S block of this row
+  const uint32_t t_dp = tmem + lane_base + 128 + rc.g * SLOT;   // dP block of this row
   // rows that do not exist (i >= Lq, pair beyond B*H) get P = 0 so they add nothing to dK / dV
-  // S and dP rows: ONE 32-column TMEM load each (a round trip per 8 columns and per pass was ~2 us of this kernel); the
-  // probabilities and the masked, rescaled dP values then stay in registers for pass 2
-  uint32_t accs[32], accd[32];
-  tmem_ld_32x32(t_s, accs);
-  tmem_ld_32x32(t_dp, accd);
-  tmem_ld_wait();
-  float pjs[32], dps[32];
+  // S and dP rows: one 32-column TMEM load each per half; the probabilities and the masked, rescaled dP values then stay in
+  // registers for pass 2
+  float pjs[SLOT], dps[SLOT];
   // pass 1: rowdot = sum_j P_j dP_j (dP through the dropout mask)
   float rowdot = 0.f;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (k * 8 >= a.Lk) break;
-    float sc[8];
-    score8(sc, *reinterpret_cast<const uint32_t(*)[8]>(&accs[8 * k]), k, rc.visible, a.scale, bq[2 * k], bq[2 * k + 1]);
-    const uint32_t inr = rc.row_ok ? (rc.in_range >> (k * 8)) : 0u, kp = keep >> (k * 8);
+  for (int hf = 0; hf < NH; ++hf) {
+    if (hf * 32 >= a.Lk) break;
+    uint32_t accs[32], accd[32];
+    tmem_ld_32x32(t_s + hf * 32, accs);
+    tmem_ld_32x32(t_dp + hf * 32, accd);
+    if (hf > 0) load_bias_row(bq, a.bias, rc.h, rc.i, a.Lq, a.Lk, hf);
+    tmem_ld_wait();
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float pj = ((inr >> e) & 1u) ? __expf(sc[e] - mx) * inv : 0.f;
-      const float dp = ((kp >> e) & 1u) ? __uint_as_float(accd[8 * k + e]) * dc.scale : 0.f;
-      pjs[8 * k + e] = pj;
-      dps[8 * k + e] = dp;
-      rowdot = fmaf(pj, dp, rowdot);
+    for (int k = 0; k < 4; ++k) {
+      const int j0 = hf * 32 + k * 8;
+      if (j0 >= a.Lk) break;
+      float sc[8];
+      score8(sc, *reinterpret_cast<const uint32_t(*)[8]>(&accs[8 * k]), static_cast<uint32_t>(rc.visible >> j0), a.scale,
+             bq[2 * k], bq[2 * k + 1]);
+      const uint32_t inr = rc.row_ok ? static_cast<uint32_t>(rc.in_range >> j0) : 0u, kp = static_cast<uint32_t>(keep >> j0);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float pj = ((inr >> e) & 1u) ? __expf(sc[e] - mx) * inv : 0.f;
+        const float dp = ((kp >> e) & 1u) ? __uint_as_float(accd[8 * k + e]) * dc.scale : 0.f;
+        pjs[j0 + e] = pj;
+        dps[j0 + e] = dp;
+        rowdot = fmaf(pj, dp, rowdot);
+      }
     }
   }
   // pass 2: dS = P (dP - rowdot); bias gradient; bf16 operands of the three output MMAs
@@ -579,31 +571,32 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   float* dbrow = (a.dbias != nullptr && rc.row_ok) ? a.dbias + (static_cast<long long>(rc.h) * a.Lq + rc.i) * a.Lk : nullptr;
   const bool dbvec = dbrow != nullptr && (a.Lk & 3) == 0 && (reinterpret_cast<uintptr_t>(dbrow) & 15) == 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (k * 8 >= a.Lk) break;
+  for (int kk = 0; kk < SLOT / 8; ++kk) {
+    const int j0 = kk * 8;
+    if (j0 >= a.Lk) break;
     float sc[8], ds[8];
-    const uint32_t kp = keep >> (k * 8);
+    const uint32_t kp = static_cast<uint32_t>(keep >> j0);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float pj = pjs[8 * k + e];
+      const float pj = pjs[j0 + e];
       // dps already carries the dropout mask and its 1/(1-p): dropped keys contribute -P * rowdot, as before
-      ds[e] = pj * (dps[8 * k + e] - rowdot);
+      ds[e] = pj * (dps[j0 + e] - rowdot);
       sc[e] = ((kp >> e) & 1u) ? pj * dc.scale : 0.f;   // dropped probabilities (operand of dV)
     }
     if (dbrow != nullptr) {
       if (dbvec) {
-        atomicAdd(reinterpret_cast<float4*>(dbrow) + 2 * k, make_float4(ds[0], ds[1], ds[2], ds[3]));
-        atomicAdd(reinterpret_cast<float4*>(dbrow) + 2 * k + 1, make_float4(ds[4], ds[5], ds[6], ds[7]));
+        atomicAdd(reinterpret_cast<float4*>(dbrow) + 2 * kk, make_float4(ds[0], ds[1], ds[2], ds[3]));
+        atomicAdd(reinterpret_cast<float4*>(dbrow) + 2 * kk + 1, make_float4(ds[4], ds[5], ds[6], ds[7]));
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e)
-          if (k * 8 + e < a.Lk) atomicAdd(dbrow + k * 8 + e, ds[e]);
+          if (j0 + e < a.Lk) atomicAdd(dbrow + j0 + e, ds[e]);
       }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) ds[e] *= a.scale;   // both dQ and dK carry the score scale
-    store_diag8(Pdg, t, warp, k, sc);
-    store_diag8(dSg, t, warp, k, ds);
+    store_diag8(Pdg, t, rc.g * SLOT + j0, sc);
+    store_diag8(dSg, t, rc.g * SLOT + j0, ds);
   }
   VQA_STAMP(6);
   fence_async_smem();
@@ -666,9 +659,28 @@ int raise_smem(K kern, size_t bytes, const char* what) {
   return 0;
 }
 
-int operand_map(CUtensorMap* tm, const void* base, long long rows, int H, int hd, long long ld, const char* what) {
+int operand_map(CUtensorMap* tm, const void* base, long long rows, int H, int hd, long long ld, int slot, const char* what) {
   if (reinterpret_cast<uintptr_t>(base) & 15) { set_last_error("%s: operand pointers must be 16-byte aligned", what); return -1; }
-  return make_tmap_2d(tm, base, static_cast<uint64_t>(rows), static_cast<uint64_t>(H) * hd, static_cast<uint64_t>(ld), 64, kSlot);
+  return make_tmap_2d(tm, base, static_cast<uint64_t>(rows), static_cast<uint64_t>(H) * hd, static_cast<uint64_t>(ld), 64, slot);
+}
+
+inline int slot_for(int Lq, int Lk) { return (Lq <= 32 && Lk <= 32) ? 32 : 64; }
+
+template <int HD, int SLOT>
+int launch_fwd(int grid, cudaStream_t s, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FwdP& a) {
+  static bool attr = false;
+  if (!attr) { if (raise_smem(attn_tc_fwd_kernel<HD, SLOT>, fwd_smem_bytes<HD>(), "attention_fwd")) return -1; attr = true; }
+  launch_pdl(attn_tc_fwd_kernel<HD, SLOT>, dim3(grid), dim3(kThreads), fwd_smem_bytes<HD>(), s, tq, tk, tv, a);
+  return launch_status("attention_fwd");
+}
+
+template <int HD, int SLOT>
+int launch_bwd(int grid, cudaStream_t s, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+               const CUtensorMap& tdo, const BwdP& a) {
+  static bool attr = false;
+  if (!attr) { if (raise_smem(attn_tc_bwd_kernel<HD, SLOT>, bwd_smem_bytes<HD>(), "attention_bwd")) return -1; attr = true; }
+  launch_pdl(attn_tc_bwd_kernel<HD, SLOT>, dim3(grid), dim3(kThreads), bwd_smem_bytes<HD>(), s, tq, tk, tv, tdo, a);
+  return launch_status("attention_bwd");
 }
 
 }  // namespace
@@ -678,14 +690,15 @@ namespace vqa {
 void attention_tc_debug(long long* buf) { g_attn_dbg = buf; }
 
 bool attention_tc_supported(int Lq, int Lk, int hd) {
-  return Lq >= 1 && Lq <= kSlot && Lk >= 1 && Lk <= kSlot && (hd == 64 || hd == 96);
+  return Lq >= 1 && Lq <= 64 && Lk >= 1 && Lk <= 64 && (hd == 64 || hd == 96);
 }
 
 int attention_tc_fwd(void* plan, const vqa_attn_fwd_args* x, void* stream) {
   CUtensorMap tq, tk, tv;
-  if (operand_map(&tq, x->q, static_cast<long long>(x->B) * x->Lq, x->H, x->hd, x->ldq, "attention_fwd")) return -1;
-  if (operand_map(&tk, x->k, static_cast<long long>(x->B) * x->Lk, x->H, x->hd, x->ldk, "attention_fwd")) return -1;
-  if (operand_map(&tv, x->v, static_cast<long long>(x->B) * x->Lk, x->H, x->hd, x->ldv, "attention_fwd")) return -1;
+  const int slot = slot_for(x->Lq, x->Lk);
+  if (operand_map(&tq, x->q, static_cast<long long>(x->B) * x->Lq, x->H, x->hd, x->ldq, slot, "attention_fwd")) return -1;
+  if (operand_map(&tk, x->k, static_cast<long long>(x->B) * x->Lk, x->H, x->hd, x->ldk, slot, "attention_fwd")) return -1;
+  if (operand_map(&tv, x->v, static_cast<long long>(x->B) * x->Lk, x->H, x->hd, x->ldv, slot, "attention_fwd")) return -1;
   FwdP a;
   a.B = x->B; a.H = x->H; a.Lq = x->Lq; a.Lk = x->Lk;
   a.out = static_cast<__nv_bfloat16*>(x->out); a.ldo = x->ldo;
@@ -694,25 +707,22 @@ int attention_tc_fwd(void* plan, const vqa_attn_fwd_args* x, void* stream) {
   a.rng = reinterpret_cast<const unsigned long long*>(x->rng);
   a.dbg = g_attn_dbg;
   const int hd = x->hd;
-  static bool attr64 = false, attr96 = false;
-  if (hd == 64 && !attr64) { if (raise_smem(attn_tc_fwd_kernel<64>, fwd_smem_bytes<64>(), "attention_fwd")) return -1; attr64 = true; }
-  if (hd == 96 && !attr96) { if (raise_smem(attn_tc_fwd_kernel<96>, fwd_smem_bytes<96>(), "attention_fwd")) return -1; attr96 = true; }
-  const int grid = (a.B * a.H + kPairs - 1) / kPairs;
+  const int grid = (a.B * a.H + 128 / slot - 1) / (128 / slot);
   const double fl = 4.0 * a.B * a.H * a.Lq * a.Lk * hd;
   note_op("attention_fwd", fl, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    if (hd == 64) launch_pdl(attn_tc_fwd_kernel<64>, dim3(grid), dim3(kThreads), fwd_smem_bytes<64>(), s, tq, tk, tv, a);
-    else launch_pdl(attn_tc_fwd_kernel<96>, dim3(grid), dim3(kThreads), fwd_smem_bytes<96>(), s, tq, tk, tv, a);
-    return launch_status("attention_fwd");
+    if (hd == 64) return slot == 32 ? launch_fwd<64, 32>(grid, s, tq, tk, tv, a) : launch_fwd<64, 64>(grid, s, tq, tk, tv, a);
+    return slot == 32 ? launch_fwd<96, 32>(grid, s, tq, tk, tv, a) : launch_fwd<96, 64>(grid, s, tq, tk, tv, a);
   });
 }
 
 int attention_tc_bwd(void* plan, const vqa_attn_bwd_args* x, void* stream) {
   CUtensorMap tq, tk, tv, tdo;
-  if (operand_map(&tq, x->q, static_cast<long long>(x->B) * x->Lq, x->H, x->hd, x->ldq, "attention_bwd")) return -1;
-  if (operand_map(&tk, x->k, static_cast<long long>(x->B) * x->Lk, x->H, x->hd, x->ldk, "attention_bwd")) return -1;
-  if (operand_map(&tv, x->v, static_cast<long long>(x->B) * x->Lk, x->H, x->hd, x->ldv, "attention_bwd")) return -1;
-  if (operand_map(&tdo, x->dout, static_cast<long long>(x->B) * x->Lq, x->H, x->hd, x->ldo, "attention_bwd")) return -1;
+  const int slot = slot_for(x->Lq, x->Lk);
+  if (operand_map(&tq, x->q, static_cast<long long>(x->B) * x->Lq, x->H, x->hd, x->ldq, slot, "attention_bwd")) return -1;
+  if (operand_map(&tk, x->k, static_cast<long long>(x->B) * x->Lk, x->H, x->hd, x->ldk, slot, "attention_bwd")) return -1;
+  if (operand_map(&tv, x->v, static_cast<long long>(x->B) * x->Lk, x->H, x->hd, x->ldv, slot, "attention_bwd")) return -1;
+  if (operand_map(&tdo, x->dout, static_cast<long long>(x->B) * x->Lq, x->H, x->hd, x->ldo, slot, "attention_bwd")) return -1;
   BwdP a;
   a.B = x->B; a.H = x->H; a.Lq = x->Lq; a.Lk = x->Lk;
   a.stats = x->stats; a.bias = x->bias; a.key_mask = x->key_mask;
@@ -723,16 +733,12 @@ int attention_tc_bwd(void* plan, const vqa_attn_bwd_args* x, void* stream) {
   a.rng = reinterpret_cast<const unsigned long long*>(x->rng);
   a.dbg = g_attn_dbg;
   const int hd = x->hd;
-  static bool attr64 = false, attr96 = false;
-  if (hd == 64 && !attr64) { if (raise_smem(attn_tc_bwd_kernel<64>, bwd_smem_bytes<64>(), "attention_bwd")) return -1; attr64 = true; }
-  if (hd == 96 && !attr96) { if (raise_smem(attn_tc_bwd_kernel<96>, bwd_smem_bytes<96>(), "attention_bwd")) return -1; attr96 = true; }
-  const int grid = (a.B * a.H + kPairs - 1) / kPairs;
+  const int grid = (a.B * a.H + 128 / slot - 1) / (128 / slot);
   const double fl = 10.0 * a.B * a.H * a.Lq * a.Lk * hd;
   note_op("attention_bwd", fl, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
-    if (hd == 64) launch_pdl(attn_tc_bwd_kernel<64>, dim3(grid), dim3(kThreads), bwd_smem_bytes<64>(), s, tq, tk, tv, tdo, a);
-    else launch_pdl(attn_tc_bwd_kernel<96>, dim3(grid), dim3(kThreads), bwd_smem_bytes<96>(), s, tq, tk, tv, tdo, a);
-    return launch_status("attention_bwd");
+    if (hd == 64) return slot == 32 ? launch_bwd<64, 32>(grid, s, tq, tk, tv, tdo, a) : launch_bwd<64, 64>(grid, s, tq, tk, tv, tdo, a);
+    return slot == 32 ? launch_bwd<96, 32>(grid, s, tq, tk, tv, tdo, a) : launch_bwd<96, 64>(grid, s, tq, tk, tv, tdo, a);
   });
 }
 

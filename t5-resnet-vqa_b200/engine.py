@@ -317,7 +317,7 @@ class Engine:
         # T5 blocks 0..n-1 run their forward GEMMs with two-term (hi + lo bf16) operands: their weights' and normalised
         # inputs' bf16 rounding is what pulls the deepest tensors' gradient cosine below the 0.999 bar
         # (tools/precision_probe.py).  0 = plain bf16 everywhere.
-        self.t5_split_blocks = int(os.environ.get("VQA_B200_T5_SPLIT_BLOCKS", "4"))
+        self.t5_split_blocks = int(os.environ.get("VQA_B200_T5_SPLIT_BLOCKS", "2"))
         # the SGA stack's and the classifier's forward GEMMs add the weights' low-order term (x W_hi + x W_lo): the log-probs
         # of the flat random-init classifier then agree with fp32 closely enough for >= 99 % top-1 agreement with margin
         self.split_head = _env_flag("VQA_B200_SPLIT_HEAD", True)
@@ -561,6 +561,16 @@ class Engine:
         parameters the engine controls: forward, weight preparation, state_dict(), optimizer.state_dict()."""
         if self.opt_event is not None:
             (stream or torch.cuda.current_stream(self.device)).wait_event(self.opt_event)
+
+    def refresh_lo_after_update(self, stream):
+        """Low-order halves of the split-precision weights, recomputed right behind the fused optimizer pass on ITS stream
+        (None: the current one), i.e. off the next forward's critical path (which waits for the optimizer event anyway)."""
+        if not self.lo_ranges or self.lo_fresh or not self.shadow_fresh:
+            return
+        rec = _Rec(self.lib, None, (lambda: stream.cuda_stream) if stream is not None else self._stream)
+        for lo0, lo1 in self.lo_ranges:
+            rec.split_lo_bf16(self.master.data_ptr() + 4 * lo0, self.shadow_lo.data_ptr() + 2 * lo0, lo1 - lo0)
+        self.lo_fresh = True
 
     def note_fused_update(self, covered):
         """Called by VQAFusedAdamW after it updated `covered` of this engine's parameters in place (raw

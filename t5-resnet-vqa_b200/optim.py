@@ -197,6 +197,8 @@ class VQAFusedAdamW(torch.optim.Optimizer):
         for eng, covered in engines.items():
             eng.note_fused_update(covered)
             eng.pending_clip = None
+            if covered == len(eng.params):
+                eng.refresh_lo_after_update(side.get(eng))
             if side.get(eng) is not None:
                 eng.note_optimizer_launched(side[eng])
         return loss

@@ -63,9 +63,10 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
         return sid_counter[0]
 
     def attn_save(nheads, Lq, Lk):
-        """What attention saves for backward: (probs, stats).  Up to 32 x 32 tokens the tcgen05 flash kernels run
-        and keep only the softmax row statistics; longer key sequences use the SIMT kernel and its fp32 probs."""
-        if Lq <= 32 and Lk <= 32 and eng.use_tc_attention:
+        """What attention saves for backward: (probs, stats).  Up to 64 x 64 tokens (the 49 / 64 vision tokens of 224x224 /
+        256x256 images included) the tcgen05 flash kernels run and keep only the softmax row statistics; longer key
+        sequences (196 tokens at 448x448) use the SIMT kernel and its fp32 probs."""
+        if Lq <= 64 and Lk <= 64 and eng.use_tc_attention:
             return None, al(B * nheads * Lq, 2, dtype=f32)
         return al(B * nheads * Lq * Lk, dtype=f32), None
 

@@ -501,10 +501,15 @@ def test_embedding_and_bias(C, pkg):
 @pytest.mark.parametrize("B,H,Lq,Lk,hd,t5,tc", [
     (4, 12, 32, 32, 64, True, False), (3, 12, 16, 16, 64, True, False), (4, 8, 32, 32, 96, False, False),
     (4, 8, 32, 49, 96, False, False), (2, 8, 16, 64, 96, False, False), (2, 8, 32, 196, 96, False, False),
-    # tcgen05 flash kernels (Lq, Lk <= 32): full groups, ragged last group, short sequences, ragged Lk
+    # tcgen05 flash kernels, 32-row slots (Lq, Lk <= 32): full groups, ragged last group, short sequences, ragged Lk
     (4, 12, 32, 32, 64, True, True), (3, 12, 16, 16, 64, True, True), (64, 12, 32, 32, 64, True, True),
     (4, 8, 32, 32, 96, False, True), (3, 7, 32, 32, 96, False, True), (5, 6, 20, 27, 64, True, True),
-    (2, 8, 16, 16, 96, False, True)])
+    (2, 8, 16, 16, 96, False, True),
+    # 64-row slots (33 <= max(Lq, Lk) <= 64): the guided attention over 49 (224x224) / 64 (256x256) vision tokens, the
+    # reference's native 16-token questions, odd pair counts, long questions through the T5 path (bias + key mask)
+    (64, 8, 32, 49, 96, False, True), (4, 8, 32, 64, 96, False, True), (2, 8, 16, 64, 96, False, True),
+    (3, 7, 32, 49, 96, False, True), (3, 12, 64, 64, 64, True, True), (5, 12, 40, 40, 64, True, True),
+    (2, 12, 33, 50, 64, True, True)])
 def test_attention_fwd_bwd(C, B, H, Lq, Lk, hd, t5, tc):
     D = H * hd
     q = rnd(B * Lq, D, seed=1, scale=1.0 if not t5 else 0.4, dtype=BF)
@@ -549,7 +554,7 @@ def test_attention_fwd_bwd(C, B, H, Lq, Lk, hd, t5, tc):
         assert rel_fro(dbias, bias.grad) < 1.5e-2
 
 
-@pytest.mark.parametrize("H,hd,Lk", [(12, 64, 32), (8, 96, 32), (6, 64, 27)])
+@pytest.mark.parametrize("H,hd,Lk", [(12, 64, 32), (8, 96, 32), (6, 64, 27), (8, 96, 49), (8, 96, 64), (12, 64, 40)])
 def test_attention_tcgen05_dropout_matches_simt(C, H, hd, Lk):
     """Both kernels draw the dropout mask of probability (b,h,i,j) from the same Philox stream, so with dropout on
     the tcgen05 path must reproduce the SIMT path (forward and every gradient) up to bf16 rounding of P."""

@@ -138,8 +138,10 @@ def test_trainer_drives_three_steps(pkg, cuda):
             assert float(da.abs().max()) == 0.0 and float(db.abs().max()) == 0.0, k      # frozen / unused: untouched
             continue
         assert float(da.norm()) > 0, k
-        assert float((da - db).norm()) <= 0.05 * float(da.norm()), (k, float((da - db).norm() / da.norm()))
         moved += 1
+        if k.endswith("linear_k.bias"):
+            continue       # gradient is mathematically zero (softmax is shift invariant): Adam normalises pure rounding noise
+        assert float((da - db).norm()) <= 0.05 * float(da.norm()), (k, float((da - db).norm() / da.norm()))
     assert moved == 183
     out = os.path.join(os.path.dirname(GOLD), "..", "..", "gpurun_out")
     os.makedirs(out, exist_ok=True)
