@@ -161,6 +161,9 @@ int vqa_image_to_stem(void* plan, const float* img, void* out, int N, int H, int
 /* input edge: uint8 RGB [N,H,W,3] as cv2 produces it (dataset_utils/resnet_vqa_daquar_dataset.py:153-171)
  * -> the same stem layout with transforms.ToTensor()'s /255 folded in: a quarter of the fp32 CHW upload */
 int vqa_image_u8_to_stem(void* plan, const uint8_t* img, void* out, int N, int H, int W, void* stream);
+/* F.interpolate(mode="nearest") on bf16 NHWC [N,h,w,C] -> [N,H,W,C]: the FPN top-down pathway of the Faster R-CNN backbone
+ * (torchvision feature_pyramid_network.py; model/faster_rcnn_vqa_model.py:51-53,150-154) */
+int vqa_upsample_nearest_nhwc(void* plan, const void* x, void* out, int N, int h, int w, int H, int W, int C, void* stream);
 int vqa_nhwc_to_nchw_f32(void* plan, const void* x, float* out, int N, int H, int W, int C, void* stream);
 /* MaxPool2d(3, stride 2, pad 1) on bf16 NHWC (tv:200) */
 int vqa_maxpool3x3s2(void* plan, const void* x, void* out, int N, int H, int W, int C, void* stream);

@@ -30,6 +30,12 @@ CASES = {
     # all-ones mask, and the same with a padded tail of 10 tokens
     "r50_b64": dict(vision="resnet50", B=64, L=32, H=224, W=224, masked_tail=0),
     "r50_b64_masked": dict(vision="resnet50", B=64, L=32, H=224, W=224, masked_tail=10),
+    # BASELINE.json configs[3] regime: 448x448 images -> 14x14 = 196 vision tokens through the 512 -> 768 upscaling path
+    "r34_b2_448": dict(vision="resnet34", B=2, L=32, H=448, W=448, masked_tail=4),
+    # FasterRcnnVQAModel (model/faster_rcnn_vqa_model.py): FPN 'pool' level, 256 -> 768; the reference's collate shapes
+    # (256x256 -> 4x4 = 16 tokens, 16-token questions) and 448x448 (7x7 = 49 tokens)
+    "frcnn_b2_256_l16": dict(vision="faster-rcnn", B=2, L=16, H=256, W=256, masked_tail=3),
+    "frcnn_b2_448": dict(vision="faster-rcnn", B=2, L=32, H=448, W=448, masked_tail=0),
 }
 
 
@@ -44,6 +50,19 @@ def reference_model(vision):
                    num_heads=12, relative_attention_num_buckets=32, relative_attention_max_distance=128,
                    dropout_rate=0.1, layer_norm_epsilon=1e-6, feed_forward_proj="relu")
     T5ForQuestionAnswering.from_pretrained = staticmethod(lambda name, *a, **k: T5ForQuestionAnswering(cfg))
+    if vision == "faster-rcnn":
+        # fasterrcnn_resnet50_fpn(pretrained=True) builds its backbone as resnet50(norm_layer=FrozenBatchNorm2d) behind
+        # _resnet_fpn_extractor(.., trainable_layers=3) and then downloads weights; the same construction without the download
+        import types
+        import model.faster_rcnn_vqa_model as fref
+        from torchvision.models.detection.backbone_utils import _resnet_fpn_extractor
+        from torchvision.ops import misc as misc_nn_ops
+
+        def detector(pretrained=True):
+            body = torchvision.models.resnet50(weights=None, norm_layer=misc_nn_ops.FrozenBatchNorm2d)
+            return types.SimpleNamespace(backbone=_resnet_fpn_extractor(body, 3))
+        fref.fasterrcnn_resnet50_fpn = detector
+        return fref.FasterRcnnVQAModel("faster-rcnn", "t5-base", answer_spaces=170)
     return ref.ResnetVQAModel(vision, "t5-base", answer_spaces=170)
 
 

@@ -36,19 +36,22 @@ def state_dict_spec(vision_name, answer_spaces=170, num_attention_blocks=3):
     def conv(k, o, i, r):
         spec.append((k + ".weight", (o, i, r, r), "conv"))
 
+    frcnn = vision_name == "faster-rcnn"
+
     def bn(k, c, last=False):
         spec.extend([(k + ".weight", (c,), "bn_w_last" if last else "bn_w"), (k + ".bias", (c,), "bn_b"),
-                     (k + ".running_mean", (c,), "bn_m"), (k + ".running_var", (c,), "bn_v"),
-                     (k + ".num_batches_tracked", (), "count")])
+                     (k + ".running_mean", (c,), "bn_m"), (k + ".running_var", (c,), "bn_v")])
+        if not frcnn:      # torchvision FrozenBatchNorm2d (the detector's backbone) keeps no batch counter
+            spec.append((k + ".num_batches_tracked", (), "count"))
 
     def linear(k, o, i, bias=True, kind="linear"):
         spec.append((k + ".weight", (o, i), kind))
         if bias:
             spec.append((k + ".bias", (o,), "bias"))
 
-    kind, layers = RESNET_CFG[vision_name]
+    kind, layers = RESNET_CFG["resnet50" if frcnn else vision_name]
     exp = 4 if kind == "bottleneck" else 1
-    v = "vision_model."
+    v = "vision_model.body." if frcnn else "vision_model."
     conv(v + "conv1", 64, 3, 7); bn(v + "bn1", 64)
     inpl = 64
     for li, (planes, n) in enumerate(zip([64, 128, 256, 512], layers)):
@@ -65,7 +68,17 @@ def state_dict_spec(vision_name, answer_spaces=170, num_attention_blocks=3):
             if bi == 0 and (stride != 1 or inpl != planes * exp):
                 conv(p + "downsample.0", planes * exp, inpl, 1); bn(p + "downsample.1", planes * exp)
             inpl = planes * exp
-    linear(v + "fc", 1000, 512 * exp)
+    if frcnn:
+        # FeaturePyramidNetwork([256, 512, 1024, 2048], 256): lateral 1x1 and output 3x3 convs with bias (key '.0.':
+        # Conv2dNormActivation without norm / activation)
+        for i, cin in enumerate([256, 512, 1024, 2048]):
+            spec.append(("vision_model.fpn.inner_blocks.%d.0.weight" % i, (256, cin, 1, 1), "fpn_conv"))
+            spec.append(("vision_model.fpn.inner_blocks.%d.0.bias" % i, (256,), "bn_b"))
+        for i in range(4):
+            spec.append(("vision_model.fpn.layer_blocks.%d.0.weight" % i, (256, 256, 3, 3), "fpn_conv"))
+            spec.append(("vision_model.fpn.layer_blocks.%d.0.bias" % i, (256,), "bn_b"))
+    else:
+        linear(v + "fc", 1000, 512 * exp)
     t = "lang_model."
     d, inner, dff = T5["d_model"], T5["d_kv"] * T5["num_heads"], T5["d_ff"]
     spec.append((t + "embed_tokens.weight", (T5["vocab"], d), "embed"))
@@ -82,7 +95,7 @@ def state_dict_spec(vision_name, answer_spaces=170, num_attention_blocks=3):
         spec.append(("%sblock.%d.layer.1.DenseReluDense.wo.weight" % (t, b), (d, dff), "t5_wo"))
         spec.append(("%sblock.%d.layer.1.layer_norm.weight" % (t, b), (d,), "norm_w"))
     spec.append((t + "final_layer_norm.weight", (d,), "norm_w"))
-    for name, cin in (("upscale_layer", 512), ("downscale_layer", 2048)):
+    for name, cin in ((("upscale_layer", 256),) if frcnn else (("upscale_layer", 512), ("downscale_layer", 2048))):
         spec.append((name + ".weight", (cin, 768, 3, 3), "convT"))
         spec.append((name + ".bias", (768,), "bias"))
     for l in range(num_attention_blocks):
@@ -112,6 +125,9 @@ def random_state_dict(vision_name, answer_spaces=170, seed=0, num_attention_bloc
         if kind == "conv":
             std = math.sqrt(2.0 / (shape[0] * shape[2] * shape[3]))
             t = torch.randn(shape, generator=g) * std
+        elif kind == "fpn_conv":
+            bound = math.sqrt(3.0 / (shape[1] * shape[2] * shape[3]))     # kaiming_uniform_(a=1)
+            t = (torch.rand(shape, generator=g) * 2 - 1) * bound
         elif kind in ("bn_w", "bn_v"):
             t = 0.5 + torch.rand(shape, generator=g)
         elif kind == "bn_w_last":
@@ -166,11 +182,12 @@ def _bn(sd, k, x):
                         False, 0.0, 1e-5)
 
 
-def resnet_body(sd, x, vision_name, p="vision_model."):
+def resnet_body(sd, x, vision_name, p="vision_model.", return_levels=False):
     """conv1/bn1/relu/maxpool/layer1..4 without avgpool/fc (model/resnet_vqa_model.py:119-121; tv:266-277)."""
     kind, layers = RESNET_CFG[vision_name]
     x = F.relu(_bn(sd, p + "bn1", F.conv2d(x, sd[p + "conv1.weight"], None, 2, 3)))
     x = F.max_pool2d(x, 3, 2, 1)
+    levels = []
     for li, n in enumerate(layers):
         for bi in range(n):
             b = "%slayer%d.%d." % (p, li + 1, bi)
@@ -186,7 +203,30 @@ def resnet_body(sd, x, vision_name, p="vision_model."):
             if (b + "downsample.0.weight") in sd:
                 idn = _bn(sd, b + "downsample.1", F.conv2d(x, sd[b + "downsample.0.weight"], None, stride, 0))
             x = F.relu(o + idn)
-    return x
+        levels.append(x)
+    return levels if return_levels else x
+
+
+def fpn_backbone(sd, x, p="vision_model."):
+    """`fasterrcnn_resnet50_fpn(pretrained=True).backbone` in eval mode (model/faster_rcnn_vqa_model.py:51-53,102-108):
+    ResNet-50 body with FrozenBatchNorm2d (same arithmetic as eval BatchNorm, eps 1e-5) returning layer1..4, then
+    torchvision's FeaturePyramidNetwork (lateral 1x1, nearest top-down, 3x3 output convs) and LastLevelMaxPool
+    (max_pool2d(kernel 1, stride 2) of the top level) -> {'0','1','2','3','pool'}."""
+    c = resnet_body(sd, x, "resnet50", p + "body.", return_levels=True)
+
+    def inner(i, t):
+        return F.conv2d(t, sd[p + "fpn.inner_blocks.%d.0.weight" % i], sd[p + "fpn.inner_blocks.%d.0.bias" % i])
+
+    def layer(i, t):
+        return F.conv2d(t, sd[p + "fpn.layer_blocks.%d.0.weight" % i], sd[p + "fpn.layer_blocks.%d.0.bias" % i], 1, 1)
+    last = inner(3, c[3])
+    out = {"3": layer(3, last)}
+    for i in (2, 1, 0):
+        lat = inner(i, c[i])
+        last = lat + F.interpolate(last, size=lat.shape[-2:], mode="nearest")
+        out[str(i)] = layer(i, last)
+    out["pool"] = F.max_pool2d(out["3"], kernel_size=1, stride=2, padding=0)
+    return out
 
 
 def t5_buckets(Lq, Lk, num_buckets=32, max_distance=128):
@@ -262,7 +302,12 @@ def forward(sd, vision_name, question_input_ids, question_attention_masks, annot
             num_attention_blocks=3, return_features=False):
     """ResnetVQAModel.forward in eval mode with grad enabled (model/resnet_vqa_model.py:114-165)."""
     with torch.no_grad():
-        feat = resnet_body(sd, image_tensors.float(), vision_name)
+        if vision_name == "faster-rcnn":      # model/faster_rcnn_vqa_model.py:102-108: the FPN's 'pool' level
+            feat_all = fpn_backbone(sd, image_tensors.float())
+            feat = feat_all["pool"]
+        else:
+            feat = resnet_body(sd, image_tensors.float(), vision_name)
+            feat_all = feat
     proj = "downscale_layer" if vision_name == "resnet50" else "upscale_layer"
     ve = F.conv_transpose2d(feat, sd[proj + ".weight"], sd[proj + ".bias"], 1, 1)
     text = t5_encoder(sd, question_input_ids, question_attention_masks)
@@ -277,14 +322,14 @@ def forward(sd, vision_name, question_input_ids, question_attention_masks, annot
     logp = F.log_softmax(F.linear(pooled, sd["classification_layer.weight"], sd["classification_layer.bias"]), -1)
     loss = F.nll_loss(logp, annotation_ids) if annotation_ids is not None else None
     if return_features:
-        return logp, loss, feat
+        return logp, loss, feat_all
     return logp, loss
 
 
 def trainable_keys(sd, vision_name):
     """Keys that receive a gradient in the reference (everything but the frozen backbone and the unused
     scaling layer)."""
-    unused = "upscale_layer." if vision_name == "resnet50" else "downscale_layer."
+    unused = "upscale_layer." if vision_name == "resnet50" else "downscale_layer."     # (faster-rcnn has no downscale_layer)
     return [k for k, v in sd.items()
             if not k.startswith("vision_model.") and not k.startswith(unused) and v.is_floating_point()]
 

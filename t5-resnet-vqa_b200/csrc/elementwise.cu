@@ -211,6 +211,25 @@ __global__ void image_u8_to_stem_kernel(const uint8_t* __restrict__ img, uint4* 
   }
 }
 
+// F.interpolate(mode="nearest") on bf16 NHWC (the FPN's top-down pathway, torchvision/ops/feature_pyramid_network.py):
+// out[n, y, x, :] = in[n, floor(y * h / H), floor(x * w / W), :]; one thread per 8 channels
+__global__ void upsample_nearest_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int h, int w, int H,
+                                        int W, int C8) {
+  pdl_grid_sync();
+  const long long total = static_cast<long long>(N) * H * W * C8;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int c = static_cast<int>(idx % C8);
+    long long t = idx / C8;
+    const int x = static_cast<int>(t % W); t /= W;
+    const int y = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    const int sy = min(static_cast<int>((static_cast<long long>(y) * h) / H), h - 1);
+    const int sx = min(static_cast<int>((static_cast<long long>(x) * w) / W), w - 1);
+    out[idx] = in[((static_cast<long long>(n) * h + sy) * w + sx) * C8 + c];
+  }
+}
+
 // x bf16 [N, HW, C] -> out fp32 [N, C, HW]
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int HW, int C) {
   pdl_grid_sync();
@@ -422,6 +441,17 @@ int vqa_image_u8_to_stem(void* plan, const uint8_t* img, void* out, int N, int H
     if (total >= (1LL << 31)) { set_last_error("image_u8_to_stem: more than 2^31 pixels"); return -1; }
     launch_pdl(image_u8_to_stem_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, s, img, static_cast<uint4*>(out), N, H, W);
     return launch_status("image_u8_to_stem");
+  });
+}
+
+int vqa_upsample_nearest_nhwc(void* plan, const void* x, void* out, int N, int h, int w, int H, int W, int C, void* stream) {
+  if (C % 8 || h < 1 || w < 1 || H < 1 || W < 1) { set_last_error("upsample_nearest: C must be a multiple of 8"); return -1; }
+  note_op("upsample_nearest", 0.0, 0.0);
+  return submit(plan, stream, [=](cudaStream_t s) {
+    const long long total = static_cast<long long>(N) * H * W * (C / 8);
+    launch_pdl(upsample_nearest_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, s, static_cast<const uint4*>(x),
+               static_cast<uint4*>(out), N, h, w, H, W, C / 8);
+    return launch_status("upsample_nearest");
   });
 }
 

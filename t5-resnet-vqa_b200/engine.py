@@ -452,7 +452,7 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     def _vision_convs(self):
         """(conv, bn) pairs of the frozen backbone in execution order, with their role."""
-        vm = self.model.vision_model
+        vm = self.model._resnet_body()
         out = [("stem", vm.conv1, vm.bn1)]
         for li, layer in enumerate([vm.layer1, vm.layer2, vm.layer3, vm.layer4]):
             for bi, blk in enumerate(layer):
@@ -461,13 +461,18 @@ class Engine:
                     out.append(("l%d.%d.%s" % (li, bi, nm), getattr(blk, nm), getattr(blk, "bn%d" % (j + 1))))
                 if blk.downsample is not None:
                     out.append(("l%d.%d.ds" % (li, bi), blk.downsample[0], blk.downsample[1]))
+        fpn = self.model._fpn()
+        if fpn is not None:      # lateral (1x1) and output (3x3) convs with bias, no normalisation (bn = None)
+            for i in range(len(fpn.inner_blocks)):
+                out.append(("fpn.inner%d" % i, fpn.inner_blocks[i][0], None))
+                out.append(("fpn.layer%d" % i, fpn.layer_blocks[i][0], None))
         return out
 
     def _prepare_vision(self):
         convs = self._vision_convs()
         sig = []
         for _, c, b in convs:
-            for t in (c.weight, b.weight, b.bias, b.running_mean, b.running_var):
+            for t in ((c.weight, b.weight, b.bias, b.running_mean, b.running_var) if b is not None else (c.weight, c.bias)):
                 if t.device != self.device:
                     raise RuntimeError("vision_model parameters must live on %s" % (self.device,))
                 sig.append((t.data_ptr(), t._version))
@@ -489,13 +494,27 @@ class Engine:
                 bias = torch.empty(O, dtype=torch.float32, device=self.device)
                 self.vw[name], self.vb[name] = w, bias
                 realloc = True
-            r.fold_conv_bn(c.weight.detach().float().contiguous(), b.weight.detach(), b.bias.detach(),
-                           b.running_mean, b.running_var, float(b.eps), w, bias, O, I, R, S, Sp, Ip)
+            if b is not None:
+                r.fold_conv_bn(c.weight.detach().float().contiguous(), b.weight.detach(), b.bias.detach(),
+                               b.running_mean, b.running_var, float(b.eps), w, bias, O, I, R, S, Sp, Ip)
+            else:
+                # no normalisation: identity scale (gamma 1, var 1, eps 0), shift = the conv's own bias (beta, mean 0)
+                one, zero = self._fold_const(O)
+                r.fold_conv_bn(c.weight.detach().float().contiguous(), one, c.bias.detach().float().contiguous(), zero, one,
+                               0.0, w, bias, O, I, R, S, Sp, Ip)
         if realloc and self.plans:
             for st in self.plans.values():
                 st.destroy(self.lib)
             self.plans = {}
         self.vision_sig = sig
+
+    def _fold_const(self, n):
+        key = ("fold_const", n)
+        if not hasattr(self, "_consts"):
+            self._consts = {}
+        if key not in self._consts:
+            self._consts[key] = (torch.ones(n, device=self.device), torch.zeros(n, device=self.device))
+        return self._consts[key]
 
     def _param_signature(self):
         return tuple(p._version for p in self.params)

@@ -90,6 +90,7 @@ SIGNATURES = {
     "vqa_convT_wgrad_unprep": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "vqa_image_to_stem": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "vqa_image_u8_to_stem": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
+    "vqa_upsample_nearest_nhwc": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "vqa_nhwc_to_nchw_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "vqa_maxpool3x3s2": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "vqa_embedding_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_f, c_u32, _P, _P]),

@@ -75,24 +75,19 @@ class _StepFunction(torch.autograd.Function):
         return (None, None, None) + tuple(grads)
 
 
-class ResnetVQAModel(nn.Module):
-    """ResNet-18/34/50 (frozen, eval) -> ConvTranspose2d 512/2048->768 -> tokens; T5-base encoder over the
-    question; 3 x SGA; AttentionPooler; Linear(768 -> answer_spaces); log_softmax; NLLLoss."""
+class _VQAModelBase(nn.Module):
+    """What the two CNN + T5 + SGA models of the reference share (model/resnet_vqa_model.py, model/faster_rcnn_vqa_model.py:
+    identical heads and forward / generate_answers signatures; they differ in the frozen backbone and the scaling layer)."""
 
-    def __init__(self, vision_model_name: str, language_model_name: str, answer_spaces: int,
-                 fine_tune_lm_encoder: bool = True, fine_tune_lm_decoder: bool = True,
-                 fine_tune_vision: bool = True, num_attention_blocks=3, device="cpu"):
-        super().__init__()
-        if vision_model_name not in M.ResNet.CFG:
-            raise ValueError("vision_model_name must be one of %s" % sorted(M.ResNet.CFG))
+    def _init_common(self, vision_model_name, language_model_name, answer_spaces, fine_tune_lm_encoder,
+                     fine_tune_lm_decoder, fine_tune_vision, num_attention_blocks, device):
         if language_model_name != "t5-base":
             raise ValueError("language_model_name must be 't5-base'")
         self.vision_model_name = vision_model_name
         self.language_model_name = language_model_name
-        self.vision_model = M.ResNet(vision_model_name)
+        self._build_vision()            # registration order = the reference's state_dict key order
         self.lang_model = M.T5Encoder()
-        self.upscale_layer = M.ConvTranspose2d(512, 768, 3)
-        self.downscale_layer = M.ConvTranspose2d(2048, 768, 3)
+        self._build_scalers()
         self.sga_modules = nn.ModuleList([M.SGA() for _ in range(num_attention_blocks)])
         self.classification_layer = M.Linear(768, answer_spaces)
         self.attention_pooler = M.AttentionPooler(768)
@@ -118,10 +113,14 @@ class ResnetVQAModel(nn.Module):
         loaded = []
         try:
             import torchvision
-            weights = torchvision.models.get_model_weights(self.vision_model_name).DEFAULT
+            name = self.vision_model_name if self._fpn() is None else "fasterrcnn_resnet50_fpn"
+            weights = torchvision.models.get_model_weights(name).DEFAULT
             hub = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(weights.url))
             if os.path.exists(hub):
-                self.vision_model.load_state_dict(torch.load(hub, map_location="cpu"))
+                sd = torch.load(hub, map_location="cpu")
+                if self._fpn() is not None:     # the detector's checkpoint: keep its `backbone.` entries
+                    sd = {k[len("backbone."):]: v for k, v in sd.items() if k.startswith("backbone.")}
+                self.vision_model.load_state_dict(sd)
                 loaded.append("vision")
         except Exception as e:  # pragma: no cover - depends on local caches
             if mode == "1":
@@ -139,6 +138,20 @@ class ResnetVQAModel(nn.Module):
             raise RuntimeError("VQA_B200_PRETRAINED=1 but pretrained weights are not available offline")
         self.pretrained_loaded = loaded
 
+    def _build_vision(self):
+        raise NotImplementedError
+
+    def _build_scalers(self):
+        raise NotImplementedError
+
+    def _resnet_body(self):
+        """The container holding conv1 / bn1 / layer1..4 of the frozen backbone."""
+        return self.vision_model
+
+    def _fpn(self):
+        """FeaturePyramidNetwork container behind the body, or None."""
+        return None
+
     def named_parameters(self, *args, **kwargs):
         """Same iterator as nn.Module's; reading parameters through it (or parameters(), state_dict()) is ordered
         after a fused optimizer pass that may still be running on the engine's optimizer stream."""
@@ -146,7 +159,7 @@ class ResnetVQAModel(nn.Module):
         return super().named_parameters(*args, **kwargs)
 
     def _projection(self):
-        return self.downscale_layer if self.vision_model_name == "resnet50" else self.upscale_layer
+        raise NotImplementedError
 
     # ------------------------------------------------------------------------------------------
     def _run(self, question_input_ids, question_attention_masks, annotation_ids, image_tensors, want_features):
@@ -182,7 +195,7 @@ class ResnetVQAModel(nn.Module):
         else:
             logp = st.logp.clone()
             loss = st.loss.reshape(()).clone() if has_labels else None
-        feats = st.features.clone() if want_features else None
+        feats = {k: v.clone() for k, v in st.features.items()} if want_features else None
         return logp, loss, feats
 
     def forward(self, question_input_ids: torch.Tensor, decoder_question_input_ids: torch.Tensor = None,
@@ -201,6 +214,70 @@ class ResnetVQAModel(nn.Module):
                          question_type_ids: torch.Tensor = None):
         logp, loss, feats = self._run(question_input_ids, question_attention_masks, annotation_ids, image_tensors,
                                       True)
+        return logp, loss, self._feature_dict(feats)
+
+
+class ResnetVQAModel(_VQAModelBase):
+    """ResNet-18/34/50 (frozen, eval) -> ConvTranspose2d 512/2048->768 -> tokens; T5-base encoder over the
+    question; 3 x SGA; AttentionPooler; Linear(768 -> answer_spaces); log_softmax; NLLLoss
+    (model/resnet_vqa_model.py:28-231)."""
+
+    def __init__(self, vision_model_name: str, language_model_name: str, answer_spaces: int,
+                 fine_tune_lm_encoder: bool = True, fine_tune_lm_decoder: bool = True,
+                 fine_tune_vision: bool = True, num_attention_blocks=3, device="cpu"):
+        super().__init__()
+        if vision_model_name not in M.ResNet.CFG:
+            raise ValueError("vision_model_name must be one of %s" % sorted(M.ResNet.CFG))
+        self._init_common(vision_model_name, language_model_name, answer_spaces, fine_tune_lm_encoder,
+                          fine_tune_lm_decoder, fine_tune_vision, num_attention_blocks, device)
+
+    def _build_vision(self):
+        self.vision_model = M.ResNet(self.vision_model_name)
+
+    def _build_scalers(self):
+        self.upscale_layer = M.ConvTranspose2d(512, 768, 3)
+        self.downscale_layer = M.ConvTranspose2d(2048, 768, 3)
+
+    def _projection(self):
+        return self.downscale_layer if self.vision_model_name == "resnet50" else self.upscale_layer
+
+    def _feature_dict(self, feats):
         d = defaultdict()
-        d["features"] = feats
-        return logp, loss, d
+        d["features"] = feats["features"]            # backbone map [B, C, h, w] fp32 (model/resnet_vqa_model.py:189,201)
+        return d
+
+
+class FasterRcnnVQAModel(_VQAModelBase):
+    """`fasterrcnn_resnet50_fpn().backbone` (frozen, eval; FrozenBatchNorm ResNet-50 + FPN) -> its 'pool' level (256 channels)
+    -> ConvTranspose2d 256->768 -> tokens; the same T5 / SGA / pooler / classifier head (model/faster_rcnn_vqa_model.py:28-197).
+    generate_answers returns the FPN's five feature maps ('0'..'3', 'pool'), fp32 NCHW."""
+
+    def __init__(self, vision_model_name: str, language_model_name: str, answer_spaces: int,
+                 fine_tune_lm_encoder: bool = True, fine_tune_lm_decoder: bool = True,
+                 fine_tune_vision: bool = True, num_attention_blocks=3, device="cpu"):
+        super().__init__()
+        if vision_model_name != "faster-rcnn":
+            raise ValueError("vision_model_name must be 'faster-rcnn'")
+        self._init_common(vision_model_name, language_model_name, answer_spaces, fine_tune_lm_encoder,
+                          fine_tune_lm_decoder, fine_tune_vision, num_attention_blocks, device)
+
+    def _build_vision(self):
+        self.vision_model = M.BackboneWithFPN()
+
+    def _build_scalers(self):
+        self.upscale_layer = M.ConvTranspose2d(256, 768, 3)
+
+    def _resnet_body(self):
+        return self.vision_model.body
+
+    def _fpn(self):
+        return self.vision_model.fpn
+
+    def _projection(self):
+        return self.upscale_layer
+
+    def _feature_dict(self, feats):
+        d = defaultdict()
+        for k in ("0", "1", "2", "3", "pool"):       # model/faster_rcnn_vqa_model.py:150-154
+            d[k] = feats[k]
+        return d

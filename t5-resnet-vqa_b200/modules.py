@@ -279,3 +279,94 @@ class AttentionPooler(_Holder):
         super().__init__()
         self.hidden_size = hidden_size
         self.attention = nn.ModuleList([Linear(hidden_size, 1)])  # key: attention.0.{weight,bias}
+
+
+# ------------------------------------------------------------------------------------------------
+# Faster R-CNN backbone: ResNet-50 body with FrozenBatchNorm2d + FeaturePyramidNetwork (torchvision key layout of
+# `fasterrcnn_resnet50_fpn(pretrained=True).backbone`, model/faster_rcnn_vqa_model.py:51-53)
+# ------------------------------------------------------------------------------------------------
+class FrozenBatchNorm2d(_Holder):
+    """torchvision.ops.misc.FrozenBatchNorm2d: weight / bias / running statistics are BUFFERS (no num_batches_tracked)."""
+
+    def __init__(self, c, eps=1e-5):
+        super().__init__()
+        self.num_features, self.eps = c, eps
+        self.register_buffer("weight", torch.ones(c))
+        self.register_buffer("bias", torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+
+
+class Conv2dBias(_Holder):
+    """Conv2d with bias and no norm (the FPN's lateral / output convs); torchvision FPN init: kaiming_uniform_(a=1), bias 0."""
+
+    def __init__(self, cin, cout, k, stride=1, padding=0):
+        super().__init__()
+        self.in_channels, self.out_channels = cin, cout
+        self.kernel_size, self.stride, self.padding = k, stride, padding
+        bound = math.sqrt(3.0 / (cin * k * k))      # gain sqrt(2 / (1 + a^2)) = 1 with a = 1
+        self.weight = nn.Parameter(torch.empty(cout, cin, k, k).uniform_(-bound, bound))
+        self.bias = nn.Parameter(torch.zeros(cout))
+
+
+class _FrozenBottleneck(_Holder):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = Conv2d(inplanes, planes, 1)
+        self.bn1 = FrozenBatchNorm2d(planes)
+        self.conv2 = Conv2d(planes, planes, 3, stride, 1)
+        self.bn2 = FrozenBatchNorm2d(planes)
+        self.conv3 = Conv2d(planes, planes * 4, 1)
+        self.bn3 = FrozenBatchNorm2d(planes * 4)
+        self.downsample = downsample
+        self.stride = stride
+
+
+class ResNet50Body(_Holder):
+    """IntermediateLayerGetter(resnet50(norm_layer=FrozenBatchNorm2d), layer1..4): no avgpool / fc."""
+
+    def __init__(self):
+        super().__init__()
+        self.block_type = _FrozenBottleneck
+        self.inplanes = 64
+        self.conv1 = Conv2d(3, 64, 7, 2, 3)
+        self.bn1 = FrozenBatchNorm2d(64)
+        self.layer1 = self._make_layer(64, 3, 1)
+        self.layer2 = self._make_layer(128, 4, 2)
+        self.layer3 = self._make_layer(256, 6, 2)
+        self.layer4 = self._make_layer(512, 3, 2)
+        self.out_channels = 2048
+        # fasterrcnn_resnet50_fpn(pretrained=True): trainable_backbone_layers = 3 -> conv1 and layer1 are frozen
+        for mod in (self.conv1, self.layer1):
+            for p in mod.parameters():
+                p.requires_grad_(False)
+
+    def _make_layer(self, planes, n, stride):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * 4:
+            downsample = _Seq(Conv2d(self.inplanes, planes * 4, 1, stride, 0), FrozenBatchNorm2d(planes * 4))
+        blocks = [_FrozenBottleneck(self.inplanes, planes, stride, downsample)]
+        self.inplanes = planes * 4
+        for _ in range(1, n):
+            blocks.append(_FrozenBottleneck(self.inplanes, planes))
+        return _Seq(*blocks)
+
+
+class FeaturePyramidNetwork(_Holder):
+    def __init__(self, in_channels=(256, 512, 1024, 2048), out_channels=256):
+        super().__init__()
+        self.inner_blocks = nn.ModuleList([_Seq(Conv2dBias(c, out_channels, 1)) for c in in_channels])
+        self.layer_blocks = nn.ModuleList([_Seq(Conv2dBias(out_channels, out_channels, 3, 1, 1)) for _ in in_channels])
+        self.out_channels = out_channels
+
+
+class BackboneWithFPN(_Holder):
+    """`fasterrcnn_resnet50_fpn(pretrained=True).backbone`: keys body.* and fpn.{inner,layer}_blocks.N.0.{weight,bias}."""
+
+    def __init__(self):
+        super().__init__()
+        self.body = ResNet50Body()
+        self.fpn = FeaturePyramidNetwork()
+        self.out_channels = 256

@@ -97,7 +97,9 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
     # frozen ResNet body (tv:266-277 without avgpool/fc), NHWC bf16, BatchNorm folded
     # =============================================================================================
     two_lanes = eng.use_lanes
-    vm = m.vision_model
+    vm = m._resnet_body()
+    fpn = m._fpn()
+    levels = []     # (map, C, H, W) after layer1..4: the FPN's inputs
     stem_in = al(B, H, W + 8, 8)
     if u8_images:
         r.image_u8_to_stem(st.images, stem_in, B, H, W)
@@ -145,11 +147,48 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
                 r.conv(B, Ho, Wo, planes, Cout, 3, 1, 1, t1, eng.vw[pre + "conv2"], y, bias=eng.vb[pre + "conv2"],
                        residual=idn, relu=1)
             x, C, Hc, Wc = y, Cout, Ho, Wo
-    feat, Cf, Hf, Wf = x, C, Hc, Wc
+        levels.append((x, C, Hc, Wc))
+    st.features = {}
+
+    def export(name, t, c, h, w):
+        st.features[name] = al(B, c, h, w, dtype=f32)
+        r.nhwc_to_nchw_f32(t, st.features[name], B, h, w, c)
+
+    if fpn is None:
+        feat, Cf, Hf, Wf = x, C, Hc, Wc
+        if want_features:
+            export("features", feat, Cf, Hf, Wf)
+    else:
+        # FeaturePyramidNetwork + LastLevelMaxPool (torchvision feature_pyramid_network.py; the reference uses its 'pool'
+        # output, model/faster_rcnn_vqa_model.py:102-108).  The top level receives no top-down term, and
+        # max_pool2d(kernel 1, stride 2) of its 3x3 output conv is that conv evaluated at stride 2: two launches.
+        Fo = fpn.out_channels
+        c5, C5, H5, W5 = levels[3]
+        inner = al(B, H5, W5, Fo)
+        r.conv(B, H5, W5, C5, Fo, 1, 1, 0, c5, eng.vw["fpn.inner3"], inner, bias=eng.vb["fpn.inner3"], relu=0)
+        Hp, Wp = (H5 + 2 - 3) // 2 + 1, (W5 + 2 - 3) // 2 + 1
+        pool = al(B, Hp, Wp, Fo)
+        r.conv(B, H5, W5, Fo, Fo, 3, 2, 1, inner, eng.vw["fpn.layer3"], pool, bias=eng.vb["fpn.layer3"], relu=0)
+        feat, Cf, Hf, Wf = pool, Fo, Hp, Wp
+        if want_features:     # generate_answers returns all five maps (model/faster_rcnn_vqa_model.py:150-154)
+            export("pool", pool, Fo, Hp, Wp)
+            out3 = al(B, H5, W5, Fo)
+            r.conv(B, H5, W5, Fo, Fo, 3, 1, 1, inner, eng.vw["fpn.layer3"], out3, bias=eng.vb["fpn.layer3"], relu=0)
+            export("3", out3, Fo, H5, W5)
+            last, hl, wl = inner, H5, W5
+            for idx in (2, 1, 0):
+                ci, Ci, Hi, Wi = levels[idx]
+                up = al(B, Hi, Wi, Fo)
+                r.upsample_nearest_nhwc(last, up, B, hl, wl, Hi, Wi, Fo)
+                lat = al(B, Hi, Wi, Fo)
+                r.conv(B, Hi, Wi, Ci, Fo, 1, 1, 0, ci, eng.vw["fpn.inner%d" % idx], lat, bias=eng.vb["fpn.inner%d" % idx],
+                       residual=up, relu=0)
+                oi = al(B, Hi, Wi, Fo)
+                r.conv(B, Hi, Wi, Fo, Fo, 3, 1, 1, lat, eng.vw["fpn.layer%d" % idx], oi, bias=eng.vb["fpn.layer%d" % idx],
+                       relu=0)
+                export(str(idx), oi, Fo, Hi, Wi)
+                last, hl, wl = lat, Hi, Wi
     st.feat_shape = (B, Cf, Hf, Wf)
-    if want_features:
-        st.features = al(B, Cf, Hf, Wf, dtype=f32)
-        r.nhwc_to_nchw_f32(feat, st.features, B, Hf, Wf, Cf)
 
     # channel projection = ConvTranspose2d(k3,s1,p1) as a 3x3 same conv with flipped/transposed weights
     # (model/resnet_vqa_model.py:124,135) writing [B*hw, 768] tokens directly (:142-143)

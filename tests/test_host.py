@@ -32,6 +32,27 @@ def test_state_dict_layout_matches_reference(model):
     assert torch.equal(model.state_dict()["sga_modules.1.mhatt2.linear_k.bias"], ref["sga_modules.1.mhatt2.linear_k.bias"])
 
 
+def test_faster_rcnn_state_dict_layout_matches_reference(pkg):
+    """FasterRcnnVQAModel: the state_dict the unmodified reference class produced when tests/golden/frcnn_*.pt were made
+    (torchvision BackboneWithFPN with FrozenBatchNorm2d + the shared head), key for key, and strict loading both ways."""
+    import torch
+    from oracle import vqa_oracle as O
+    os.environ["VQA_B200_PRETRAINED"] = "0"
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frcnn_b2_256_l16.pt"),
+                      weights_only=False)
+    m = pkg.FasterRcnnVQAModel("faster-rcnn", "t5-base", answer_spaces=170)
+    assert list(m.state_dict().keys()) == gold["state_dict_keys"] and len(gold["state_dict_keys"]) == 464
+    sd = O.random_state_dict("faster-rcnn", 170, seed=0)
+    assert list(sd.keys()) == gold["state_dict_keys"]
+    m.load_state_dict(sd, strict=True)
+    assert all(torch.equal(v, sd[k]) for k, v in m.state_dict().items())
+    frozen = [k for k, p in m.named_parameters() if not p.requires_grad]
+    assert frozen and all(k.startswith(("vision_model.body.conv1", "vision_model.body.layer1")) for k in frozen)
+    assert m._projection() is m.upscale_layer and not hasattr(m, "downscale_layer")
+    with pytest.raises(ValueError):
+        pkg.FasterRcnnVQAModel("resnet50", "t5-base", answer_spaces=170)
+
+
 def test_trainer_facing_attributes(model):
     for name in ("vision_model", "lang_model", "upscale_layer", "downscale_layer", "sga_modules", "attention_pooler",
                  "classification_layer"):

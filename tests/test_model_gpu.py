@@ -24,7 +24,8 @@ LOGP_REL, LOSS_REL, TOP1, GRAD_COS = 2e-2, 1e-3, 0.99, 0.999
 
 def build(pkg, vision, sd, device, train=False):
     os.environ["VQA_B200_PRETRAINED"] = "0"
-    m = pkg.ResnetVQAModel(vision, "t5-base", answer_spaces=170)
+    cls = pkg.FasterRcnnVQAModel if vision == "faster-rcnn" else pkg.ResnetVQAModel
+    m = cls(vision, "t5-base", answer_spaces=170)
     m.load_state_dict(sd, strict=True)
     m.to(device)
     m.train(train)
@@ -70,7 +71,8 @@ def check_outputs(logp, loss, ref_logp, ref_loss, name=""):
     return agree
 
 
-@pytest.mark.parametrize("case", ["r34_b4", "r50_b2_masked", "r18_b2_256_l16", "r50_b64", "r50_b64_masked"])
+@pytest.mark.parametrize("case", ["r34_b4", "r50_b2_masked", "r18_b2_256_l16", "r50_b64", "r50_b64_masked",
+                                  "r34_b2_448", "frcnn_b2_256_l16", "frcnn_b2_448"])
 def test_parity_with_reference_golden_and_oracle(pkg, cuda, case):
     from oracle import vqa_oracle as O
     gold = torch.load(os.path.join(GOLD, case + ".pt"), weights_only=False)
@@ -111,6 +113,28 @@ def test_parity_with_reference_golden_and_oracle(pkg, cuda, case):
     report(case + ":grad_cosine_summary", frac_ge_0p999=frac, worst=cos[0][0], median=cos[len(cos) // 2][0])
     assert cos[0][0] >= GRAD_COS, cos[:5]            # the north-star bar, on every tensor
     assert cos[len(cos) // 2][0] >= 0.9998, cos[len(cos) // 2]
+
+
+def test_faster_rcnn_generate_answers_returns_the_fpn_maps(pkg, cuda):
+    """FasterRcnnVQAModel.generate_answers (model/faster_rcnn_vqa_model.py:128-197): log-probs as forward, plus the FPN's five
+    feature maps ('0'..'3', 'pool') as fp32 NCHW, against the oracle's restatement of torchvision's BackboneWithFPN."""
+    from oracle import vqa_oracle as O
+    sd = O.random_state_dict("faster-rcnn", 170, seed=0)
+    batch = O.synthetic_batch(2, 16, 256, 256, 170, seed=3)
+    m = build(pkg, "faster-rcnn", sd, cuda)
+    kw = {k: v.to(cuda) for k, v in batch.items()}
+    with torch.no_grad():
+        logp, loss, d = m.generate_answers(kw["question_input_ids"], None, kw["question_attention_masks"], None,
+                                           kw["image_tensors"], annotation_ids=kw["annotation_ids"])
+        logp_f, loss_f = run(m, batch, cuda)
+    assert torch.equal(logp, logp_f) and torch.equal(loss, loss_f)
+    o_logp, o_loss, feats = O.forward(sd, "faster-rcnn", batch["question_input_ids"], batch["question_attention_masks"],
+                                      batch["annotation_ids"], batch["image_tensors"], return_features=True)
+    assert sorted(d.keys()) == ["0", "1", "2", "3", "pool"]
+    for k, ref in feats.items():
+        assert d[k].shape == ref.shape and d[k].dtype == torch.float32, k
+        assert float((d[k].cpu() - ref).norm() / ref.norm()) < 3e-2, k
+    check_outputs(logp, loss, o_logp.detach(), o_loss.detach(), "frcnn_generate_answers")
 
 
 def test_generate_answers_features_and_eval_determinism(pkg, cuda):

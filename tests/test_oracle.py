@@ -8,7 +8,7 @@ import torch
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("case", ["r34_b4", "r18_b2_256_l16", "r50_b2_masked", "r50_b64"])
+@pytest.mark.parametrize("case", ["r34_b4", "r18_b2_256_l16", "r50_b2_masked", "r50_b64", "r34_b2_448", "frcnn_b2_256_l16", "frcnn_b2_448"])
 def test_oracle_matches_reference_golden(case):
     from oracle import vqa_oracle as O
     gold = torch.load(os.path.join(GOLD, case + ".pt"), weights_only=False)
@@ -24,6 +24,7 @@ def test_oracle_matches_reference_golden(case):
     trainable = set(grads)
     assert all(k.startswith("vision_model.") or k.startswith(("upscale_layer.", "downscale_layer."))
                for k in gold["grad_none"])
+    noise = 1e-6 * max(gold["grad_norm"].values())
     assert not (trainable & set(gold["grad_none"]))
     scale = max(gold["grad_norm"].values())
     for k, g in grads.items():
@@ -31,6 +32,8 @@ def test_oracle_matches_reference_golden(case):
         assert abs(float(g.norm()) - n_ref) <= 1e-4 * n_ref + 1e-6 * scale, k
         f = g.flatten()
         s = f if f.numel() <= 2304 else f[::f.numel() // 128][:128]
+        # (the detector backbone's FrozenBatchNorm2d and eval BatchNorm differ in rounding: tensors whose gradient is
+        # mathematically zero - linear_k.bias, softmax shift invariance - hold different rounding noise)
         assert torch.allclose(s, gold["grad_sample"][k], rtol=1e-3, atol=1e-6 * scale), k
 
 
