@@ -15,7 +15,7 @@
 using namespace vqa;
 
 namespace vqa {
-// attention_tc.cu: tcgen05 flash kernels for Lq, Lk <= 32
+// attention_tc.cu: tcgen05 flash kernels for Lq, Lk <= 64
 bool attention_tc_supported(int Lq, int Lk, int hd);
 int attention_tc_fwd(void* plan, const vqa_attn_fwd_args* x, void* stream);
 int attention_tc_bwd(void* plan, const vqa_attn_bwd_args* x, void* stream);
@@ -302,10 +302,12 @@ inline size_t bwd_smem(int hd, int Lk) {
   return static_cast<size_t>(2 * kMaxLq + 2 * Lk) * RW * 4 + static_cast<size_t>(2 * kMaxLq) * (Lk | 1) * 4;
 }
 
+// tc: the tcgen05 flash kernels will take the call (they carry up to 64 query rows; the SIMT kernel kMaxLq = 32)
 inline int check_common(int Lq, int Lk, int hd, long long l0, long long l1, long long l2, long long l3,
-                        const char* what) {
+                        const char* what, bool tc) {
   if (hd != 64 && hd != 96) { set_last_error("%s: head dim must be 64 or 96 (got %d)", what, hd); return -1; }
-  if (Lq < 1 || Lq > kMaxLq) { set_last_error("%s: Lq must be in [1, %d] (got %d)", what, kMaxLq, Lq); return -1; }
+  const int max_lq = tc ? 64 : kMaxLq;
+  if (Lq < 1 || Lq > max_lq) { set_last_error("%s: Lq must be in [1, %d] (got %d)", what, max_lq, Lq); return -1; }
   if (Lk < 1 || Lk > 512) { set_last_error("%s: Lk must be in [1, 512] (got %d)", what, Lk); return -1; }
   if ((l0 | l1 | l2 | l3) & 7) { set_last_error("%s: row strides must be multiples of 8 elements", what); return -1; }
   return 0;
@@ -334,8 +336,9 @@ int vqa_debug_attn_timing(long long* buf) {
 }
 
 int vqa_attention_fwd(void* plan, const vqa_attn_fwd_args* x, void* stream) {
-  if (check_common(x->Lq, x->Lk, x->hd, x->ldq, x->ldk, x->ldv, x->ldo, "attention_fwd")) return -1;
-  if (x->stats != nullptr && attention_tc_supported(x->Lq, x->Lk, x->hd)) return attention_tc_fwd(plan, x, stream);
+  const bool tc = x->stats != nullptr && attention_tc_supported(x->Lq, x->Lk, x->hd);
+  if (check_common(x->Lq, x->Lk, x->hd, x->ldq, x->ldk, x->ldv, x->ldo, "attention_fwd", tc)) return -1;
+  if (tc) return attention_tc_fwd(plan, x, stream);
   FwdArgs a;
   a.B = x->B; a.H = x->H; a.Lq = x->Lq; a.Lk = x->Lk;
   a.q = static_cast<const __nv_bfloat16*>(x->q); a.k = static_cast<const __nv_bfloat16*>(x->k);
@@ -358,9 +361,10 @@ int vqa_attention_fwd(void* plan, const vqa_attn_fwd_args* x, void* stream) {
 }
 
 int vqa_attention_bwd(void* plan, const vqa_attn_bwd_args* x, void* stream) {
-  if (check_common(x->Lq, x->Lk, x->hd, x->ldq, x->ldk, x->ldv, x->ldo, "attention_bwd")) return -1;
+  const bool tc = x->stats != nullptr && attention_tc_supported(x->Lq, x->Lk, x->hd);
+  if (check_common(x->Lq, x->Lk, x->hd, x->ldq, x->ldk, x->ldv, x->ldo, "attention_bwd", tc)) return -1;
   if ((x->lddq | x->lddk | x->lddv) & 7) { set_last_error("attention_bwd: gradient strides must be multiples of 8"); return -1; }
-  if (x->stats != nullptr && attention_tc_supported(x->Lq, x->Lk, x->hd)) return attention_tc_bwd(plan, x, stream);
+  if (tc) return attention_tc_bwd(plan, x, stream);
   if (x->probs == nullptr) { set_last_error("attention_bwd: the SIMT kernel needs the saved probabilities"); return -1; }
   BwdArgs a;
   a.B = x->B; a.H = x->H; a.Lq = x->Lq; a.Lk = x->Lk;

@@ -139,7 +139,7 @@ def test_trainer_drives_three_steps(pkg, cuda):
             continue
         assert float(da.norm()) > 0, k
         moved += 1
-        if k.endswith("linear_k.bias"):
+        if k.endswith("linear_k.bias") or k == "attention_pooler.attention.0.bias":
             continue       # gradient is mathematically zero (softmax is shift invariant): Adam normalises pure rounding noise
         assert float((da - db).norm()) <= 0.05 * float(da.norm()), (k, float((da - db).norm() / da.norm()))
     assert moved == 183
