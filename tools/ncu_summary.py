@@ -2,7 +2,7 @@
 of `ncu --set full` captures (.ncu-rep), as markdown.
 
     python tools/ncu_summary.py launches gpurun_out/launches.csv > profiles/rN_launches_summary.md
-    python tools/ncu_summary.py full gpurun_out/prof.ncu-rep [...] > profiles/rN_ncu_full_summary.md
+    python tools/ncu_summary.py full gpurun_out/prof.ncu-rep|raw.csv [...] > profiles/rN_ncu_full_summary.md
 """
 import csv
 import re
@@ -52,7 +52,10 @@ WANT = [
 
 def full(paths):
     for path in paths:
-        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        if path.endswith(".csv"):      # already exported on the GPU box with `ncu -i rep --page raw --csv` (reports are large)
+            out = open(path, errors="replace").read()
+        else:
+            out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(out.splitlines()))
         h, units = rows[0], rows[1]
         cols = [(h.index(m), lbl, m) for m, lbl in WANT if m in h]
