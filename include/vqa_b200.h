@@ -155,6 +155,8 @@ int vqa_fold_conv_bn(void* plan, const float* w, const float* gamma, const float
 /* ConvTranspose2d weight [Cin,Cout,3,3] fp32 -> equivalent Conv2d weight bf16 [Cout, 3,3, Cin] with the
  * taps flipped; and the inverse mapping of its fp32 gradient (model/resnet_vqa_model.py:64-78). */
 int vqa_convT_weight_prep(void* plan, const float* w, void* w_out, int Cin, int Cout, void* stream);
+/* same, from the bf16 shadow of the weight (identical result: the shadow is bf16_rn of the fp32 weight) */
+int vqa_convT_weight_prep_bf16(void* plan, const void* w_bf16, void* w_out, int Cin, int Cout, void* stream);
 int vqa_convT_wgrad_unprep(void* plan, const float* dw_conv, float* dw, int Cin, int Cout, void* stream);
 /* images fp32 [N,3,H,W] -> bf16 [N,H,W+8,8] (stem layout); bf16 NHWC -> fp32 NCHW feature map */
 int vqa_image_to_stem(void* plan, const float* img, void* out, int N, int H, int W, void* stream);
@@ -174,6 +176,13 @@ int vqa_embedding_fwd(void* plan, const long long* ids, const float* table, floa
                       int vocab, float drop_p, uint32_t sid, const uint64_t* rng, void* stream);
 int vqa_embedding_bwd(void* plan, const long long* ids, const float* dout, float* dtable, int M, int D,
                       int vocab, float drop_p, uint32_t sid, const uint64_t* rng, void* stream);
+/* Data-parallel form of embedding_bwd: rows[t,:] = scale * dropout(dout[t,:]) leave the rank (all-gather with the ids), and
+ * every rank scatter-adds all ranks' rows into its zeroed dtable in ONE fixed order (token index), without atomics, so the
+ * replicas' embedding gradients are bit-identical.  first_ws: int[vocab] scratch.  (New work: the reference is single-device.) */
+int vqa_embedding_bwd_rows(void* plan, const float* dout, float* rows, int M, int D, float drop_p, uint32_t sid,
+                           const uint64_t* rng, float scale, void* stream);
+int vqa_embedding_scatter_ordered(void* plan, const long long* ids, const float* rows, float* dtable, int* first_ws, int T,
+                                  int D, int vocab, void* stream);
 /* T5LayerNorm (hf:55-68): y = w * x * rsqrt(mean(x^2) + eps), then optional dropout (hf:768).
  * y_bf16 and/or y_f32 may be NULL.  Backward: dx = (dres?) + d/dx, dw += sum_rows (atomic). */
 int vqa_rmsnorm_fwd(void* plan, const float* x, const float* w, void* y_bf16, float* y_f32,

@@ -121,14 +121,14 @@ __global__ void fold_conv_bn_kernel(const float* __restrict__ w, const float* __
 // ---- ConvTranspose2d weight views -------------------------------------------------------------
 // src fp32 [R0, C0] (C0 = G*9) -> dst [C0 (with tap flip inside each group of 9), R0]
 //   dst[(g*9 + 8 - t), r] = src[r, g*9 + t]
-template <typename TOut>
-__global__ void transpose_flip9_kernel(const float* __restrict__ src, TOut* __restrict__ dst, int R0, int C0) {
+template <typename TOut, typename TIn = float>
+__global__ void transpose_flip9_kernel(const TIn* __restrict__ src, TOut* __restrict__ dst, int R0, int C0) {
   pdl_grid_sync();
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int r = r0 + j, c = c0 + threadIdx.x;
-    tile[j][threadIdx.x] = (r < R0 && c < C0) ? src[static_cast<long long>(r) * C0 + c] : 0.f;
+    tile[j][threadIdx.x] = (r < R0 && c < C0) ? static_cast<float>(src[static_cast<long long>(r) * C0 + c]) : 0.f;
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -411,6 +411,16 @@ int vqa_convT_weight_prep(void* plan, const float* w, void* w_out, int Cin, int 
     dim3 grid((Cout * 9 + 31) / 32, (Cin + 31) / 32), block(32, 8);
     launch_pdl(transpose_flip9_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, s, w, static_cast<__nv_bfloat16*>(w_out), Cin, Cout * 9);
     return launch_status("convT_weight_prep");
+  });
+}
+
+int vqa_convT_weight_prep_bf16(void* plan, const void* w_bf16, void* w_out, int Cin, int Cout, void* stream) {
+  note_op("convT_weight_prep", 0.0, 0.0);
+  return submit(plan, stream, [=](cudaStream_t s) {
+    dim3 grid((Cout * 9 + 31) / 32, (Cin + 31) / 32), block(32, 8);
+    launch_pdl(transpose_flip9_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(grid), dim3(block), 0, s,
+               static_cast<const __nv_bfloat16*>(w_bf16), static_cast<__nv_bfloat16*>(w_out), Cin, Cout * 9);
+    return launch_status("convT_weight_prep_bf16");
   });
 }
 

@@ -322,6 +322,9 @@ class Engine:
         # of the flat random-init classifier then agree with fp32 closely enough for >= 99 % top-1 agreement with margin
         self.split_head = _env_flag("VQA_B200_SPLIT_HEAD", True)
         self._ddp = None
+        self.ddp_shards = None      # sharded data parallelism: [(lo, big_hi, own_lo, own_hi)] of the CURRENT step, else None
+        self.master_stale = False   # fp32 master of the GEMM weights is current only on the owning rank (ddp.py)
+        self.master_shards = None
         self.fused_opt = None       # weakref to a VQAFusedAdamW that updates every parameter of this engine
         self.pending_clip = None    # max_norm of a clip_grad_norm_ whose scaling the fused optimizer will apply
         self.clip_sumsq = None      # device scalar: sum of squared gradients of the last clip_grad_norm_
@@ -540,9 +543,17 @@ class Engine:
         self.lo_fresh = False
         self.vision_sig = None
 
+    def sync_master(self):
+        """Sharded data parallelism: make the fp32 master copy of every parameter current on this rank (COLLECTIVE: all
+        ranks must call it).  No-op otherwise.  Runs before state_dict(); call it before reading parameter values."""
+        if self.master_stale and self._ddp is not None:
+            self._ddp.sync_master(self)
+
     def _refresh_shadow(self):
         """bf16 copies of the fp32 master weights (what the GEMMs read), on the current stream.  Only needed when
         something other than the fused optimizer changed the parameters (it writes the shadow itself)."""
+        if self.shadow_stale and self.master_stale:
+            self.sync_master()     # (all ranks take this branch together: they changed the same parameters)
         if self.shadow_stale:
             self.rec(None).cast_f32_bf16(self.master, self.shadow, self.total)
             self.shadow_stale = False
@@ -557,7 +568,10 @@ class Engine:
         if self.proj_dirty:
             proj = self.model._projection()
             Cin, Cout = proj.weight.shape[0], proj.weight.shape[1]
-            self.rec(None).convT_weight_prep(self.mp(proj.weight), self.proj_w, Cin, Cout)
+            if self.master_stale:     # sharded update: the gathered bf16 shadow is the current copy on every rank
+                self.rec(None).convT_weight_prep_bf16(self.sp(proj.weight), self.proj_w, Cin, Cout)
+            else:
+                self.rec(None).convT_weight_prep(self.mp(proj.weight), self.proj_w, Cin, Cout)
             self.proj_dirty = False
 
     # ------------------------------------------------------------------------------------------
@@ -584,7 +598,7 @@ class Engine:
     def refresh_lo_after_update(self, stream):
         """Low-order halves of the split-precision weights, recomputed right behind the fused optimizer pass on ITS stream
         (None: the current one), i.e. off the next forward's critical path (which waits for the optimizer event anyway)."""
-        if not self.lo_ranges or self.lo_fresh or not self.shadow_fresh:
+        if not self.lo_ranges or self.lo_fresh or not self.shadow_fresh or self.master_stale:
             return
         rec = _Rec(self.lib, None, (lambda: stream.cuda_stream) if stream is not None else self._stream)
         for lo0, lo1 in self.lo_ranges:

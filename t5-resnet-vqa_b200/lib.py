@@ -87,6 +87,7 @@ SIGNATURES = {
     "vqa_axpy_f32": (c_int, [_P, _P, _P, c_f, c_ll, _P]),
     "vqa_fold_conv_bn": (c_int, [_P, _P, _P, _P, _P, _P, c_f, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "vqa_convT_weight_prep": (c_int, [_P, _P, _P, c_int, c_int, _P]),
+    "vqa_convT_weight_prep_bf16": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "vqa_convT_wgrad_unprep": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "vqa_image_to_stem": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
     "vqa_image_u8_to_stem": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P]),
@@ -95,6 +96,8 @@ SIGNATURES = {
     "vqa_maxpool3x3s2": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "vqa_embedding_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_f, c_u32, _P, _P]),
     "vqa_embedding_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_f, c_u32, _P, _P]),
+    "vqa_embedding_bwd_rows": (c_int, [_P, _P, _P, c_int, c_int, c_f, c_u32, _P, c_f, _P]),
+    "vqa_embedding_scatter_ordered": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "vqa_rmsnorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_f, c_f, c_u32, _P, _P]),
     "vqa_rmsnorm_fwd_split": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_f, _P]),
     "vqa_rmsnorm_bwd": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_f, c_u32, _P, _P, c_f, c_u32,

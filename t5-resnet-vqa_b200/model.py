@@ -101,7 +101,8 @@ class _VQAModelBase(nn.Module):
         object.__setattr__(self, "_engine", Engine(self))
         # the fused optimizer may still be running on its own stream: anything that reads the parameters through
         # state_dict() (checkpoints, trainer/callbacks.py:34-46) is ordered after it
-        self.register_state_dict_pre_hook(lambda module, prefix, keep_vars: module._engine.wait_optimizer())
+        self.register_state_dict_pre_hook(lambda module, prefix, keep_vars: (module._engine.wait_optimizer(),
+                                                                              module._engine.sync_master()))
         self._load_pretrained()
 
     # the reference always starts from pretrained torchvision / HF weights (model/resnet_vqa_model.py:51-62);

@@ -185,19 +185,31 @@ class VQAFusedAdamW(torch.optim.Optimizer):
             r_gnorm, r_max = gnorm_ptr, self.max_grad_norm
             if eng is not None and eng.pending_clip is not None:   # clip_grad_norm_ deferred its scaling to us
                 r_gnorm, r_max = eng.clip_sumsq.data_ptr(), eng.pending_clip
-            L.check(lib.vqa_adamw_amsgrad(
-                None, r["p0"], r["g0"], r["m"].data_ptr(), r["v"].data_ptr(),
-                r["vmax"].data_ptr() if r["vmax"] is not None else None, r["shadow"], r["n"],
-                float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                1.0 - b1 ** t, 1.0 - b2 ** t, r_gnorm,
-                float(r_max) if r_max is not None else 0.0,
-                int(bool(group["amsgrad"])), s), "adamw")
+            # sharded data parallelism (ddp.py): of a range of GEMM weights only this rank's slices are updated
+            spans = [(0, r["n"])]
+            if eng is not None and eng.ddp_shards is not None:
+                e0 = (r["p0"] - eng.master.data_ptr()) // 4
+                if e0 < eng.n_big:
+                    spans = [(max(olo, e0) - e0, min(ohi, e0 + r["n"]) - e0) for _, _, olo, ohi in eng.ddp_shards
+                             if max(olo, e0) < min(ohi, e0 + r["n"])]
+            for a0, a1 in spans:
+                L.check(lib.vqa_adamw_amsgrad(
+                    None, r["p0"] + 4 * a0, r["g0"] + 4 * a0, r["m"].data_ptr() + 4 * a0, r["v"].data_ptr() + 4 * a0,
+                    r["vmax"].data_ptr() + 4 * a0 if r["vmax"] is not None else None,
+                    r["shadow"] + 2 * a0 if r["shadow"] is not None else None, a1 - a0,
+                    float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                    1.0 - b1 ** t, 1.0 - b2 ** t, r_gnorm,
+                    float(r_max) if r_max is not None else 0.0,
+                    int(bool(group["amsgrad"])), s), "adamw")
             if r["engine"] is not None:
                 engines[r["engine"]] = engines.get(r["engine"], 0) + len(r["params"])
         for eng, covered in engines.items():
             eng.note_fused_update(covered)
             eng.pending_clip = None
-            if covered == len(eng.params):
+            if eng.ddp_shards is not None:
+                eng._ddp.after_update(eng, side.get(eng))     # low-order halves of the own slices + all-gather of the weights
+                eng.ddp_shards = None                         # belongs to the backward pass that produced these gradients
+            elif covered == len(eng.params):
                 eng.refresh_lo_after_update(side.get(eng))
             if side.get(eng) is not None:
                 eng.note_optimizer_launched(side[eng])
@@ -267,7 +279,16 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0, error_if_nonfinite=Fals
     sq = eng.clip_sumsq
     s = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     sq.zero_()
-    L.check(lib.vqa_sumsq_f32(None, eng.grad.data_ptr(), eng.total, sq.data_ptr(), s), "sumsq")
+    if eng.ddp_shards is not None:
+        # sharded data parallelism: this rank holds the averaged gradient of its slices of the GEMM weights (partial sums
+        # meet in a scalar all-reduce) and of all the replicated small tensors (counted once, after the reduction)
+        import torch.distributed as dist
+        for _, _, olo, ohi in eng.ddp_shards:
+            L.check(lib.vqa_sumsq_f32(None, eng.grad.data_ptr() + 4 * olo, ohi - olo, sq.data_ptr(), s), "sumsq")
+        dist.all_reduce(sq, op=dist.ReduceOp.SUM, group=eng._ddp.group)
+        L.check(lib.vqa_sumsq_f32(None, eng.grad.data_ptr() + 4 * eng.n_big, eng.total - eng.n_big, sq.data_ptr(), s), "sumsq")
+    else:
+        L.check(lib.vqa_sumsq_f32(None, eng.grad.data_ptr(), eng.total, sq.data_ptr(), s), "sumsq")
     opt = eng.fused_opt() if eng.fused_opt is not None else None
     if opt is not None and os.environ.get("VQA_B200_DEFER_CLIP", "1") != "0":
         eng.pending_clip = float(max_norm)

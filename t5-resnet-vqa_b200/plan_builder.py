@@ -567,7 +567,14 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
             r = eng.rec(bp, st.ks_store)
             side.bind(r)
     r.t5_bias_grad(dbias_pos, bucket, eng.gp(relw), nH, Lt, cfg["num_buckets"])
-    r.embedding_bwd(st.ids, dH, eng.gp(t5.embed_tokens.weight), M, D, vocab, p_t5, sid_embed, rng)
+    st.emb_rows = None
+    if eng._ddp is not None and eng._ddp.sparse_embedding:
+        # data parallel: the token rows leave the rank (scaled by 1 / world) instead of a dense 99 MB table; ddp.GradSync
+        # gathers every rank's (ids, rows) and scatters them into the zeroed table in one fixed order
+        st.emb_rows = al(M, D, dtype=f32)
+        r.embedding_bwd_rows(dH, st.emb_rows, M, D, p_t5, sid_embed, rng, 1.0 / eng._ddp.world)
+    else:
+        r.embedding_bwd(st.ids, dH, eng.gp(t5.embed_tokens.weight), M, D, vocab, p_t5, sid_embed, rng)
     close_segment(bp, seg_lo, eng.total)
     st.n_bwd_launches = sum(lib.vqa_plan_size(s.plan) for s in segs)
 

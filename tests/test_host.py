@@ -169,6 +169,31 @@ def _ddp_worker(rank, world, port, out):
     gathered = [torch.zeros_like(flat2) for _ in range(world)]
     dist.all_gather(gathered, flat2)
     ok = ok and all(torch.equal(gathered[0], t) for t in gathered)
+    # sharded optimizer: every segment's GEMM-weight range is split evenly over the ranks; the slices of all ranks tile it
+    import weakref
+
+    class Opt:
+        max_grad_norm = None
+    opt = Opt()
+
+    class Eng:
+        n_big = 64 * 30
+        fused_opt = weakref.ref(opt)
+
+    class St:
+        bwd_segments = [Seg(0, 64 * 8), Seg(64 * 8, 64 * 20), Seg(64 * 20, 64 * 30 + 500)]
+    sync = ddp.GradSync()
+    sh = sync.shards_for(Eng, St)
+    ok = ok and sh is not None and len(sh) == 3 and sh[2][1] == Eng.n_big
+    mine_sl = torch.tensor([[s[2], s[3]] for s in sh])
+    all_sl = [torch.zeros_like(mine_sl) for _ in range(world)]
+    dist.all_gather(all_sl, mine_sl)
+    for k, (lo, bhi, olo, ohi) in enumerate(sh):
+        cuts = sorted((int(a[k][0]), int(a[k][1])) for a in all_sl)
+        ok = ok and cuts[0][0] == lo and cuts[-1][1] == bhi and all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+        ok = ok and (ohi - olo) % 8 == 0
+    Eng.fused_opt = None
+    ok = ok and sync.shards_for(Eng, St) is None         # no fused optimizer over the engine: plain all-reduce
     out.put((rank, bool(ok)))
     dist.destroy_process_group()
 

@@ -78,17 +78,82 @@ def check(dev, rank, world, per=4, vision="resnet18"):
     return res
 
 
+def check_training(dev, rank, world, per=4, vision="resnet18", steps=3):
+    """`steps` training steps (dropout off, VQAFusedAdamW + clip) on `world` ranks - sharded optimizer when enabled - against
+    the same steps on one GPU over the concatenated batch: losses and the parameter updates must agree.  Returns (rank 0)
+    dict(mode, losses_ddp, losses_single, worst_update_rel_diff, ok)."""
+    os.environ.setdefault("VQA_B200_PRETRAINED", "0")
+    import t5_resnet_vqa_b200 as pkg
+    from oracle import vqa_oracle as O
+    sd = O.random_state_dict(vision, 170, seed=0)
+    full = O.synthetic_batch(per * world, 16, 64, 64, 170, seed=1, masked_tail=3)
+
+    def train(batch):
+        m = pkg.ResnetVQAModel(vision, "t5-base", 170)
+        m.load_state_dict(sd)
+        m.to(dev).eval()
+        opt = torch.optim.VQAFusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.1, amsgrad=True)
+        kw = {k: v.to(dev) for k, v in batch.items()}
+        losses = []
+        for _ in range(steps):
+            opt.zero_grad()
+            _, loss = m(kw["question_input_ids"], None, kw["question_attention_masks"], None, kw["annotation_ids"],
+                        kw["image_tensors"])
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+            opt.step()
+            losses.append(float(loss))
+        return m, losses
+    m, losses = train({k: v[rank * per:(rank + 1) * per] for k, v in full.items()})
+    sharded = bool(m._engine.master_stale)
+    t = torch.tensor(losses, device=dev)
+    dist.all_reduce(t)
+    losses_ddp = (t / world).tolist()
+    after = {k: v.detach().float().cpu().clone() for k, v in m.state_dict().items()}     # collective: gathers the master copies
+    res = None
+    if rank == 0:
+        old = os.environ.get("VQA_B200_DDP")
+        os.environ["VQA_B200_DDP"] = "0"
+        try:
+            m1, losses_1 = train(full)
+        finally:
+            if old is None:
+                del os.environ["VQA_B200_DDP"]
+            else:
+                os.environ["VQA_B200_DDP"] = old
+        ref = {k: v.detach().float().cpu() for k, v in m1.state_dict().items()}
+        worst, worst_k = 0.0, None
+        for k, v in ref.items():
+            if not v.is_floating_point() or k.startswith("vision_model."):
+                continue
+            if k.endswith("linear_k.bias") or k == "attention_pooler.attention.0.bias":
+                continue        # mathematically zero gradients: Adam normalises rounding noise
+            d0 = v - sd[k].float()
+            if float(d0.norm()) == 0.0:
+                continue
+            d = float(((after[k] - sd[k].float()) - d0).norm() / d0.norm())
+            if d > worst:
+                worst, worst_k = d, k
+        lrel = max(abs(a - b) / abs(b) for a, b in zip(losses_ddp, losses_1))
+        res = dict(world=world, sharded_optimizer=sharded, losses_ddp=losses_ddp, losses_single=losses_1,
+                   worst_update_rel_diff=worst, worst_tensor=worst_k, ok=bool(lrel < 5e-3 and worst < 0.1))
+    dist.barrier()
+    return res
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     res = check(dev, rank, world)
+    res2 = check_training(dev, rank, world)
     if rank == 0:
         print("ddp_check: %s" % res)
-        print("ddp_check OK" if res["ok"] else "ddp_check FAILED")
+        print("ddp_check training: %s" % res2)
+        print("ddp_check OK" if res["ok"] and res2["ok"] else "ddp_check FAILED")
     dist.destroy_process_group()
-    if rank == 0 and not res["ok"]:
+    if rank == 0 and not (res["ok"] and res2["ok"]):
         sys.exit(1)
 
 
