@@ -200,19 +200,25 @@ def _all_gather_slices(self, flat, shards):
 
 def _after_update(self, eng, stream):
     """Called by VQAFusedAdamW.step behind the sharded update, on the optimizer stream: low-order halves of this rank's
-    slices, then all-gather of the bf16 weights (and low-order halves) in the order the forward needs them."""
+    slices, then all-gather of the bf16 weights (and low-order halves) segment by segment in the order the forward needs
+    them (T5 block 0's segment first, the SGA stack's last), with one event per segment: the next forward starts on the
+    first segments while the later ones are still in flight (engine.forward)."""
     shards = eng.ddp_shards
     ctx = torch.cuda.stream(stream) if stream is not None else _Null()
+    events = [None] * len(shards)
     with ctx:
-        order = list(reversed(shards))          # backward order reversed = forward order (T5 block 0 first)
-        if eng.lo_ranges:
-            rec = eng.rec(None)
-            lo_sh = [s for s in order if any(s[0] < r1 and r0 < s[1] for r0, r1 in eng.lo_ranges)]
-            for lo, bhi, olo, ohi in lo_sh:
+        cur = torch.cuda.current_stream(eng.device)
+        rec = eng.rec(None)
+        for i in reversed(range(len(shards))):       # backward order reversed = forward order
+            sh = shards[i]
+            lo, bhi, olo, ohi = sh
+            self._all_gather_slices(eng.shadow, [sh])
+            if any(lo < r1 and r0 < bhi for r0, r1 in eng.lo_ranges):
                 rec.split_lo_bf16(eng.master.data_ptr() + 4 * olo, eng.shadow_lo.data_ptr() + 2 * olo, ohi - olo)
-        self._all_gather_slices(eng.shadow, order)
-        if eng.lo_ranges:
-            self._all_gather_slices(eng.shadow_lo, lo_sh)
+                self._all_gather_slices(eng.shadow_lo, [sh])
+            events[i] = torch.cuda.Event()
+            events[i].record(cur)
+    eng.shard_events = events
     eng.lo_fresh = True
     eng.master_stale = True
     eng.master_shards = list(shards)

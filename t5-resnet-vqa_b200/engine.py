@@ -322,6 +322,7 @@ class Engine:
         # of the flat random-init classifier then agree with fp32 closely enough for >= 99 % top-1 agreement with margin
         self.split_head = _env_flag("VQA_B200_SPLIT_HEAD", True)
         self._ddp = None
+        self.shard_events = None    # sharded data parallelism: per-segment "weights gathered" events of the last update
         self.ddp_shards = None      # sharded data parallelism: [(lo, big_hi, own_lo, own_hi)] of the CURRENT step, else None
         self.master_stale = False   # fp32 master of the GEMM weights is current only on the owning rank (ddp.py)
         self.master_shards = None
@@ -687,7 +688,15 @@ class Engine:
             st.mask.fill_(1)
         if labels is not None:
             st.labels.copy_(labels, non_blocking=True)
-        self.wait_optimizer(main)
+        # sharded optimizer: the all-gathers of the updated weights are still in flight on the optimizer stream; each part of
+        # the text forward waits only for the segments it reads (ddp.after_update records one event per segment)
+        pipelined = (self.shard_events is not None and self.use_lanes and not self.shadow_stale and self.lo_fresh
+                     and len(st.fwd_text_parts) > 1 and all(s < len(self.shard_events) for _, sg in st.fwd_text_parts for s in sg))
+        if pipelined:
+            for sidx in st.fwd_text_parts[0][1]:
+                main.wait_event(self.shard_events[sidx])
+        else:
+            self.wait_optimizer(main)
         self._refresh_shadow()
         if st.training:
             # one dropout stream position per TRAINING forward: its backward (and a second backward under retain_graph)
@@ -698,7 +707,12 @@ class Engine:
             self.run_plan(st.fwd_vis)
             self._refresh_projection()
             self.run_plan(st.fwd_proj)
-        self.run_plan(st.fwd_text)
+        for k, (plan, segs) in enumerate(st.fwd_text_parts):
+            if pipelined and k > 0:
+                for sidx in segs:
+                    main.wait_event(self.shard_events[sidx])
+            self.run_plan(plan)
+        self.shard_events = None
         if self.use_lanes:
             main.wait_event(self.ev_vis)
         self.run_plan(st.fwd_fuse)

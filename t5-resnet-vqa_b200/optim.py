@@ -189,9 +189,13 @@ class VQAFusedAdamW(torch.optim.Optimizer):
             spans = [(0, r["n"])]
             if eng is not None and eng.ddp_shards is not None:
                 e0 = (r["p0"] - eng.master.data_ptr()) // 4
-                if e0 < eng.n_big:
-                    spans = [(max(olo, e0) - e0, min(ohi, e0 + r["n"]) - e0) for _, _, olo, ohi in eng.ddp_shards
-                             if max(olo, e0) < min(ohi, e0 + r["n"])]
+                e1 = e0 + r["n"]
+                if e0 < eng.n_big:      # (a range may run from the GEMM weights into the replicated small tensors)
+                    big_end = min(e1, eng.n_big)
+                    spans = [(max(olo, e0) - e0, min(ohi, big_end) - e0) for _, _, olo, ohi in eng.ddp_shards
+                             if max(olo, e0) < min(ohi, big_end)]
+                    if e1 > eng.n_big:
+                        spans.append((eng.n_big - e0, r["n"]))
             for a0, a1 in spans:
                 L.check(lib.vqa_adamw_amsgrad(
                     None, r["p0"] + 4 * a0, r["g0"] + 4 * a0, r["m"].data_ptr() + 4 * a0, r["v"].data_ptr() + 4 * a0,

@@ -87,9 +87,12 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
     #   fwd_proj  channel projection (trainable weights)  -> vision stream, after the optimizer
     #   fwd_text  T5 encoder + the start of SGA layer 1    -> main stream, after the optimizer
     #   fwd_fuse  everything from the first use of the vision tokens on -> main stream, after fwd_proj
+    # fwd_text is a LIST of plans, cut where the T5 blocks change backward segment: under the sharded optimizer (ddp.py) each
+    # part only waits for the all-gather of the weights it reads, so the gathers of later blocks run under earlier blocks
     st.fwd_vis, st.fwd_proj = lib.vqa_plan_create(), lib.vqa_plan_create()
-    st.fwd_text, st.fwd_fuse = lib.vqa_plan_create(), lib.vqa_plan_create()
-    st.fwd_plans = [st.fwd_vis, st.fwd_proj, st.fwd_text, st.fwd_fuse]
+    st.fwd_fuse = lib.vqa_plan_create()
+    st.fwd_text_parts = []        # [(plan, [backward segment indices whose weights it reads])]
+    st.fwd_plans = [st.fwd_vis, st.fwd_proj, st.fwd_fuse]
     r = eng.rec(st.fwd_vis, st.ks_store)
     M = B * Lt
 
@@ -200,7 +203,17 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
     y0 = al(My, D)
     r = eng.rec(st.fwd_proj, st.ks_store)
     r.conv(B, Hf, Wf, Cf, D, 3, 1, 1, feat, eng.proj_w, y0, bias=eng.mp(proj.bias), relu=0)
-    r = eng.rec(st.fwd_text, st.ks_store)
+    blocks_per_seg = max(1, int(os.environ.get("VQA_B200_DDP_BLOCKS_PER_SEG", "3")))
+
+    def new_text_part(segs):
+        plan = lib.vqa_plan_create()
+        st.fwd_text_parts.append((plan, list(segs)))
+        st.fwd_plans.append(plan)
+        return eng.rec(plan, st.ks_store)
+
+    def seg_of_block(bi, nblk):    # backward segment holding T5 block bi's weights (segment 0 = head + SGA stack)
+        return 1 + (nblk - 1 - bi) // blocks_per_seg
+    r = None
 
     # =============================================================================================
     # T5 encoder (hf:637-792)
@@ -213,6 +226,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
     blocks = list(t5.block)
     nblk = len(blocks)
     hid = [al(M, D, dtype=f32) for _ in range(nblk + 1)]
+    r = new_text_part([seg_of_block(0, nblk)])
     sid_embed = new_sid()
     r.embedding_fwd(st.ids, eng.mp(t5.embed_tokens.weight), hid[0], M, D, vocab, p_t5, sid_embed, rng)
     bucket = t5_relative_buckets(Lt, Lt, cfg["num_buckets"], cfg["max_distance"]).to(dev).contiguous()
@@ -230,6 +244,9 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
         # written as [M, 2D] = hi | lo, the weights' low-order halves come from the engine (engine.lp), and one k-loop adds
         # x_hi W_hi + x_lo W_hi + x_hi W_lo (o / wo: their bf16 inputs have no low half, two terms).  The backward still
         # uses the plain bf16 operands (backward rounding does not move the gradient cosine, tools/precision_probe.py).
+        if bi > 0 and seg_of_block(bi, nblk) != seg_of_block(bi - 1, nblk):
+            last = seg_of_block(bi, nblk) == 1      # the last part also runs the start of the SGA stack (segment 0)
+            r = new_text_part([seg_of_block(bi, nblk)] + ([0] if last else []))
         split = bi < nsplit
         ldy = 2 * D if split else D
         sv = dict(y1=al(M, ldy), rstd1=al(M, dtype=f32), qkv=al(M, 3 * inner), probs=t5_probs, stats=t5_stats,
@@ -524,8 +541,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
     r.rmsnorm_bwd(dText, 1, hid[nblk], eng.mp(t5.final_layer_norm.weight), rstd_f, None, dH,
                   eng.gp(t5.final_layer_norm.weight), M, D, p_t5, sid_final, rng,
                   g_bf, p_t5, saved_t5[nblk - 1]["sid_f"])
-    # T5 blocks per backward segment (= per gradient all-reduce bucket under data parallelism)
-    blocks_per_seg = max(1, int(os.environ.get("VQA_B200_DDP_BLOCKS_PER_SEG", "3")))
+    # T5 blocks per backward segment (= per gradient exchange bucket under data parallelism): blocks_per_seg, above
     seg_lo = o[id(proj.weight)]
     for bi in reversed(range(nblk)):
         blk, sv = blocks[bi], saved_t5[bi]
