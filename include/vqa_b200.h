@@ -177,12 +177,14 @@ int vqa_embedding_fwd(void* plan, const long long* ids, const float* table, floa
 int vqa_embedding_bwd(void* plan, const long long* ids, const float* dout, float* dtable, int M, int D,
                       int vocab, float drop_p, uint32_t sid, const uint64_t* rng, void* stream);
 /* Data-parallel form of embedding_bwd: rows[t,:] = scale * dropout(dout[t,:]) leave the rank (all-gather with the ids), and
- * every rank scatter-adds all ranks' rows into its zeroed dtable in ONE fixed order (token index), without atomics, so the
- * replicas' embedding gradients are bit-identical.  first_ws: int[vocab] scratch.  (New work: the reference is single-device.) */
+ * every rank scatters all ranks' rows into its zeroed dtable such that the result does not depend on the order of the
+ * additions (ids carried by several tokens are summed as 64-bit fixed-point integers, unit 2^-40), so the replicas'
+ * embedding gradients are bit-identical.  first_ws: int[2*vocab] scratch, acc_ws: int64[T*D] scratch (16-byte aligned).
+ * (New work: the reference is single-device.) */
 int vqa_embedding_bwd_rows(void* plan, const float* dout, float* rows, int M, int D, float drop_p, uint32_t sid,
                            const uint64_t* rng, float scale, void* stream);
-int vqa_embedding_scatter_ordered(void* plan, const long long* ids, const float* rows, float* dtable, int* first_ws, int T,
-                                  int D, int vocab, void* stream);
+int vqa_embedding_scatter_ordered(void* plan, const long long* ids, const float* rows, float* dtable, int* first_ws,
+                                  long long* acc_ws, int T, int D, int vocab, void* stream);
 /* T5LayerNorm (hf:55-68): y = w * x * rsqrt(mean(x^2) + eps), then optional dropout (hf:768).
  * y_bf16 and/or y_f32 may be NULL.  Backward: dx = (dres?) + d/dx, dw += sum_rows (atomic). */
 int vqa_rmsnorm_fwd(void* plan, const float* x, const float* w, void* y_bf16, float* y_f32,

@@ -260,10 +260,15 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sQ = base, sK = sQ + CH * kTile, sV = sK + CH * kTile, sP = sV + CH * kTile;
-  const uint32_t bar_tma = sP + 2 * kTile, bar_mma = bar_tma + 8, slot = bar_mma + 8;
-  uint8_t* Pg = gen + 3 * CH * kTile;
-  const uint32_t* slot_ptr = reinterpret_cast<const uint32_t*>(gen + (3 * CH + 2) * kTile + 16);
+  // P (two tiles) lives in K's buffer when K has two tiles (hd = 96): K is dead once S = Q K^T has completed, which every
+  // thread waits for before it touches P.  96 KB instead of 128 KB: two CTAs per SM, so the 256 CTAs of the guided
+  // attention over 49 / 64 vision tokens are one wave instead of two.
+  constexpr bool kAliasP = CH == 2;
+  constexpr int kTiles = 3 * CH + (kAliasP ? 0 : 2);
+  const uint32_t sQ = base, sK = sQ + CH * kTile, sV = sK + CH * kTile, sP = kAliasP ? sK : sV + CH * kTile;
+  const uint32_t bar_tma = base + kTiles * kTile, bar_mma = bar_tma + 8, slot = bar_mma + 8;
+  uint8_t* Pg = gen + (kAliasP ? CH : 3 * CH) * kTile;
+  const uint32_t* slot_ptr = reinterpret_cast<const uint32_t*>(gen + kTiles * kTile + 16);
   const int t = threadIdx.x;
   // lane-0 broadcast: ptxas then knows the warp index is warp-uniform (uniform branches / uniform registers below)
   const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
@@ -281,7 +286,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tmem_alloc(slot, kCols);
     tmem_relinquish();
   }
-  for (int i = t; i < 2 * kTile / 16; i += kThreads) reinterpret_cast<uint4*>(Pg)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (!kAliasP)
+    for (int i = t; i < 2 * kTile / 16; i += kThreads) reinterpret_cast<uint4*>(Pg)[i] = make_uint4(0u, 0u, 0u, 0u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -353,6 +359,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int e = 0; e < 8; ++e)
         if ((inr >> e) & 1u) mx = fmaxf(mx, scs[j0 + e]);
+    }
+  }
+  if (kAliasP) {   // P shares K's buffer: clear this thread's row of both tiles now that S is complete
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint4* prow = reinterpret_cast<uint4*>(Pg + c * kTile + (t >> 3) * 1024 + (t & 7) * 128);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) prow[j] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
   // pass 2: exp, row sum, dropout, bf16 P (unnormalised: the 1/sum goes onto O, flash style)
@@ -649,7 +663,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
-template <int HD> constexpr size_t fwd_smem_bytes() { return (3 * ((HD + 63) / 64) + 2) * kTile + 64 + 1024; }
+template <int HD> constexpr size_t fwd_smem_bytes() {
+  return (3 * ((HD + 63) / 64) + ((HD + 63) / 64 == 2 ? 0 : 2)) * kTile + 64 + 1024;   // hd = 96: P aliases K
+}
 template <int HD> constexpr size_t bwd_smem_bytes() { return (4 * ((HD + 63) / 64) + 3) * kTile + 64; }
 
 template <typename K>

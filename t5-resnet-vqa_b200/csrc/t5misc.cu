@@ -51,7 +51,7 @@ __global__ void embedding_bwd_kernel(const long long* __restrict__ ids, const fl
   }
 }
 
-// ---- data-parallel embedding gradient: rows travel, every rank scatters them in the same fixed order ----------------
+// ---- data-parallel embedding gradient: rows travel, every rank scatters them with an order-independent sum ---------
 // rows[t, :] = scale * dropout_mask(t, :) * dout[t, :]   (what embedding_bwd would have added to dtable[ids[t], :])
 __global__ void embedding_bwd_rows_kernel(const float* __restrict__ dout, float* __restrict__ rows, int M, int D, float drop_p,
                                           uint32_t sid, const unsigned long long* __restrict__ rng, float scale) {
@@ -75,55 +75,95 @@ __device__ __forceinline__ int clamp_id(long long id, int vocab) {
   return id < 0 ? 0 : (id >= vocab ? vocab - 1 : static_cast<int>(id));
 }
 
-// first[id] = smallest token index carrying that id (atomicMin: the result does not depend on the execution order)
-__global__ void embedding_first_kernel(const long long* __restrict__ ids, int* __restrict__ first, int T, int vocab) {
+// ---- order-independent scatter: identical on every rank, whatever order the hardware adds in -----------------
+// Pass 1: first[id] = smallest token index carrying that id (atomicMin) and count[id] (integer atomicAdd): both exact.
+__global__ void embedding_first_kernel(const long long* __restrict__ ids, int* __restrict__ first, int* __restrict__ count,
+                                       int T, int vocab) {
   pdl_grid_sync();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < T) atomicMin(first + clamp_id(ids[t], vocab), t);
+  if (t < T) {
+    const int id = clamp_id(ids[t], vocab);
+    atomicMin(first + id, t);
+    atomicAdd(count + id, 1);
+  }
 }
 
-// One warp per token t.  The FIRST token of each id owns that id's row of the table: it walks the later tokens in
-// index order and adds the rows of those with the same id, so the sum is formed in one fixed order on every rank
-// (bit-identical replicas; fp32 atomics would add duplicates in arrival order), then stores the row (no atomics: one
-// owner per id; untouched rows keep the zeros the backward pass wrote).
-__global__ void embedding_scatter_ordered_kernel(const long long* __restrict__ ids, const float* __restrict__ rows,
-                                                 const int* __restrict__ first, float* __restrict__ dtable, int T, int D,
-                                                 int vocab) {
+constexpr float kFixScale = 1099511627776.f;          // 2^40: fixed-point unit 9.1e-13, |sum| up to 2^23
+constexpr float kFixInv = 1.f / 1099511627776.f;
+
+// Pass 2 (warp per token, eight consecutive tokens per CTA).  An id carried by ONE token: its row is copied into the table.
+// An id carried by several tokens (padding, frequent words): the rows are added as 64-bit FIXED-POINT integers into the
+// accumulator row of the id's first token - integer addition is associative, so thousands of concurrent atomics give the
+// same bits on every rank and in every run (fp32 atomics would not).  Tokens of one CTA that share an id (runs of padding)
+// are first summed in shared memory, so a run of eight costs one atomic per column instead of eight.
+// mode 0: first tokens of shared ids clear their accumulator row; 1: add; 2: first tokens convert the sum into the table row.
+constexpr int kScatWarps = 8;
+__global__ void __launch_bounds__(kScatWarps * 32)
+embedding_scatter_fixed_kernel(const long long* __restrict__ ids, const float* __restrict__ rows,
+                               const int* __restrict__ first, const int* __restrict__ count,
+                               long long* __restrict__ acc, float* __restrict__ dtable, int T, int D, int vocab, int mode) {
   pdl_grid_sync();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int t = warp; t < T; t += nwarps) {
-    const int id = clamp_id(ids[t], vocab);
-    if (first[id] != t) continue;            // warp-uniform
-    float acc[32];                            // D <= 1024: lane owns columns lane*8 + 256*j
+  extern __shared__ __align__(16) long long sfix[];        // mode 1: [kScatWarps][D] fixed-point rows of this CTA's tokens
+  __shared__ int skey[kScatWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * kScatWarps; base < T; base += gridDim.x * kScatWarps) {   // trip count uniform per CTA
+    const int t = base + warp;
+    const bool valid = t < T;
+    const int id = valid ? clamp_id(ids[t], vocab) : 0;
+    const int c = valid ? count[id] : 0, f = valid ? first[id] : -1;
+    if (mode != 1) {
+      if (!valid || c == 1) continue;
+      long long* arow = acc + static_cast<long long>(f) * D;
+      if (f != t) continue;
+      if (mode == 0) {
+        for (int col = lane * 2; col < D; col += 64) *reinterpret_cast<longlong2*>(arow + col) = make_longlong2(0ll, 0ll);
+      } else {
+        float* dst = dtable + static_cast<long long>(id) * D;
+        for (int col = lane * 8; col < D; col += 256) {
+          float v[8];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    for (int u0 = t; u0 < T; u0 += 32) {
-      const int u = u0 + lane;
-      const bool hit = u < T && clamp_id(ids[u], vocab) == id;
-      unsigned m = __ballot_sync(0xffffffffu, hit);
-      while (m) {                              // ascending token index
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        const float* src = rows + static_cast<long long>(u0 + b) * D;
+          for (int i = 0; i < 8; ++i) v[i] = __ll2float_rn(arow[col + i]) * kFixInv;
+          store_f32x8(dst + col, v);
+        }
+      }
+      continue;
+    }
+    // ---- mode 1 ----
+    const bool shared_id = valid && c > 1;
+    if (lane == 0) skey[warp] = shared_id ? f : -1 - warp;     // unique negative keys never match
+    if (valid && c == 1) {
+      const float* src = rows + static_cast<long long>(t) * D;
+      float* dst = dtable + static_cast<long long>(id) * D;
+      for (int col = lane * 8; col < D; col += 256) {
+        float v[8];
+        load_f32x8(src + col, v);
+        store_f32x8(dst + col, v);
+      }
+    } else if (shared_id) {
+      const float* src = rows + static_cast<long long>(t) * D;
+      long long* srow = sfix + static_cast<long long>(warp) * D;
+      for (int col = lane * 8; col < D; col += 256) {
+        float v[8];
+        load_f32x8(src + col, v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int col = lane * 8 + 256 * j;
-          if (col < D) {
-            float f[8];
-            load_f32x8(src + col, f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[8 * j + i] += f[i];
-          }
+        for (int i = 0; i < 8; ++i) srow[col + i] = __float2ll_rn(v[i] * kFixScale);
+      }
+    }
+    __syncthreads();
+    if (shared_id) {
+      bool leader = true;                       // the first warp of the CTA holding this id adds for all of them
+      for (int w = 0; w < warp; ++w) leader = leader && skey[w] != f;
+      if (leader) {
+        long long* arow = acc + static_cast<long long>(f) * D;
+        for (int col = lane; col < D; col += 32) {
+          long long sum = sfix[static_cast<long long>(warp) * D + col];
+          for (int w = warp + 1; w < kScatWarps; ++w)
+            if (skey[w] == f) sum += sfix[static_cast<long long>(w) * D + col];
+          atomicAdd(reinterpret_cast<unsigned long long*>(arow + col), static_cast<unsigned long long>(sum));
         }
       }
     }
-    float* dst = dtable + static_cast<long long>(id) * D;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = lane * 8 + 256 * j;
-      if (col < D) store_f32x8(dst + col, *reinterpret_cast<float(*)[8]>(&acc[8 * j]));
-    }
+    __syncthreads();
   }
 }
 
@@ -188,18 +228,30 @@ int vqa_embedding_bwd_rows(void* plan, const float* dout, float* rows, int M, in
   });
 }
 
-int vqa_embedding_scatter_ordered(void* plan, const long long* ids, const float* rows, float* dtable, int* first_ws, int T,
-                                  int D, int vocab, void* stream) {
-  if (D % 8 || D > 1024) { set_last_error("embedding_scatter_ordered: D must be a multiple of 8, at most 1024"); return -1; }
+int vqa_embedding_scatter_ordered(void* plan, const long long* ids, const float* rows, float* dtable, int* first_ws,
+                                  long long* acc_ws, int T, int D, int vocab, void* stream) {
+  if (D % 8 || D > 1024 || (reinterpret_cast<uintptr_t>(acc_ws) & 15)) {
+    set_last_error("embedding_scatter_ordered: D must be a multiple of 8, at most 1024, and the workspace 16-byte aligned");
+    return -1;
+  }
   note_op("embedding_scatter", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
+    int* count_ws = first_ws + vocab;
     cudaError_t e = cudaMemsetAsync(first_ws, 0x7f, sizeof(int) * static_cast<size_t>(vocab), s);   // 0x7f7f7f7f > any index
+    if (e == cudaSuccess) e = cudaMemsetAsync(count_ws, 0, sizeof(int) * static_cast<size_t>(vocab), s);
     if (e != cudaSuccess) { set_last_error("embedding_scatter_ordered: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
-    launch_pdl(embedding_first_kernel, dim3((T + 255) / 256), dim3(256), 0, s, ids, first_ws, T, vocab);
+    launch_pdl(embedding_first_kernel, dim3((T + 255) / 256), dim3(256), 0, s, ids, first_ws, count_ws, T, vocab);
     int grid = (T + 7) / 8;
     if (grid > 148 * 8) grid = 148 * 8;
-    launch_pdl(embedding_scatter_ordered_kernel, dim3(grid), dim3(256), 0, s, ids, rows, static_cast<const int*>(first_ws),
-               dtable, T, D, vocab);
+    const size_t smem = static_cast<size_t>(kScatWarps) * D * sizeof(long long);
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(embedding_scatter_fixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 8);
+      attr = true;
+    }
+    for (int mode = 0; mode < 3; ++mode)
+      launch_pdl(embedding_scatter_fixed_kernel, dim3(grid), dim3(kScatWarps * 32), mode == 1 ? smem : 0, s, ids, rows,
+                 static_cast<const int*>(first_ws), static_cast<const int*>(count_ws), acc_ws, dtable, T, D, vocab, mode);
     return launch_status("embedding_scatter_ordered");
   });
 }

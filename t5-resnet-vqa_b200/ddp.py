@@ -75,7 +75,7 @@ class GradSync:
             raise ValueError("VQA_B200_DDP_GRAD_DTYPE must be bf16 or fp32")
         self.stage = None
         # The token-embedding gradient (24.7 M parameters, 99 MB fp32, 2048 non-zero rows per rank) is exchanged as rows:
-        # all-gather (ids, rows) = 6 MB per rank, then a deterministic local scatter (csrc/t5misc.cu).  It is the last
+        # all-gather (ids, rows) = 6 MB per rank, then an order-independent local scatter (csrc/t5misc.cu).  It is the last
         # gradient of the backward pass, so its exchange cannot overlap anything: the dense form was a third of the tail.
         self.sparse_embedding = os.environ.get("VQA_B200_DDP_SPARSE_EMBEDDING", "1") != "0"
         self._emb = None
@@ -244,17 +244,18 @@ class _Null:
 
 def _gather_embedding(self, eng, st, rows, emb):
     """(current stream = communication stream) all-gather every rank's token ids and gradient rows, then scatter them into
-    this rank's zeroed table gradient in token order: bit-identical on all ranks."""
+    this rank's zeroed table gradient with an order-independent kernel: bit-identical on all ranks."""
     M, D = rows.shape
     T = M * self.world
     if self._emb is None or self._emb[0].shape[0] != T or self._emb[0].device != rows.device:
         self._emb = (torch.empty(T, D, dtype=torch.float32, device=rows.device),
                      torch.empty(T, dtype=torch.int64, device=rows.device),
-                     torch.empty(emb.shape[0], dtype=torch.int32, device=rows.device))
-    rows_all, ids_all, first = self._emb
+                     torch.empty(2 * emb.shape[0], dtype=torch.int32, device=rows.device),
+                     torch.empty(T * D, dtype=torch.int64, device=rows.device))
+    rows_all, ids_all, first, acc = self._emb
     dist.all_gather_into_tensor(ids_all, st.ids.reshape(-1), group=self.group)
     dist.all_gather_into_tensor(rows_all, rows, group=self.group)
-    eng.rec(None).embedding_scatter_ordered(ids_all, rows_all, eng.gp(emb), first, T, D, emb.shape[0])
+    eng.rec(None).embedding_scatter_ordered(ids_all, rows_all, eng.gp(emb), first, acc, T, D, emb.shape[0])
 
 
 GradSync._exchange_embedding_rows = _gather_embedding

@@ -97,7 +97,7 @@ SIGNATURES = {
     "vqa_embedding_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_f, c_u32, _P, _P]),
     "vqa_embedding_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_f, c_u32, _P, _P]),
     "vqa_embedding_bwd_rows": (c_int, [_P, _P, _P, c_int, c_int, c_f, c_u32, _P, c_f, _P]),
-    "vqa_embedding_scatter_ordered": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "vqa_embedding_scatter_ordered": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "vqa_rmsnorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_f, c_f, c_u32, _P, _P]),
     "vqa_rmsnorm_fwd_split": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_f, _P]),
     "vqa_rmsnorm_bwd": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_f, c_u32, _P, _P, c_f, c_u32,

@@ -203,7 +203,15 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
     y0 = al(My, D)
     r = eng.rec(st.fwd_proj, st.ks_store)
     r.conv(B, Hf, Wf, Cf, D, 3, 1, 1, feat, eng.proj_w, y0, bias=eng.mp(proj.bias), relu=0)
-    blocks_per_seg = max(1, int(os.environ.get("VQA_B200_DDP_BLOCKS_PER_SEG", "3")))
+    # T5 blocks per backward segment, from the LAST block down (= per gradient-exchange bucket under data parallelism).  The
+    # final segments are short: the exchange of the last one cannot overlap anything, and under the sharded optimizer the
+    # next forward starts as soon as block 0's weights are gathered.  VQA_B200_DDP_SEG_PLAN="3,3,3,2,1";
+    # VQA_B200_DDP_BLOCKS_PER_SEG=<n> gives uniform segments.
+    if os.environ.get("VQA_B200_DDP_BLOCKS_PER_SEG"):
+        seg_plan = [max(1, int(os.environ["VQA_B200_DDP_BLOCKS_PER_SEG"]))] * 64
+    else:
+        seg_plan = [max(1, int(v)) for v in os.environ.get("VQA_B200_DDP_SEG_PLAN", "3,3,3,2,1").split(",")] + [1] * 64
+    _seg_of = {}
 
     def new_text_part(segs):
         plan = lib.vqa_plan_create()
@@ -212,7 +220,17 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
         return eng.rec(plan, st.ks_store)
 
     def seg_of_block(bi, nblk):    # backward segment holding T5 block bi's weights (segment 0 = head + SGA stack)
-        return 1 + (nblk - 1 - bi) // blocks_per_seg
+        if not _seg_of:
+            b, sidx = nblk - 1, 1
+            for n in seg_plan:
+                for _ in range(n):
+                    if b >= 0:
+                        _seg_of[b] = sidx
+                        b -= 1
+                sidx += 1
+                if b < 0:
+                    break
+        return _seg_of[bi]
     r = None
 
     # =============================================================================================
@@ -541,7 +559,6 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
     r.rmsnorm_bwd(dText, 1, hid[nblk], eng.mp(t5.final_layer_norm.weight), rstd_f, None, dH,
                   eng.gp(t5.final_layer_norm.weight), M, D, p_t5, sid_final, rng,
                   g_bf, p_t5, saved_t5[nblk - 1]["sid_f"])
-    # T5 blocks per backward segment (= per gradient exchange bucket under data parallelism): blocks_per_seg, above
     seg_lo = o[id(proj.weight)]
     for bi in reversed(range(nblk)):
         blk, sv = blocks[bi], saved_t5[bi]
@@ -575,7 +592,7 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
         r.rmsnorm_bwd(dsm, 0, hid[bi], eng.mp(att.layer_norm.weight), sv["rstd1"], dH, dH,
                       eng.gp(att.layer_norm.weight), M, D, 0.0, 0, rng,
                       g_bf if bi > 0 else None, p_t5, saved_t5[bi - 1]["sid_f"] if bi > 0 else 0)
-        if bi > 0 and (nblk - bi) % blocks_per_seg == 0:
+        if bi > 0 and seg_of_block(bi, nblk) != seg_of_block(bi - 1, nblk):
             hi = o[id(blocks[bi - 1].layer[0].SelfAttention.q.weight)]
             close_segment(bp, seg_lo, hi)
             seg_lo = hi

@@ -300,6 +300,28 @@ def test_clip_grad_norm_fast_path(pkg, cuda):
     ropt.step()
     for r, (k, p) in zip(ref, m.named_parameters()):
         assert float((p.detach() - r.detach()).abs().max()) < 2e-6, k
+    # step 3: a caller that bound torch's own clip_grad_norm_ before this package was imported (`from torch.nn.utils import
+    # clip_grad_norm_`) keeps calling torch's implementation: it scales the flat-buffer views in place, nothing is deferred,
+    # and the fused optimizer then updates from the clipped gradients like torch.optim.AdamW
+    g = fwd_bwd()
+    before = {k: p.detach().clone() for k, p in m.named_parameters()}
+    state = copy.deepcopy(opt.state_dict())
+    want, clipped = torch_clip(g)
+    got = vo._torch_clip_grad_norm_(m.parameters(), MAXN)
+    assert abs(float(got) / float(want) - 1) < 1e-5 and m._engine.pending_clip is None
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            assert float((p.grad - clipped[k]).abs().max()) <= 1e-6 * max(1.0, float(clipped[k].abs().max())), k
+    opt.step()
+    ref = [before[k].clone().requires_grad_(True) for k, _ in m.named_parameters()]
+    ropt = torch.optim.AdamW(ref, lr=1e-3, weight_decay=0.1, amsgrad=True)
+    ropt.load_state_dict(state)
+    for r, (k, _) in zip(ref, m.named_parameters()):
+        if k in clipped:
+            r.grad = clipped[k]
+    ropt.step()
+    for r, (k, p) in zip(ref, m.named_parameters()):
+        assert float((p.detach() - r.detach()).abs().max()) < 2e-6, k
     # tensors outside an engine still go to torch
     w = torch.randn(10, 10, device=cuda, requires_grad=True)
     w.grad = torch.ones_like(w)
