@@ -163,6 +163,8 @@ class VQAFusedAdamW(torch.optim.Optimizer):
             gnorm_ptr = self._gnorm.data_ptr()
         steps = {}
         engines = {}
+        deferred = []  # (segment index | None, range, span, ...): GEMM-weight spans launched after the small tensors, in forward order
+        pipeline = {}  # engine -> [(segment index, (lo, big_hi))] when the update is pipelined with the next forward
         side = {}      # engine -> its optimizer stream (ordered after everything queued on the current stream)
         for r in self._ranges:
             eng = r["engine"]
@@ -171,6 +173,8 @@ class VQAFusedAdamW(torch.optim.Optimizer):
                 if so is not None:
                     so.wait_stream(torch.cuda.current_stream(r["dev"]))
                 side[eng] = so
+                if so is not None and eng.pipeline_update:
+                    pipeline[eng] = eng.segment_ranges()
         for r in self._ranges:
             group = self.param_groups[r["group"]]
             gi = r["group"]
@@ -187,6 +191,22 @@ class VQAFusedAdamW(torch.optim.Optimizer):
                 r_gnorm, r_max = eng.clip_sumsq.data_ptr(), eng.pending_clip
             # sharded data parallelism (ddp.py): of a range of GEMM weights only this rank's slices are updated
             spans = [(0, r["n"])]
+            if eng is not None and eng.ddp_shards is None and pipeline.get(eng):
+                # single GPU: the range is cut at the backward-segment boundaries and updated in FORWARD order, one event per
+                # segment, so that the next forward starts on the first T5 blocks while the rest of the pass still runs
+                e0 = (r["p0"] - eng.master.data_ptr()) // 4
+                e1 = e0 + r["n"]
+                cuts = []
+                for si, (lo, bhi) in pipeline[eng]:
+                    a, b = max(lo, e0), min(bhi, e1)
+                    if a < b:
+                        cuts.append((si, a - e0, b - e0))
+                if cuts:
+                    if e1 > eng.n_big:
+                        deferred.append((None, r, (max(eng.n_big, e0) - e0, r["n"]), group, t, r_gnorm, r_max, s))
+                    for si, a, b in cuts:
+                        deferred.append((si, r, (a, b), group, t, r_gnorm, r_max, s))
+                    spans = []
             if eng is not None and eng.ddp_shards is not None:
                 e0 = (r["p0"] - eng.master.data_ptr()) // 4
                 e1 = e0 + r["n"]
@@ -197,27 +217,52 @@ class VQAFusedAdamW(torch.optim.Optimizer):
                     if e1 > eng.n_big:
                         spans.append((eng.n_big - e0, r["n"]))
             for a0, a1 in spans:
-                L.check(lib.vqa_adamw_amsgrad(
-                    None, r["p0"] + 4 * a0, r["g0"] + 4 * a0, r["m"].data_ptr() + 4 * a0, r["v"].data_ptr() + 4 * a0,
-                    r["vmax"].data_ptr() + 4 * a0 if r["vmax"] is not None else None,
-                    r["shadow"] + 2 * a0 if r["shadow"] is not None else None, a1 - a0,
-                    float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                    1.0 - b1 ** t, 1.0 - b2 ** t, r_gnorm,
-                    float(r_max) if r_max is not None else 0.0,
-                    int(bool(group["amsgrad"])), s), "adamw")
+                self._launch(lib, r, a0, a1, group, t, r_gnorm, r_max, s)
             if r["engine"] is not None:
                 engines[r["engine"]] = engines.get(r["engine"], 0) + len(r["params"])
+        if deferred:
+            # small-tensor tails first (None), then the segments from the one the forward reads first (highest index) down
+            deferred.sort(key=lambda d: (0, 0) if d[0] is None else (1, -d[0]))
+            events = {}
+            for i, (si, r, (a0, a1), group, t, r_gnorm, r_max, s) in enumerate(deferred):
+                self._launch(lib, r, a0, a1, group, t, r_gnorm, r_max, s)
+                last_of_segment = i + 1 == len(deferred) or deferred[i + 1][0] != si
+                if si is not None and last_of_segment:
+                    eng = r["engine"]
+                    if eng.lo_ranges:
+                        eng.refresh_lo_segment(pipeline[eng], si, side[eng])
+                    ev = torch.cuda.Event()
+                    ev.record(side[eng])
+                    events.setdefault(eng, {})[si] = ev
+            for eng, evs in events.items():
+                n = max(evs) + 1
+                eng.shard_events = [evs.get(i) for i in range(n)]
+                if any(e is None for e in eng.shard_events):
+                    eng.shard_events = None
         for eng, covered in engines.items():
             eng.note_fused_update(covered)
             eng.pending_clip = None
             if eng.ddp_shards is not None:
                 eng._ddp.after_update(eng, side.get(eng))     # low-order halves of the own slices + all-gather of the weights
                 eng.ddp_shards = None                         # belongs to the backward pass that produced these gradients
-            elif covered == len(eng.params):
+            elif covered == len(eng.params) and eng.shard_events is None:
                 eng.refresh_lo_after_update(side.get(eng))
+            elif covered == len(eng.params):
+                eng.lo_fresh = True                # refreshed segment by segment above
             if side.get(eng) is not None:
                 eng.note_optimizer_launched(side[eng])
         return loss
+
+    def _launch(self, lib, r, a0, a1, group, t, r_gnorm, r_max, s):
+        b1, b2 = group["betas"]
+        L.check(lib.vqa_adamw_amsgrad(
+            None, r["p0"] + 4 * a0, r["g0"] + 4 * a0, r["m"].data_ptr() + 4 * a0, r["v"].data_ptr() + 4 * a0,
+            r["vmax"].data_ptr() + 4 * a0 if r["vmax"] is not None else None,
+            r["shadow"] + 2 * a0 if r["shadow"] is not None else None, a1 - a0,
+            float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+            1.0 - b1 ** t, 1.0 - b2 ** t, r_gnorm,
+            float(r_max) if r_max is not None else 0.0,
+            int(bool(group["amsgrad"])), s), "adamw")
 
     def zero_grad(self, set_to_none=True):
         if not set_to_none:      # zeroing in place would race with an optimizer pass still reading the gradients
