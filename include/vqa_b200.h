@@ -269,6 +269,44 @@ int vqa_logsoftmax_nll_fwd(void* plan, const float* logits, long long ld, const 
 int vqa_logsoftmax_nll_bwd(void* plan, const float* logp, const long long* labels, const float* gloss,
                            const float* glogp, void* dlogits, long long ld, int B, int A, void* stream);
 
+/* ---- VitVQAModel step (model/vit_vqa_model.py:127-227).  `vit:` = transformers/models/vit/modeling_vit.py -- */
+/* softmax(scale * Q K^T) V for ONE sequence length L <= 256 on both sides, hd = 64, no mask / bias / dropout, nothing saved:
+ * the frozen ViT-B/16's self-attention over 197 tokens (vit: ViTSelfAttention; the reference runs it under torch.no_grad(),
+ * model/vit_vqa_model.py:184-186).  tcgen05 kernel, one CTA per (batch, head, 128-query tile).  Indexing as vqa_attn_fwd_args. */
+int vqa_attention_long_fwd(void* plan, const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                           long long ldv, void* out, long long ldo, int B, int H, int L, int hd, float scale, void* stream);
+/* pixel_values fp32 [B,3,H,W] -> bf16 [B*(H/P)*(W/P), 3*P*P] patch rows (column = c*P*P + ky*P + kx): the A operand of the
+ * patch-projection GEMM, Conv2d(3,768,P,stride P) as a matrix product (vit: ViTPatchEmbeddings) */
+int vqa_vit_patchify(void* plan, const float* img, void* out, int B, int H, int W, int P, void* stream);
+/* hidden fp32 [B, NP+1, D]: token 0 = cls + pos[0], token 1+p = patch[b,p,:] + pos[1+p] (vit: ViTEmbeddings.forward) */
+int vqa_vit_assemble(void* plan, const float* patch, const float* cls, const float* pos, float* hidden, int B, int NP,
+                     int D, void* stream);
+/* exact (erf) GELU in place on n bf16 values (vit: ViTIntermediate, hidden_act = "gelu") */
+int vqa_gelu_bf16(void* plan, void* x, long long n, void* stream);
+/* out bf16 [B, 2D] = [tanh(pooled_pre[b,:]) | enc[b*L, :]]: ViTPooler's activation and torch.cat([pooler_output, encoder
+ * token 0]) (model/vit_vqa_model.py:192-198); pooled_out (fp32 [B,D], may be NULL) receives the tanh half */
+int vqa_vit_fuse_concat(void* plan, const float* pooled_pre, const float* enc, int L, void* out, float* pooled_out, int B,
+                        int D, void* stream);
+/* T5 decoder cross-attention onto ONE encoder token (encoder_hidden_states = fused_embedding.unsqueeze(1),
+ * model/vit_vqa_model.py:207-212): the softmax over a single key is 1, so ctx[b*Lq+q, h*hd+d] = keep(b,h,q) * v[b, h*hd+d],
+ * keep = the dropout HF applies to the attention weights [B,H,Lq,1] (hf:327-334); backward sums dctx over q into dv.
+ * The query / key projections receive exactly zero gradient. */
+int vqa_xattn1_fwd(void* plan, const void* v, void* ctx, int B, int H, int Lq, int hd, float drop_p, uint32_t sid,
+                   const uint64_t* rng, void* stream);
+int vqa_xattn1_bwd(void* plan, const void* dctx, void* dv, int B, int H, int Lq, int hd, float drop_p, uint32_t sid,
+                   const uint64_t* rng, void* stream);
+/* out[b,:] = src[b*L + last(b), :], last(b) = the last position with mask[b,j] == 1 (0 if none or mask == NULL): the answer
+ * token gather (model/vit_vqa_model.py:215-219) and, with mask == NULL, encoder_outputs[:,0,:] (:192).  scatter_rows is the
+ * backward: dst fp32 [B*L, D] = 0 except row last(b) = src[b,:]. */
+int vqa_gather_rows(void* plan, const float* src, const long long* mask, void* out_bf16, float* out_f32, int B, int L,
+                    int D, void* stream);
+int vqa_scatter_rows(void* plan, const float* src, const long long* mask, float* dst, int B, int L, int D, void* stream);
+/* decoder self-attention: bias[h,i,j] = finfo.min for j > i on top of vqa_t5_bias_build's table (HF causal mask) */
+int vqa_t5_bias_causal(void* plan, float* bias, int H, int L, void* stream);
+/* gradient through Dropout(ReLU(.)) from the layer's OUTPUT y: out bf16 = y > 0 ? dy * scale : 0 (fusing_layer,
+ * model/vit_vqa_model.py:150-154; scale = 1/(1-p) in training, 1 in eval) */
+int vqa_relu_dropout_bwd(void* plan, const float* dy, const void* y, void* out, float scale, long long n, void* stream);
+
 /* ---- optimizer step (trainer/faster_rcnn_vqa_trainer.py:399-404) -------------------------------- */
 /* out[0] += sum x^2 */
 int vqa_sumsq_f32(void* plan, const float* x, long long n, float* out, void* stream);

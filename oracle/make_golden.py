@@ -66,6 +66,62 @@ def reference_model(vision):
     return ref.ResnetVQAModel(vision, "t5-base", answer_spaces=170)
 
 
+VIT_CASES = {
+    # VitVQAModel (model/vit_vqa_model.py:127-227, BASELINE.json configs[4]): ViT-B/16 224x224 + T5-base encoder-decoder;
+    # decoder questions padded to Enums.MAX_LEN = 20 with per-sample lengths, the reference collate's 'longest' questions
+    "vit_b2_l16": dict(B=2, L=16, Ld=20, masked_tail=3),
+    "vit_b4_l32": dict(B=4, L=32, Ld=20, masked_tail=0),
+}
+
+
+def reference_vit_model():
+    sys.path.insert(0, REF)
+    from transformers import T5Config, T5ForConditionalGeneration, ViTConfig, ViTModel
+    cfg = T5Config(vocab_size=32128, d_model=768, d_kv=64, d_ff=3072, num_layers=12, num_decoder_layers=12,
+                   num_heads=12, relative_attention_num_buckets=32, relative_attention_max_distance=128,
+                   dropout_rate=0.1, layer_norm_epsilon=1e-6, feed_forward_proj="relu")
+    T5ForConditionalGeneration.from_pretrained = staticmethod(lambda name, *a, **k: T5ForConditionalGeneration(cfg))
+    ViTModel.from_pretrained = staticmethod(lambda name, *a, **k: ViTModel(ViTConfig()))
+    import model.vit_vqa_model as vref
+    return vref.VitVQAModel("google/vit-base-patch16-224-in21k", "t5-base", answer_spaces=170)
+
+
+def main_vit(out_dir, only):
+    from oracle import vit_oracle as V
+    for name, c in VIT_CASES.items():
+        if only and name not in only:
+            continue
+        sd = V.random_state_dict(170, seed=0)
+        batch = V.synthetic_batch(c["B"], c["L"], c["Ld"], 170, seed=1, masked_tail=c["masked_tail"])
+        m = reference_vit_model()
+        missing = m.load_state_dict(sd, strict=True)
+        m.eval()
+        logp, loss = m(question_input_ids=batch["question_input_ids"],
+                       decoder_question_input_ids=batch["decoder_question_input_ids"],
+                       question_attention_masks=batch["question_attention_masks"],
+                       decoder_question_attention_masks=batch["decoder_question_attention_masks"],
+                       annotation_ids=batch["annotation_ids"], pixel_values=batch["pixel_values"], image_tensors=None,
+                       answer_input_ids=None, answer_attention_masks=None)
+        loss.backward()
+        with torch.no_grad():
+            pooled = m.vision_model(batch["pixel_values"]).pooler_output
+        grads = {k: p.grad for k, p in m.named_parameters()}
+        none_keys = sorted(k for k, g in grads.items() if g is None)
+        gold = dict(case=c, logp=logp.detach().clone(), loss=loss.detach().clone(), vit_pooled=pooled.clone(),
+                    grad_norm={k: float(g.norm()) for k, g in grads.items() if g is not None},
+                    grad_sample={k: sample(g) for k, g in grads.items() if g is not None},
+                    grad_none=none_keys, state_dict_keys=list(m.state_dict().keys()),
+                    param_keys=[k for k, _ in m.named_parameters()], versions=dict(torch=torch.__version__))
+        o_logp, o_loss, o_grads = V.forward_backward(sd, batch)
+        print(name, "loss ref %.6f oracle %.6f | max|dlogp| %.3e | pooled %.3e | n_grad %d n_none %d | %s" % (
+            float(loss), float(o_loss), float((logp - o_logp).abs().max()),
+            float((pooled - V.vit_pooled(sd, batch["pixel_values"])).abs().max()), len(gold["grad_norm"]), len(none_keys),
+            missing))
+        worst = max(float((grads[k] - o_grads[k]).norm() / (grads[k].norm() + 1e-30)) for k in o_grads)
+        print(name, "worst per-tensor grad rel diff oracle vs reference: %.3e" % worst)
+        torch.save(gold, os.path.join(out_dir, name + ".pt"))
+
+
 def sample(g):
     f = g.flatten()
     if f.numel() <= 2304:
@@ -79,6 +135,7 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     only = sys.argv[1:]
+    main_vit(out_dir, only)
     for name, c in CASES.items():
         if only and name not in only:
             continue

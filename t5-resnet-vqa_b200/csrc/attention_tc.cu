@@ -663,6 +663,156 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Long-sequence forward (the frozen ViT-B/16 of VitVQAModel, model/vit_vqa_model.py:184-186; vit: ViTSelfAttention):
+// 197 tokens, hd = 64, softmax(Q K^T / 8) V, no mask / bias / dropout, nothing saved (the ViT runs under no_grad).
+// One CTA per (batch, head, 128-query tile): S[128 x 256] = Q K^T is ONE tcgen05.mma chain (N = 256 keys: two 128-row K
+// tiles, rows past the sequence hold the next sample's finite data or TMA zero fill and are masked in the softmax), the
+// row softmax runs thread-per-row out of TMEM (two passes of 32-column loads), P goes to shared memory as the bf16 K-major
+// A operand [128 x 256] (aliased onto the dead Q / K tiles: 96 KB per CTA, two CTAs per SM), O = P V reads V MN-major
+// straight from its TMA tiles and lands in the recycled S columns.
+// ---------------------------------------------------------------------------------------------------------------------
+struct LongP {
+  int B, H, L;
+  __nv_bfloat16* out; long long ldo;
+  float scale;
+};
+
+__global__ void __launch_bounds__(kThreads)
+attn_long_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const LongP a) {
+  constexpr int HD = 64;
+  constexpr uint32_t kCols = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  // [Q | K0 | K1 | pad] = 4 tiles, re-used as P's four 64-column chunks; then V0 | V1
+  const uint32_t sQ = base, sK = base + kTile, sP = base, sV = base + 4 * kTile;
+  const uint32_t bar_tma = base + 6 * kTile, bar_mma = bar_tma + 8, slot = bar_mma + 8;
+  const uint32_t* slot_ptr = reinterpret_cast<const uint32_t*>(gen + 6 * kTile + 16);
+  const int t = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const int pair = blockIdx.x >> 1, qt = blockIdx.x & 1;
+  const int b = pair / a.H, h = pair - b * a.H;
+
+  pdl_launch_dependents();
+  if (t == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(bar_tma, 1);
+    mbar_init(bar_mma, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(slot, kCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot_ptr;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (t == 0) mbar_expect_tx(bar_tma, 5u * kTile);
+    __syncwarp();
+    if (t < 5) {
+      const CUtensorMap* tm = t == 0 ? &tmQ : (t < 3 ? &tmK : &tmV);
+      const uint32_t dst = t == 0 ? sQ : (t < 3 ? sK + (t - 1) * kTile : sV + (t - 3) * kTile);
+      const int row = b * a.L + (t == 0 ? qt * 128 : ((t - 1) & 1) * 128);
+      tma_load_2d(dst, tm, bar_tma, h * HD, row);
+    }
+    __syncwarp();
+    mbar_wait_lean(bar_tma, 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, 256, false, false);
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks)
+      umma_bf16_e<1>(tmem, umma_smem_desc(sQ + ks * 32, 16u, 1024u), umma_smem_desc(sK + ks * 32, 16u, 1024u), idesc,
+                     ks ? 1u : 0u);
+    umma_commit_e<1>(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait_lean(bar_mma, 0);
+  tc_fence_after();
+
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  const int qi = qt * 128 + t;
+  const bool row_ok = qi < a.L;
+  const int nch = (a.L + 31) >> 5;
+  // pass 1: row maximum of the raw scores (scale > 0)
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < nch; ++c) {
+    uint32_t acc[32];
+    tmem_ld_32x32(tmem + lane_base + c * 32, acc);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 32; ++e)
+      if (c * 32 + e < a.L) mx = fmaxf(mx, __uint_as_float(acc[e]));
+  }
+  // pass 2: exp, row sum, bf16 P (unnormalised; 1/sum goes onto O).  Every thread writes all 256 columns of its row.
+  const float sl2 = a.scale * 1.4426950408889634f;
+  float sum = 0.f;
+  uint8_t* prow = gen + (t >> 3) * 1024 + (t & 7) * 128;
+  const int sw = t & 7;
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    float p[32];
+    if (c < nch) {
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem + lane_base + c * 32, acc);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float ex = (c * 32 + e < a.L) ? exp2f((__uint_as_float(acc[e]) - mx) * sl2) : 0.f;
+        sum += ex;
+        p[e] = ex;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) p[e] = 0.f;
+    }
+    uint8_t* tile = prow + (c >> 1) * kTile;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint4 u;
+      u.x = pack_bf16x2(p[8 * k + 0], p[8 * k + 1]); u.y = pack_bf16x2(p[8 * k + 2], p[8 * k + 3]);
+      u.z = pack_bf16x2(p[8 * k + 4], p[8 * k + 5]); u.w = pack_bf16x2(p[8 * k + 6], p[8 * k + 7]);
+      *reinterpret_cast<uint4*>(tile + ((((c & 1) * 4 + k) ^ sw) << 4)) = u;
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, HD, false, true);
+    const int nks = (a.L + 15) >> 4;
+#pragma unroll 1
+    for (int ks = 0; ks < nks; ++ks) {
+      const uint64_t da = umma_smem_desc(sP + (ks >> 2) * kTile + (ks & 3) * 32, 16u, 1024u);
+      const uint64_t db = umma_smem_desc(sV + ks * 2048, kTile, 1024u);
+      umma_bf16_e<1>(tmem, da, db, idesc, ks ? 1u : 0u);
+    }
+    umma_commit_e<1>(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait_lean(bar_mma, 1);
+  tc_fence_after();
+  __nv_bfloat16* op = a.out + (static_cast<long long>(b) * a.L + (row_ok ? qi : 0)) * a.ldo + h * HD;
+  store_tmem_row_warp<HD>(tmem + lane_base, op, row_ok, 1.f / sum, gen + warp * 2048, t & 31);   // scratch: P (dead)
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, kCols);
+  }
+}
+
+constexpr size_t kLongSmem = 6 * kTile + 64 + 1024;
+
 template <int HD> constexpr size_t fwd_smem_bytes() {
   return (3 * ((HD + 63) / 64) + ((HD + 63) / 64 == 2 ? 0 : 2)) * kTile + 64 + 1024;   // hd = 96: P aliases K
 }
@@ -759,3 +909,29 @@ int attention_tc_bwd(void* plan, const vqa_attn_bwd_args* x, void* stream) {
 }
 
 }  // namespace vqa
+
+extern "C" int vqa_attention_long_fwd(void* plan, const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                                      long long ldv, void* out, long long ldo, int B, int H, int L, int hd, float scale,
+                                      void* stream) {
+  using namespace vqa;
+  if (hd != 64 || L < 1 || L > 256 || B < 1 || H < 1 || !(scale > 0.f)) {
+    set_last_error("attention_long_fwd: hd must be 64, 1 <= L <= 256, scale > 0");
+    return -1;
+  }
+  if ((ldq | ldk | ldv | ldo) & 7) { set_last_error("attention_long_fwd: strides must be multiples of 8"); return -1; }
+  if (reinterpret_cast<uintptr_t>(out) & 15) { set_last_error("attention_long_fwd: out must be 16-byte aligned"); return -1; }
+  CUtensorMap tq, tk, tv;
+  const long long rows = static_cast<long long>(B) * L;
+  if (operand_map(&tq, q, rows, H, hd, ldq, 128, "attention_long_fwd")) return -1;
+  if (operand_map(&tk, k, rows, H, hd, ldk, 128, "attention_long_fwd")) return -1;
+  if (operand_map(&tv, v, rows, H, hd, ldv, 128, "attention_long_fwd")) return -1;
+  LongP a;
+  a.B = B; a.H = H; a.L = L; a.out = static_cast<__nv_bfloat16*>(out); a.ldo = ldo; a.scale = scale;
+  note_op("attention_long_fwd", 4.0 * B * H * static_cast<double>(L) * L * hd, 0.0);
+  return submit(plan, stream, [=](cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) { if (raise_smem(attn_long_fwd_kernel, kLongSmem, "attention_long_fwd")) return -1; attr = true; }
+    launch_pdl(attn_long_fwd_kernel, dim3(B * H * 2), dim3(kThreads), kLongSmem, s, tq, tk, tv, a);
+    return launch_status("attention_long_fwd");
+  });
+}

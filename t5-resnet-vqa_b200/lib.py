@@ -115,6 +115,17 @@ SIGNATURES = {
     "vqa_pooler_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "vqa_logsoftmax_nll_fwd": (c_int, [_P, _P, c_ll, _P, _P, _P, c_int, c_int, _P]),
     "vqa_logsoftmax_nll_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_ll, c_int, c_int, _P]),
+    "vqa_attention_long_fwd": (c_int, [_P, _P, c_ll, _P, c_ll, _P, c_ll, _P, c_ll, c_int, c_int, c_int, c_int, c_f, _P]),
+    "vqa_vit_patchify": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "vqa_vit_assemble": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "vqa_gelu_bf16": (c_int, [_P, _P, c_ll, _P]),
+    "vqa_vit_fuse_concat": (c_int, [_P, _P, _P, c_int, _P, _P, c_int, c_int, _P]),
+    "vqa_xattn1_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_f, c_u32, _P, _P]),
+    "vqa_xattn1_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_f, c_u32, _P, _P]),
+    "vqa_gather_rows": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "vqa_scatter_rows": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "vqa_t5_bias_causal": (c_int, [_P, _P, c_int, c_int, _P]),
+    "vqa_relu_dropout_bwd": (c_int, [_P, _P, _P, _P, c_f, c_ll, _P]),
     "vqa_sumsq_f32": (c_int, [_P, _P, c_ll, _P, _P]),
     "vqa_clip_scale_f32": (c_int, [_P, _P, c_ll, _P, c_f, _P]),
     "vqa_adamw_amsgrad": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_ll, c_d, c_d, c_d, c_d, c_d, c_d, c_d, _P, c_f,
