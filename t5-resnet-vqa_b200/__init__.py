@@ -6,9 +6,9 @@ include/vqa_b200.h via ctypes.  There is no CPU or torch-op fallback: without th
 a GPU the compute entry points raise.
 """
 from . import lib  # noqa: F401
-from .model import FasterRcnnVQAModel, ResnetVQAModel  # noqa: F401
+from .model import FasterRcnnVQAModel, ResnetVQAModel, VitVQAModel  # noqa: F401
 from .optim import VQAFusedAdamW, register as _register_optim  # noqa: F401
 
 _register_optim()
 
-__all__ = ["lib", "ResnetVQAModel", "FasterRcnnVQAModel", "VQAFusedAdamW"]
+__all__ = ["lib", "ResnetVQAModel", "FasterRcnnVQAModel", "VitVQAModel", "VQAFusedAdamW"]

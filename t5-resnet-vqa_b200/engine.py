@@ -400,14 +400,7 @@ class Engine:
         self.lo_fresh = False
         # low-order bf16 halves of the split-precision GEMM weights, at the same offsets as the bf16 shadow.  Two contiguous
         # ranges of `big`: classifier + SGA stack (its head), and T5 blocks n-1 .. 0 (its tail: reverse execution order)
-        blocks = list(self.model.lang_model.block)
-        nsplit = max(0, min(self.t5_split_blocks, len(blocks)))
-        self.t5_split_blocks = nsplit
-        self.lo_ranges = []
-        if self.split_head:
-            self.lo_ranges.append((0, offs[id(self.model._projection().weight)]))
-        if nsplit > 0:
-            self.lo_ranges.append((offs[id(blocks[nsplit - 1].layer[0].SelfAttention.q.weight)], self.n_big))
+        self.lo_ranges = self._split_ranges(offs)
         self.shadow_lo = torch.zeros(self.n_big, dtype=torch.bfloat16, device=device) if self.lo_ranges else None
         self.plans = {}
         self.rng = torch.zeros(2, dtype=torch.int64, device=device)
@@ -416,6 +409,26 @@ class Engine:
         # vision caches are rebuilt whenever the frozen weights change
         self.vision_sig = None
         _REGISTRY[self.master.data_ptr()] = self
+
+    def _split_ranges(self, offs):
+        """[(lo, hi)] element ranges of `big` whose weights also get a low-order bf16 half (split precision)."""
+        blocks = list(self.model.lang_model.block)
+        nsplit = max(0, min(self.t5_split_blocks, len(blocks)))
+        self.t5_split_blocks = nsplit
+        ranges = []
+        if self.split_head:
+            ranges.append((0, offs[id(self.model._projection().weight)]))
+        if nsplit > 0:
+            ranges.append((offs[id(blocks[nsplit - 1].layer[0].SelfAttention.q.weight)], self.n_big))
+        return ranges
+
+    def _after_flatten(self, device):
+        """Model-specific device buffers that follow the flat layout (here: the projection's conv-layout weight)."""
+        proj = self.model._projection()
+        self.proj_w = torch.empty(proj.weight.numel(), dtype=torch.bfloat16, device=device)
+        self.proj_dirty = True
+        from .ddp import maybe_enable
+        maybe_enable(self)
 
     def _reseed(self):
         """Dropout seed = torch's global seed (so a later torch.manual_seed is honoured), mixed with the data-parallel rank (each
@@ -648,18 +661,14 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     def _ensure(self, device):
         if device.type != "cuda":
-            raise RuntimeError("ResnetVQAModel (B200-native) runs on CUDA only: there is no CPU fallback path; "
-                               "move the model and its inputs to a cuda device")
+            raise RuntimeError("%s (B200-native) runs on CUDA only: there is no CPU fallback path; "
+                               "move the model and its inputs to a cuda device" % type(self.model).__name__)
         if self.device is None or not self._params_on(device):
             for p in self.model.parameters():
                 if p.device != device:
                     raise RuntimeError("model parameters are on %s but inputs are on %s" % (p.device, device))
             self._flatten(device)
-            proj = self.model._projection()
-            self.proj_w = torch.empty(proj.weight.numel(), dtype=torch.bfloat16, device=device)
-            self.proj_dirty = True
-            from .ddp import maybe_enable
-            maybe_enable(self)
+            self._after_flatten(device)
 
     def prepare(self):
         """Refresh the folded frozen-backbone weights if their sources changed (the trainable caches are refreshed

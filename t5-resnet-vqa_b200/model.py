@@ -282,3 +282,108 @@ class FasterRcnnVQAModel(_VQAModelBase):
         for k in ("0", "1", "2", "3", "pool"):       # model/faster_rcnn_vqa_model.py:150-154
             d[k] = feats[k]
         return d
+
+
+class VitVQAModel(nn.Module):
+    """Drop-in `VitVQAModel` (reference: model/vit_vqa_model.py:127-351; SURVEY.md 8f-4, BASELINE.json configs[4]): frozen
+    ViT-B/16 pooled output + T5 encoder token 0 -> Linear(1536, 768) + ReLU + Dropout(0.5) -> T5 decoder over the decoder
+    question with a one-token cross-attention -> last un-padded position -> Linear(768, answers) -> log_softmax -> NLLLoss.
+    Same constructor / forward signature, attribute names (`vision_model`, `lang_model`, `fusing_layer`,
+    `classification_layer`: what trainer/vit_vqa_trainer.py:300-318 builds its parameter groups from) and state_dict keys
+    (464 entries, the tied token table under its four names) as the reference."""
+
+    def __init__(self, vision_model_name: str, language_model_name: str, answer_spaces: int,
+                 fine_tune_lm_encoder: bool = True, fine_tune_lm_decoder: bool = True, fine_tune_vision: bool = True,
+                 device="cpu"):
+        super().__init__()
+        if vision_model_name != "google/vit-base-patch16-224-in21k":
+            raise ValueError("vision_model_name must be 'google/vit-base-patch16-224-in21k'")
+        if language_model_name != "t5-base":
+            raise ValueError("language_model_name must be 't5-base'")
+        from .vit_step import VitEngine
+        self.vision_model_name = vision_model_name
+        self.language_model_name = language_model_name
+        self.vision_model = M.ViTModel()
+        self.lang_model = M.T5ForConditionalGeneration()
+        self.fusing_layer = nn.ModuleList([M.Linear(768 + 768, 768)])      # keys fusing_layer.0.{weight,bias} (nn.Sequential)
+        self.classification_layer = M.Linear(768, answer_spaces)
+        self.fine_tune_lm_encoder = fine_tune_lm_encoder
+        self.fine_tune_lm_decoder = fine_tune_lm_decoder
+        self.fine_tune_vision = fine_tune_vision
+        self.device = device
+        self.num_beams = 2
+        self.max_answer_length = 5
+        object.__setattr__(self, "_engine", VitEngine(self))
+        self.register_state_dict_pre_hook(lambda module, prefix, keep_vars: module._engine.wait_optimizer())
+        self._load_pretrained()
+
+    def _load_pretrained(self):
+        """The reference starts from pretrained HF weights (:146-150); offline they are used only when cached locally."""
+        mode = os.environ.get("VQA_B200_PRETRAINED", "auto")
+        self.pretrained_loaded = []
+        if mode == "0":
+            return
+        try:
+            from transformers import T5ForConditionalGeneration, ViTModel
+            vit = ViTModel.from_pretrained(self.vision_model_name, local_files_only=True)
+            self.vision_model.load_state_dict(vit.state_dict())
+            self.pretrained_loaded.append("vision")
+            t5 = T5ForConditionalGeneration.from_pretrained(self.language_model_name, local_files_only=True)
+            self.lang_model.load_state_dict(t5.state_dict())
+            self.pretrained_loaded.append("t5")
+        except Exception:  # pragma: no cover - depends on local caches
+            if mode == "1":
+                raise
+
+    def named_parameters(self, *args, **kwargs):
+        self._engine.wait_optimizer()
+        return super().named_parameters(*args, **kwargs)
+
+    def _run(self, question_input_ids, decoder_question_input_ids, question_attention_masks,
+             decoder_question_attention_masks, annotation_ids, pixel_values):
+        if pixel_values is None or decoder_question_input_ids is None:
+            raise ValueError("VitVQAModel needs pixel_values and decoder_question_input_ids")
+        if question_input_ids.dim() != 2 or decoder_question_input_ids.dim() != 2 or pixel_values.dim() != 4:
+            raise ValueError("expected question_input_ids [B, L], decoder_question_input_ids [B, Ld], pixel_values [B,3,H,W]")
+        dev = self.classification_layer.weight.device
+        eng = self._engine
+        eng._ensure(dev)
+        B, Lt = question_input_ids.shape
+        Ld = decoder_question_input_ids.shape[1]
+        has_labels = annotation_ids is not None
+        eng.prepare()
+        st = eng.get_plan(B, Lt, Ld, pixel_values.shape[2], pixel_values.shape[3], self.training, has_labels)
+        eng.forward(st, question_input_ids, question_attention_masks, decoder_question_input_ids,
+                    decoder_question_attention_masks, annotation_ids, pixel_values.float())
+        if torch.is_grad_enabled() and any(p.requires_grad for p in eng.params):
+            out = _StepFunction.apply(self, st, has_labels, *eng.params)
+            logp, loss = (out if has_labels else (out, None))
+        else:
+            logp = st.logp.clone()
+            loss = st.loss.reshape(()).clone() if has_labels else None
+        return logp, loss, st
+
+    def forward(self, question_input_ids: torch.Tensor, decoder_question_input_ids: torch.Tensor = None,
+                question_attention_masks: torch.Tensor = None, decoder_question_attention_masks: torch.Tensor = None,
+                annotation_ids: torch.Tensor = None, pixel_values: torch.Tensor = None, image_tensors: torch.Tensor = None,
+                answer_input_ids: torch.Tensor = None, answer_attention_masks: torch.Tensor = None,
+                question_type_ids: torch.Tensor = None):
+        logp, loss, _ = self._run(question_input_ids, decoder_question_input_ids, question_attention_masks,
+                                  decoder_question_attention_masks, annotation_ids, pixel_values)
+        return logp, loss
+
+    def vision_pooler_output(self):
+        """pooler_output of the frozen ViT for the last forward's batch, fp32 [B, 768] (what :186 feeds the fusing layer)."""
+        return self._engine.last_state.pooled.clone()
+
+    def generate_answers(self, question_input_ids: torch.Tensor, decoder_question_input_ids: torch.Tensor = None,
+                         question_attention_masks: torch.Tensor = None,
+                         decoder_question_attention_masks: torch.Tensor = None, pixel_values: torch.Tensor = None,
+                         image_tensors: torch.Tensor = None, answer_input_ids: torch.Tensor = None,
+                         answer_attention_masks: torch.Tensor = None, annotation_ids: torch.Tensor = None,
+                         question_type_ids: torch.Tensor = None):
+        """(log_probs, loss or None, attentions) as model/vit_vqa_model.py:229-293.  The ViT's per-layer attention maps (the
+        third element, used only by the heat-map script ViT_vqa_heatmap.py) are not materialised by the flash kernel: None."""
+        logp, loss, _ = self._run(question_input_ids, decoder_question_input_ids, question_attention_masks,
+                                  decoder_question_attention_masks, annotation_ids, pixel_values)
+        return logp, loss, None

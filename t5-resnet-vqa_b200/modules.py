@@ -370,3 +370,130 @@ class BackboneWithFPN(_Holder):
         self.body = ResNet50Body()
         self.fpn = FeaturePyramidNetwork()
         self.out_channels = 256
+
+
+# ------------------------------------------------------------------------------------------------
+# VitVQAModel (model/vit_vqa_model.py:127-227): transformers ViTModel and T5ForConditionalGeneration key layouts
+# ------------------------------------------------------------------------------------------------
+class T5LayerCrossAttention(_Holder):
+    def __init__(self, cfg):
+        super().__init__()
+        self.EncDecAttention = T5Attention(cfg["d_model"], cfg["d_kv"], cfg["num_heads"], False, cfg["num_buckets"])
+        self.layer_norm = RMSNormParams(cfg["d_model"], cfg["eps"])
+
+
+class T5DecoderBlock(_Holder):
+    def __init__(self, cfg, has_bias):
+        super().__init__()
+        self.layer = nn.ModuleList([T5LayerSelfAttention(cfg, has_bias), T5LayerCrossAttention(cfg), T5LayerFF(cfg)])
+
+
+class T5Stack(_Holder):
+    """encoder / decoder of T5ForConditionalGeneration; `embed_tokens` IS the model's shared table (same module object)."""
+
+    def __init__(self, cfg, shared, is_decoder):
+        super().__init__()
+        self.cfg = cfg
+        self.is_decoder = is_decoder
+        self.embed_tokens = shared
+        blk = T5DecoderBlock if is_decoder else T5Block
+        self.block = nn.ModuleList([blk(cfg, i == 0) for i in range(cfg["num_layers"])])
+        self.final_layer_norm = RMSNormParams(cfg["d_model"], cfg["eps"])
+
+
+class T5ForConditionalGeneration(_Holder):
+    """`T5ForConditionalGeneration.from_pretrained("t5-base")` (model/vit_vqa_model.py:149-150): state_dict keys shared.weight,
+    encoder.embed_tokens.weight, encoder.block.*, decoder.embed_tokens.weight, decoder.block.*, lm_head.weight; the four
+    token-table names are ONE tied parameter (named_parameters() lists it once, as shared.weight).  lm_head is never
+    evaluated on this path (the model classifies from the decoder's last hidden state)."""
+
+    def __init__(self, cfg=None):
+        super().__init__()
+        cfg = dict(T5_BASE if cfg is None else cfg)
+        self.cfg = cfg
+        self.shared = Embedding(cfg["vocab"], cfg["d_model"], std=1.0)
+        self.encoder = T5Stack(cfg, self.shared, False)
+        self.decoder = T5Stack(cfg, self.shared, True)
+        self.lm_head = Linear(cfg["d_model"], cfg["vocab"], bias=False, std=1.0)
+        self.lm_head.weight = self.shared.weight
+
+
+VIT_BASE = dict(hidden=768, heads=12, layers=12, inter=3072, patch=16, image=224, eps=1e-12, init_range=0.02)
+
+
+class _Dense(_Holder):
+    def __init__(self, cin, cout, std):
+        super().__init__()
+        self.dense = Linear(cin, cout, std=std)
+        with torch.no_grad():
+            self.dense.bias.zero_()
+
+
+class ViTSelfAttention(_Holder):
+    def __init__(self, d, std):
+        super().__init__()
+        for nm in ("query", "key", "value"):
+            lin = Linear(d, d, std=std)
+            with torch.no_grad():
+                lin.bias.zero_()
+            setattr(self, nm, lin)
+
+
+class ViTAttention(_Holder):
+    def __init__(self, d, std):
+        super().__init__()
+        self.attention = ViTSelfAttention(d, std)
+        self.output = _Dense(d, d, std)
+
+
+class ViTLayer(_Holder):
+    def __init__(self, cfg):
+        super().__init__()
+        d, std = cfg["hidden"], cfg["init_range"]
+        self.attention = ViTAttention(d, std)
+        self.intermediate = _Dense(d, cfg["inter"], std)
+        self.output = _Dense(cfg["inter"], d, std)
+        self.layernorm_before = LayerNormParams(d, cfg["eps"])
+        self.layernorm_after = LayerNormParams(d, cfg["eps"])
+
+
+class ViTEncoder(_Holder):
+    def __init__(self, cfg):
+        super().__init__()
+        self.layer = nn.ModuleList([ViTLayer(cfg) for _ in range(cfg["layers"])])
+
+
+class Conv2dPatch(_Holder):
+    def __init__(self, cin, cout, k, std):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin, k, k).normal_(0.0, std))
+        self.bias = nn.Parameter(torch.zeros(cout))
+
+
+class ViTPatchEmbeddings(_Holder):
+    def __init__(self, cfg):
+        super().__init__()
+        self.projection = Conv2dPatch(3, cfg["hidden"], cfg["patch"], cfg["init_range"])
+
+
+class ViTEmbeddings(_Holder):
+    def __init__(self, cfg):
+        super().__init__()
+        n = (cfg["image"] // cfg["patch"]) ** 2
+        self.cls_token = nn.Parameter(torch.empty(1, 1, cfg["hidden"]).normal_(0.0, cfg["init_range"]))
+        self.position_embeddings = nn.Parameter(torch.empty(1, n + 1, cfg["hidden"]).normal_(0.0, cfg["init_range"]))
+        self.patch_embeddings = ViTPatchEmbeddings(cfg)
+
+
+class ViTModel(_Holder):
+    """`ViTModel.from_pretrained("google/vit-base-patch16-224-in21k")` (model/vit_vqa_model.py:146-147): embeddings, 12 pre-LN
+    layers, final layernorm, tanh pooler.  Frozen on this path (the reference evaluates it under torch.no_grad())."""
+
+    def __init__(self, cfg=None):
+        super().__init__()
+        cfg = dict(VIT_BASE if cfg is None else cfg)
+        self.cfg = cfg
+        self.embeddings = ViTEmbeddings(cfg)
+        self.encoder = ViTEncoder(cfg)
+        self.layernorm = LayerNormParams(cfg["hidden"], cfg["eps"])
+        self.pooler = _Dense(cfg["hidden"], cfg["hidden"], cfg["init_range"])

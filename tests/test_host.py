@@ -229,3 +229,25 @@ def test_tile_model_agrees_with_the_measured_table(pkg):
         bn, ks = E.pick_tile(M, N, K)
         assert ks == 1
         assert t[bn] <= 1.12 * min(t.values()), (kind, M, N, K, bn, t)
+
+
+def test_vit_vqa_model_surface_and_tied_table(pkg):
+    """VitVQAModel (model/vit_vqa_model.py:127-227): constructor arguments, state_dict layout of the reference (464 entries,
+    the tied token table under four names), named_parameters lists it once, strict load both ways, no CPU path."""
+    import os
+    os.environ["VQA_B200_PRETRAINED"] = "0"
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vit_b2_l16.pt"), weights_only=False)
+    m = pkg.VitVQAModel("google/vit-base-patch16-224-in21k", "t5-base", answer_spaces=170)
+    assert list(m.state_dict().keys()) == gold["state_dict_keys"] and len(gold["state_dict_keys"]) == 464
+    assert [k for k, _ in m.named_parameters()] == gold["param_keys"]
+    sd = m.state_dict()
+    assert sd["lang_model.shared.weight"].data_ptr() == sd["lang_model.decoder.embed_tokens.weight"].data_ptr()
+    assert sd["lang_model.shared.weight"].data_ptr() == sd["lang_model.lm_head.weight"].data_ptr()
+    from oracle import vit_oracle as V
+    m.load_state_dict(V.random_state_dict(170, seed=0), strict=True)
+    for attr in ("vision_model", "lang_model", "fusing_layer", "classification_layer"):   # trainer/vit_vqa_trainer.py:300-318
+        assert len(list(getattr(m, attr).parameters())) > 0
+    with pytest.raises(ValueError):
+        pkg.VitVQAModel("resnet50", "t5-base", 170)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(2, 16, dtype=torch.long), torch.zeros(2, 20, dtype=torch.long), pixel_values=torch.zeros(2, 3, 224, 224))
