@@ -145,6 +145,10 @@ int vqa_cast_bf16_f32(void* plan, const void* src, float* dst, long long n, void
 /* dst[i] = bf16(src[i] - float(bf16(src[i]))): the low-order half of the two-term split of an fp32 weight range */
 int vqa_split_lo_bf16(void* plan, const float* src, void* dst, long long n, void* stream);
 int vqa_memset_zero(void* plan, void* ptr, long long bytes, void* stream);
+/* device-to-device copy as a plan step (the frozen backbone's last feature map is copied out of the backbone's own buffers at
+ * the start of the projection plan, so that the NEXT step's backbone may overwrite them while this step's backward still reads
+ * the copy: engine.forward, "early backbone") */
+int vqa_memcpy_d2d(void* plan, void* dst, const void* src, long long bytes, void* stream);
 int vqa_axpy_f32(void* plan, float* y, const float* x, float a, long long n, void* stream); /* y += a*x */
 /* Conv2d weight [O,I,R,S] fp32 (+ eval BatchNorm gamma/beta/mean/var, may be NULL) -> bf16
  * [O, R, Sp, Ip] (zero padded) scaled by gamma/sqrt(var+eps), and bias[O] = beta - mean*scale.

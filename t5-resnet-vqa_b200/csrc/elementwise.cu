@@ -383,6 +383,15 @@ int vqa_memset_zero(void* plan, void* ptr, long long bytes, void* stream) {
   });
 }
 
+int vqa_memcpy_d2d(void* plan, void* dst, const void* src, long long bytes, void* stream) {
+  note_op("memcpy", 0.0, 2.0 * static_cast<double>(bytes));
+  return submit(plan, stream, [=](cudaStream_t s) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) { set_last_error("memcpy: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+    return 0;
+  });
+}
+
 int vqa_axpy_f32(void* plan, float* y, const float* x, float a, long long n, void* stream) {
   note_op("axpy", 0.0, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {

@@ -84,6 +84,7 @@ SIGNATURES = {
     "vqa_cast_bf16_f32": (c_int, [_P, _P, _P, c_ll, _P]),
     "vqa_split_lo_bf16": (c_int, [_P, _P, _P, c_ll, _P]),
     "vqa_memset_zero": (c_int, [_P, _P, c_ll, _P]),
+    "vqa_memcpy_d2d": (c_int, [_P, _P, _P, c_ll, _P]),
     "vqa_axpy_f32": (c_int, [_P, _P, _P, c_f, c_ll, _P]),
     "vqa_fold_conv_bn": (c_int, [_P, _P, _P, _P, _P, _P, c_f, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "vqa_convT_weight_prep": (c_int, [_P, _P, _P, c_int, c_int, _P]),

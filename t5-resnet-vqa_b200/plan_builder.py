@@ -202,6 +202,13 @@ def build_state(eng, B, Lt, H, W, training, has_labels, want_features, u8_images
     My = B * Ty
     y0 = al(My, D)
     r = eng.rec(st.fwd_proj, st.ks_store)
+    # The backbone's last map is copied out of the backbone's own buffers here: backward reads the copy (projection weight
+    # gradient), so the NEXT step's backbone - which needs nothing but its images - may start while this step's text forward
+    # and backward still run (engine.forward: fwd_vis is not ordered behind the previous backward).  12.8 MB at batch 64.
+    feat_keep = al(B, Hf, Wf, Cf)
+    r.memcpy_d2d(feat_keep, feat, 2 * B * Hf * Wf * Cf)
+    feat = feat_keep
+    st.early_backbone_ok = not want_features     # the exported maps are read by the caller's stream after the forward
     r.conv(B, Hf, Wf, Cf, D, 3, 1, 1, feat, eng.proj_w, y0, bias=eng.mp(proj.bias), relu=0)
     # T5 blocks per backward segment, from the LAST block down (= per gradient-exchange bucket under data parallelism).  The
     # final segments are short: the exchange of the last one cannot overlap anything, and under the sharded optimizer the
