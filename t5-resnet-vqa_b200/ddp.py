@@ -93,6 +93,8 @@ class GradSync:
         """[(lo, big_hi, own_lo, own_hi)] per backward segment with GEMM weights, or None when this step cannot be sharded
         (mode, wire format, no fused optimizer over the whole engine, or a segment that does not split evenly)."""
         opt = eng.fused_opt() if eng.fused_opt is not None else None
+        if not getattr(eng, "ddp_shardable", True):
+            return None
         if self.mode != "zero1" or self.wire != "bf16" or opt is None or opt.max_grad_norm is not None:
             return None
         out = []
@@ -121,7 +123,7 @@ class GradSync:
             tr = dict(start=torch.cuda.Event(enable_timing=True), seg=[], comm=[])
             tr["start"].record(cur)
             self.trace.append(tr)
-        emb = eng.model.lang_model.embed_tokens.weight
+        emb = eng.embedding_param()
         emb_lo = eng.offs[id(emb)]
         shards = self.shards_for(eng, st)
         eng.ddp_shards = shards              # read by clip_grad_norm_ and VQAFusedAdamW.step for THIS step
@@ -136,7 +138,7 @@ class GradSync:
             lo, hi = seg.grad_lo, seg.grad_hi
             if hi <= lo:
                 continue
-            rows = st.emb_rows if (lo <= emb_lo < hi) else None
+            rows = getattr(st, "emb_rows", None) if (lo <= emb_lo < hi) else None
             if rows is not None:
                 hi = emb_lo          # the table itself is not exchanged (it is the last tensor of the flat buffer)
             sh = shard_of.get(lo)

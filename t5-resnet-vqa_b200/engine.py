@@ -431,6 +431,12 @@ class Engine:
         from .ddp import maybe_enable
         maybe_enable(self)
 
+    ddp_shardable = True          # the sharded optimizer's pipelined all-gather needs this engine's segmented text forward
+
+    def embedding_param(self):
+        """The token table (last tensor of the flat buffers; exchanged as rows under data parallelism)."""
+        return self.model.lang_model.embed_tokens.weight
+
     def _reseed(self):
         """Dropout seed = torch's global seed (so a later torch.manual_seed is honoured), mixed with the data-parallel rank (each
         replica draws its own masks); VQA_B200_SEED pins it.  The Philox offset restarts at 0."""

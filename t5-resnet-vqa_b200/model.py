@@ -314,7 +314,8 @@ class VitVQAModel(nn.Module):
         self.num_beams = 2
         self.max_answer_length = 5
         object.__setattr__(self, "_engine", VitEngine(self))
-        self.register_state_dict_pre_hook(lambda module, prefix, keep_vars: module._engine.wait_optimizer())
+        self.register_state_dict_pre_hook(lambda module, prefix, keep_vars: (module._engine.wait_optimizer(),
+                                                                              module._engine.sync_master()))
         self._load_pretrained()
 
     def _load_pretrained(self):

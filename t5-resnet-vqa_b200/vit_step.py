@@ -38,8 +38,9 @@ def t5_causal_buckets(L_q, L_k, num_buckets=32, max_distance=128):
 
 class VitEngine(Engine):
     """Flat fp32 master / gradient / bf16 shadow buffers over the trainable parameters of VitVQAModel (T5 encoder + decoder,
-    fusing layer, classifier) and bf16 / fp32 caches of the frozen ViT.  Single-GPU (the reference trainer is; data
-    parallelism is built for the north-star ResnetVQAModel step only)."""
+    fusing layer, classifier) and bf16 / fp32 caches of the frozen ViT.  Data parallel as full replicas: the flat gradient is
+    averaged with one all-reduce (bf16 wire) behind the single backward segment (ddp.GradSync, all-reduce mode); the sharded
+    optimizer and the row exchange of the token table are built for the north-star ResnetVQAModel step only."""
 
     def __init__(self, model):
         super().__init__(model)
@@ -74,10 +75,14 @@ class VitEngine(Engine):
     def _split_ranges(self, offs):
         return []
 
+    ddp_shardable = False         # replicas + one all-reduce of the flat gradient after backward (one backward segment)
+
+    def embedding_param(self):
+        return self.model.lang_model.shared.weight
+
     def _after_flatten(self, device):
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            raise RuntimeError("VitVQAModel (B200-native) is single-GPU: data parallelism covers the ResnetVQAModel step")
+        from .ddp import maybe_enable
+        maybe_enable(self)
 
     def _refresh_projection(self):
         pass

@@ -13,8 +13,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("wire,mode", [("bf16", "zero1"), ("bf16", "allreduce"), ("fp32", "allreduce")])
-def test_n_rank_step_equals_single_rank_step(cuda, wire, mode):
+@pytest.mark.parametrize("wire,mode,model", [("bf16", "zero1", "resnet"), ("bf16", "allreduce", "resnet"),
+                                             ("fp32", "allreduce", "resnet"), ("bf16", "zero1", "vit")])
+def test_n_rank_step_equals_single_rank_step(cuda, wire, mode, model):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -22,7 +23,7 @@ def test_n_rank_step_equals_single_rank_step(cuda, wire, mode):
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    env = dict(os.environ, VQA_B200_DDP_GRAD_DTYPE=wire, VQA_B200_DDP_MODE=mode)
+    env = dict(os.environ, VQA_B200_DDP_GRAD_DTYPE=wire, VQA_B200_DDP_MODE=mode, VQA_DDP_CHECK_MODEL=model)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 2)),
                         "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "ddp_check.py")],
                        env=env, capture_output=True, text=True, timeout=600)
