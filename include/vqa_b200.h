@@ -276,9 +276,11 @@ int vqa_logsoftmax_nll_bwd(void* plan, const float* logp, const long long* label
 /* ---- VitVQAModel step (model/vit_vqa_model.py:127-227).  `vit:` = transformers/models/vit/modeling_vit.py -- */
 /* softmax(scale * Q K^T) V for ONE sequence length L <= 256 on both sides, hd = 64, no mask / bias / dropout, nothing saved:
  * the frozen ViT-B/16's self-attention over 197 tokens (vit: ViTSelfAttention; the reference runs it under torch.no_grad(),
- * model/vit_vqa_model.py:184-186).  tcgen05 kernel, one CTA per (batch, head, 128-query tile).  Indexing as vqa_attn_fwd_args. */
+ * model/vit_vqa_model.py:184-186; probs != NULL also writes the softmax, output_attentions=True of :240-243).  tcgen05 kernel, one CTA per (batch, head, 128-query tile).  Indexing as vqa_attn_fwd_args. */
 int vqa_attention_long_fwd(void* plan, const void* q, long long ldq, const void* k, long long ldk, const void* v,
-                           long long ldv, void* out, long long ldo, int B, int H, int L, int hd, float scale, void* stream);
+                           long long ldv, void* out, long long ldo, int B, int H, int L, int hd, float scale,
+                           float* probs /* optional fp32 [B,H,L,L]: the attention maps generate_answers returns */,
+                           void* stream);
 /* pixel_values fp32 [B,3,H,W] -> bf16 [B*(H/P)*(W/P), 3*P*P] patch rows (column = c*P*P + ky*P + kx): the A operand of the
  * patch-projection GEMM, Conv2d(3,768,P,stride P) as a matrix product (vit: ViTPatchEmbeddings) */
 int vqa_vit_patchify(void* plan, const float* img, void* out, int B, int H, int W, int P, void* stream);

@@ -156,7 +156,7 @@ def synthetic_batch(B, L=32, Ld=20, answers=170, seed=1, masked_tail=0, dec_leng
 # --------------------------------------------------------------------------------------------------
 # forward restatement
 # --------------------------------------------------------------------------------------------------
-def vit_pooled(sd, pixel_values, p="vision_model.", return_hidden=False):
+def vit_pooled(sd, pixel_values, p="vision_model.", return_hidden=False, return_attn=False):
     """ViTModel(pixel_values).pooler_output in eval mode (vit: ViTEmbeddings, ViTLayer (pre-LN, exact GELU), ViTPooler)."""
     d, nh = VIT["hidden"], VIT["heads"]
     hd = d // nh
@@ -166,6 +166,7 @@ def vit_pooled(sd, pixel_values, p="vision_model.", return_hidden=False):
     B = x.shape[0]
     x = torch.cat([sd[p + "embeddings.cls_token"].expand(B, -1, -1), x], dim=1) + sd[p + "embeddings.position_embeddings"]
     T = x.shape[1]
+    attn = []
     for i in range(VIT["layers"]):
         l = "%sencoder.layer.%d." % (p, i)
         n = F.layer_norm(x, (d,), sd[l + "layernorm_before.weight"], sd[l + "layernorm_before.bias"], VIT["eps"])
@@ -174,6 +175,7 @@ def vit_pooled(sd, pixel_values, p="vision_model.", return_hidden=False):
         k = F.linear(n, sd[a + "key.weight"], sd[a + "key.bias"]).view(B, T, nh, hd).transpose(1, 2)
         v = F.linear(n, sd[a + "value.weight"], sd[a + "value.bias"]).view(B, T, nh, hd).transpose(1, 2)
         w = F.softmax(torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
+        attn.append(w)
         ctx = torch.matmul(w, v).transpose(1, 2).reshape(B, T, d)
         x = x + F.linear(ctx, sd[l + "attention.output.dense.weight"], sd[l + "attention.output.dense.bias"])
         n = F.layer_norm(x, (d,), sd[l + "layernorm_after.weight"], sd[l + "layernorm_after.bias"], VIT["eps"])
@@ -181,6 +183,8 @@ def vit_pooled(sd, pixel_values, p="vision_model.", return_hidden=False):
         x = x + F.linear(h, sd[l + "output.dense.weight"], sd[l + "output.dense.bias"])
     x = F.layer_norm(x, (d,), sd[p + "layernorm.weight"], sd[p + "layernorm.bias"], VIT["eps"])
     pooled = torch.tanh(F.linear(x[:, 0], sd[p + "pooler.dense.weight"], sd[p + "pooler.dense.bias"]))
+    if return_attn:          # ViTModel(..., output_attentions=True).attentions (model/vit_vqa_model.py:240-243)
+        return pooled, tuple(attn)
     return (pooled, x) if return_hidden else pooled
 
 

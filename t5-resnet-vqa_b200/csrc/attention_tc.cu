@@ -677,6 +677,7 @@ struct LongP {
   int B, H, L;
   __nv_bfloat16* out; long long ldo;
   float scale;
+  float* probs;      // optional fp32 [B, H, L, L] softmax output (output_attentions=True of generate_answers), else null
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -781,6 +782,23 @@ attn_long_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       u.x = pack_bf16x2(p[8 * k + 0], p[8 * k + 1]); u.y = pack_bf16x2(p[8 * k + 2], p[8 * k + 3]);
       u.z = pack_bf16x2(p[8 * k + 4], p[8 * k + 5]); u.w = pack_bf16x2(p[8 * k + 6], p[8 * k + 7]);
       *reinterpret_cast<uint4*>(tile + ((((c & 1) * 4 + k) ^ sw) << 4)) = u;
+    }
+  }
+  if (a.probs != nullptr) {
+    // pass 3 (heat-map path only): the normalised probabilities of this row, from the scores still in TMEM.  The TMEM load
+    // is warp-collective (.sync.aligned): every lane runs it, only rows inside the sequence store.
+    const float inv = 1.f / sum;
+    float* pr = a.probs + ((static_cast<long long>(b) * a.H + h) * a.L + (row_ok ? qi : 0)) * a.L;
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem + lane_base + c * 32, acc);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (c * 32 + e < a.L) pr[c * 32 + e] = exp2f((__uint_as_float(acc[e]) - mx) * sl2) * inv;
+      }
     }
   }
   fence_async_smem();
@@ -912,7 +930,7 @@ int attention_tc_bwd(void* plan, const vqa_attn_bwd_args* x, void* stream) {
 
 extern "C" int vqa_attention_long_fwd(void* plan, const void* q, long long ldq, const void* k, long long ldk, const void* v,
                                       long long ldv, void* out, long long ldo, int B, int H, int L, int hd, float scale,
-                                      void* stream) {
+                                      float* probs, void* stream) {
   using namespace vqa;
   if (hd != 64 || L < 1 || L > 256 || B < 1 || H < 1 || !(scale > 0.f)) {
     set_last_error("attention_long_fwd: hd must be 64, 1 <= L <= 256, scale > 0");
@@ -926,7 +944,7 @@ extern "C" int vqa_attention_long_fwd(void* plan, const void* q, long long ldq, 
   if (operand_map(&tk, k, rows, H, hd, ldk, 128, "attention_long_fwd")) return -1;
   if (operand_map(&tv, v, rows, H, hd, ldv, 128, "attention_long_fwd")) return -1;
   LongP a;
-  a.B = B; a.H = H; a.L = L; a.out = static_cast<__nv_bfloat16*>(out); a.ldo = ldo; a.scale = scale;
+  a.B = B; a.H = H; a.L = L; a.out = static_cast<__nv_bfloat16*>(out); a.ldo = ldo; a.scale = scale; a.probs = probs;
   note_op("attention_long_fwd", 4.0 * B * H * static_cast<double>(L) * L * hd, 0.0);
   return submit(plan, stream, [=](cudaStream_t s) {
     static bool attr = false;

@@ -116,7 +116,7 @@ SIGNATURES = {
     "vqa_pooler_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "vqa_logsoftmax_nll_fwd": (c_int, [_P, _P, c_ll, _P, _P, _P, c_int, c_int, _P]),
     "vqa_logsoftmax_nll_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_ll, c_int, c_int, _P]),
-    "vqa_attention_long_fwd": (c_int, [_P, _P, c_ll, _P, c_ll, _P, c_ll, _P, c_ll, c_int, c_int, c_int, c_int, c_f, _P]),
+    "vqa_attention_long_fwd": (c_int, [_P, _P, c_ll, _P, c_ll, _P, c_ll, _P, c_ll, c_int, c_int, c_int, c_int, c_f, _P, _P]),
     "vqa_vit_patchify": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "vqa_vit_assemble": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "vqa_gelu_bf16": (c_int, [_P, _P, c_ll, _P]),

@@ -341,7 +341,7 @@ class VitVQAModel(nn.Module):
         return super().named_parameters(*args, **kwargs)
 
     def _run(self, question_input_ids, decoder_question_input_ids, question_attention_masks,
-             decoder_question_attention_masks, annotation_ids, pixel_values):
+             decoder_question_attention_masks, annotation_ids, pixel_values, want_attn=False):
         if pixel_values is None or decoder_question_input_ids is None:
             raise ValueError("VitVQAModel needs pixel_values and decoder_question_input_ids")
         if question_input_ids.dim() != 2 or decoder_question_input_ids.dim() != 2 or pixel_values.dim() != 4:
@@ -353,7 +353,7 @@ class VitVQAModel(nn.Module):
         Ld = decoder_question_input_ids.shape[1]
         has_labels = annotation_ids is not None
         eng.prepare()
-        st = eng.get_plan(B, Lt, Ld, pixel_values.shape[2], pixel_values.shape[3], self.training, has_labels)
+        st = eng.get_plan(B, Lt, Ld, pixel_values.shape[2], pixel_values.shape[3], self.training, has_labels, want_attn)
         eng.forward(st, question_input_ids, question_attention_masks, decoder_question_input_ids,
                     decoder_question_attention_masks, annotation_ids, pixel_values.float())
         if torch.is_grad_enabled() and any(p.requires_grad for p in eng.params):
@@ -383,8 +383,9 @@ class VitVQAModel(nn.Module):
                          image_tensors: torch.Tensor = None, answer_input_ids: torch.Tensor = None,
                          answer_attention_masks: torch.Tensor = None, annotation_ids: torch.Tensor = None,
                          question_type_ids: torch.Tensor = None):
-        """(log_probs, loss or None, attentions) as model/vit_vqa_model.py:229-293.  The ViT's per-layer attention maps (the
-        third element, used only by the heat-map script ViT_vqa_heatmap.py) are not materialised by the flash kernel: None."""
-        logp, loss, _ = self._run(question_input_ids, decoder_question_input_ids, question_attention_masks,
-                                  decoder_question_attention_masks, annotation_ids, pixel_values)
-        return logp, loss, None
+        """(log_probs, loss or None, attentions) as model/vit_vqa_model.py:229-293: attentions = the ViT's twelve per-layer
+        attention maps, fp32 [B, 12, 197, 197] (ViTModel(..., output_attentions=True), :240-243; what ViT_vqa_heatmap.py rolls
+        out), written by the attention kernel itself on this path."""
+        logp, loss, st = self._run(question_input_ids, decoder_question_input_ids, question_attention_masks,
+                                   decoder_question_attention_masks, annotation_ids, pixel_values, want_attn=True)
+        return logp, loss, tuple(t.clone() for t in st.attentions)

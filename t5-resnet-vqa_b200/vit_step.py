@@ -155,8 +155,8 @@ class VitEngine(Engine):
         return self.vit_f.data_ptr() + 4 * self.vit_foff[name]
 
     # ---- plans ----
-    def get_plan(self, B, Lt, Ld, H, W, training, has_labels):
-        key = (B, Lt, Ld, H, W, bool(training), bool(has_labels))
+    def get_plan(self, B, Lt, Ld, H, W, training, has_labels, want_attn=False):
+        key = (B, Lt, Ld, H, W, bool(training), bool(has_labels), bool(want_attn))
         st = self.plans.get(key)
         if st is None:
             st = build_state(self, *key)
@@ -386,7 +386,7 @@ class _T5Stack:
         r.embedding_bwd(self.ids, dH, eng.gp(self.stack.embed_tokens.weight), M, D, vocab, p, self.sid_embed, rng)
 
 
-def build_state(eng, B, Lt, Ld, H, W, training, has_labels):
+def build_state(eng, B, Lt, Ld, H, W, training, has_labels, want_attn=False):
     m, dev, lib = eng.model, eng.device, eng.lib
     if not eng.use_tc_attention or Lt > 64 or Ld > 64:
         raise RuntimeError("VitVQAModel (B200-native): question / decoder lengths up to 64 tokens (tcgen05 attention)")
@@ -440,12 +440,15 @@ def build_state(eng, B, Lt, Ld, H, W, training, has_labels):
     r.vit_assemble(proj, eng.vf("cls"), eng.vf("pos"), hid_a, B, NP, Dv)
     nrm, qkv, ctx, hbuf = al(Mv, Dv), al(Mv, 3 * Dv), al(Mv, Dv), al(Mv, Iv)
     mean_s, rstd_s = al(Mv, dtype=f32), al(Mv, dtype=f32)
+    st.attentions = []      # generate_answers: the ViT's per-layer attention maps, fp32 [B, heads, T, T] (:240-243)
     for i in range(vcfg["layers"]):
         pre = "l%d." % i
+        if want_attn:
+            st.attentions.append(al(B, Hv, T, T, dtype=f32))
         r.layernorm_fwd(hid_a, eng.vf(pre + "ln1_w"), eng.vf(pre + "ln1_b"), nrm, None, mean_s, rstd_s, Mv, Dv, veps)
         r.linear(nrm, Mv, Dv, Dv, eng.vw(pre + "qkv"), 3 * Dv, qkv, 3 * Dv, bias=eng.vf(pre + "qkv_b"))
         r.attention_long_fwd(qkv, 3 * Dv, qkv.data_ptr() + 2 * Dv, 3 * Dv, qkv.data_ptr() + 4 * Dv, 3 * Dv, ctx, Dv,
-                             B, Hv, T, Dv // Hv, 1.0 / math.sqrt(Dv // Hv))
+                             B, Hv, T, Dv // Hv, 1.0 / math.sqrt(Dv // Hv), st.attentions[i] if want_attn else None)
         r.linear(ctx, Mv, Dv, Dv, eng.vw(pre + "o"), Dv, hid_b, Dv, out_fp32=1, bias=eng.vf(pre + "o_b"),
                  residual=hid_a, ldr=Dv, res_fp32=1)
         r.layernorm_fwd(hid_b, eng.vf(pre + "ln2_w"), eng.vf(pre + "ln2_b"), nrm, None, mean_s, rstd_s, Mv, Dv, veps)

@@ -30,13 +30,16 @@ def test_attention_long_fwd(C, B, H, L):
     qkv = rnd(B * L, 3 * D, seed=1, scale=1.5, dtype=BF)
     out = torch.full((B * L, D), float("nan"), dtype=BF, device="cuda")
     e = qkv.element_size()
+    probs = torch.full((B, H, L, L), float("nan"), device="cuda") if B <= 3 else None
     C.attention_long_fwd(qkv, 3 * D, qkv.data_ptr() + D * e, 3 * D, qkv.data_ptr() + 2 * D * e, 3 * D, out, D, B, H, L, hd,
-                         1.0 / math.sqrt(hd))
+                         1.0 / math.sqrt(hd), probs)
     q, k, v = [t.float().reshape(B, L, H, hd).transpose(1, 2) for t in qkv.split(D, dim=1)]
-    ref = torch.matmul(F.softmax(torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(hd), dim=-1), v)
-    ref = ref.transpose(1, 2).reshape(B * L, D)
+    p_ref = F.softmax(torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
+    ref = torch.matmul(p_ref, v).transpose(1, 2).reshape(B * L, D)
     assert bool(torch.isfinite(out.float()).all())
     assert rel_fro(out, ref) < 6e-3
+    if probs is not None:          # the attention maps generate_answers hands to the heat-map script
+        assert rel_fro(probs, p_ref) < 1e-4
 
 
 def test_patchify_assemble_match_conv_embeddings(C):

@@ -129,3 +129,30 @@ def test_vit_training_step_with_the_fused_optimizer(pkg, cuda):
         lp1, _ = run(m, batch, cuda)
         lp2, _ = run(m, batch, cuda)
     assert torch.equal(lp1, lp2)
+
+
+def test_vit_generate_answers_returns_the_attention_maps(pkg, cuda):
+    """generate_answers (model/vit_vqa_model.py:229-293): same log-probs as forward, loss None without labels, and the ViT's
+    twelve attention maps [B, 12, 197, 197] (what ViT_vqa_heatmap.py rolls out) against the oracle's."""
+    from oracle import vit_oracle as V
+    sd = V.random_state_dict(170, seed=0)
+    batch = V.synthetic_batch(2, 16, 20, 170, seed=1, masked_tail=3)
+    m = build(pkg, sd, cuda)
+    kw = {k: v.to(cuda) for k, v in batch.items()}
+    with torch.no_grad():
+        logp, loss = m(**kw)
+        kw2 = dict(kw, annotation_ids=None)
+        logp2, loss2, attn = m.generate_answers(**kw2)
+        logp3, loss3, _ = m.generate_answers(**kw)
+    assert loss2 is None and torch.equal(logp, logp2) and torch.equal(logp, logp3)
+    assert abs(float(loss3) - float(loss)) < 1e-6
+    with torch.no_grad():
+        _, o_attn = V.vit_pooled(sd, batch["pixel_values"], return_attn=True)
+    assert len(attn) == 12
+    worst = 0.0
+    for a, o in zip(attn, o_attn):
+        assert a.shape == (2, 12, 197, 197) and a.dtype == torch.float32
+        assert float((a.sum(-1) - 1).abs().max()) < 1e-4
+        worst = max(worst, float((a.cpu() - o).norm() / o.norm()))
+    report("vit_generate_answers:attention_maps", worst_rel=worst)
+    assert worst < 2e-2, worst
