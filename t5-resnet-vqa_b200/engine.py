@@ -802,11 +802,11 @@ class Engine:
         if gloss is not None:
             st.gloss.copy_(gloss.reshape(1))
         else:
-            st.gloss.zero_()
+            self.rec(None).memset_zero(st.gloss, 4)
         if glogp is not None:
             st.glogp.copy_(glogp)
         elif st.glogp_used:
-            st.glogp.zero_()
+            self.rec(None).memset_zero(st.glogp, 4 * st.glogp.numel())      # (a memset node, not a fill kernel)
         self.pending_clip = None
         if self._ddp is not None:
             self._ddp.backward(self, st)

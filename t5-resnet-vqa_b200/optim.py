@@ -327,7 +327,7 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0, error_if_nonfinite=Fals
         eng.clip_sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
     sq = eng.clip_sumsq
     s = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    sq.zero_()
+    L.check(lib.vqa_memset_zero(None, sq.data_ptr(), 4, s), "memset")
     if eng.ddp_shards is not None:
         # sharded data parallelism: this rank holds the averaged gradient of its slices of the GEMM weights (partial sums
         # meet in a scalar all-reduce) and of all the replicated small tensors (counted once, after the reduction)

@@ -82,7 +82,28 @@ def resnet50_conv_table(B=64, H=224):
     return out
 
 
+def simple(path, tag, title):
+    """Per-kernel table only (any step: used for the VitVQAModel step, tools/vit_bench.py --ncu-step)."""
+    L = load(path)
+    tot = sum(d["us"] for d in L)
+    g = collections.OrderedDict()
+    for d in L:
+        e = g.setdefault(short_name(d["name"])[:72], dict(n=0, us=0.0, rd=0.0, wr=0.0, tw=0.0))
+        e["n"] += 1; e["us"] += d["us"]; e["rd"] += d.get("dram_rd", 0); e["wr"] += d.get("dram_wr", 0)
+        e["tw"] += d.get("tensor_pct", 0) * d["us"]
+    with open(os.path.join(ROOT, "profiles", tag + "_launches_summary.md"), "w") as f:
+        f.write("# %s\n\nTotal %.0f us over %d launches (ncu: cold-cache, serialised per-launch times: compare shares).\n\n"
+                % (title, tot, len(L)))
+        f.write("| kernel | launches | total us | share | avg us | DRAM rd MB | DRAM wr MB | GB/s | tensor pipe active % (time-weighted) |\n|---|---|---|---|---|---|---|---|---|\n")
+        for k, e in sorted(g.items(), key=lambda kv: -kv[1]["us"]):
+            f.write("| `%s` | %d | %.1f | %.1f%% | %.1f | %.1f | %.1f | %.0f | %.1f |\n" % (
+                k, e["n"], e["us"], 100 * e["us"] / tot, e["us"] / e["n"], e["rd"] / 1e6, e["wr"] / 1e6,
+                (e["rd"] + e["wr"]) / e["us"] / 1e3, e["tw"] / e["us"]))
+
+
 def main():
+    if len(sys.argv) > 3 and sys.argv[3] == "--simple":
+        return simple(sys.argv[1], sys.argv[2], sys.argv[4])
     path, tag = sys.argv[1], sys.argv[2]
     L = load(path)
     prof = os.path.join(ROOT, "profiles")

@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--Ld", type=int, default=20)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (ncu --profile-from-start off)")
     a = ap.parse_args()
     os.environ.setdefault("VQA_B200_PRETRAINED", "0")
     import t5_resnet_vqa_b200 as pkg
@@ -62,6 +64,13 @@ def main():
     for _ in range(a.warmup):
         loss = step()
     torch.cuda.synchronize()
+    if a.ncu_step:
+        torch.cuda.profiler.start()
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_step": "done"}))
+        return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
