@@ -149,3 +149,67 @@ def test_trainer_drives_three_steps(pkg, cuda):
         json.dump(dict(trainer="reference FasterRcnnVQATrainer (staged at %s)" % H.REFERENCE_DIR if cls is not None
                        else "restated loop (bench.py); reference not on this machine",
                        losses=dict(AdamW=la, VQAFusedAdamW=lb)), f)
+
+
+# --------------------------------------------------------------------------------------------------
+# VitVQAModel under the reference's ViTVQATrainer (trainer/vit_vqa_trainer.py:300-341,450-464)
+# --------------------------------------------------------------------------------------------------
+def _vit_model(pkg):
+    os.environ["VQA_B200_PRETRAINED"] = "0"
+    return pkg.VitVQAModel("google/vit-base-patch16-224-in21k", "t5-base", answer_spaces=170)
+
+
+@pytest.mark.skipif(not H.reference_available(), reason="the reference is only present in the build container")
+@pytest.mark.parametrize("opt_type", ["AdamW", "VQAFusedAdamW"])
+def test_reference_vit_trainer_builds_optimizer_and_schedule_on_our_model(pkg, opt_type):
+    cls = H.load_reference_trainer_class("vit")
+    tr = H.make_trainer(cls, _vit_model(pkg), total_train_batch=TOTAL, optimizer_type=opt_type)
+    assert type(tr.optimizer).__name__ == opt_type
+    groups = tr.optimizer.param_groups
+    assert [g["model_name"] for g in groups] == ["Vision Model", "Language Model", "Fusion Layer", "Classifier Layer"]
+    assert [len(g["params"]) for g in groups] == [200, 257, 2, 2]          # the tied token table once, under lang_model
+    assert [g["initial_lr"] for g in groups] == [0.008, 0.005, 0.00001, 0.00001]
+    assert all(g["weight_decay"] == 0.1 and g["amsgrad"] for g in groups)
+
+
+@pytest.mark.gpu
+def test_vit_trainer_drives_three_steps(pkg, cuda):
+    """Three `train_one_step` calls of the UNMODIFIED ViTVQATrainer on the collate dict, "AdamW" vs "VQAFusedAdamW" from the same
+    start with dropout off: same losses, same parameter updates.  Needs a staged reference (VQA_REFERENCE_DIR) on the GPU box."""
+    if not H.reference_available():
+        pytest.skip("no staged reference on this machine (the optimizer / schedule contract is checked on CPU)")
+    from oracle import vit_oracle as V
+    cls = H.load_reference_trainer_class("vit")
+    sd = V.random_state_dict(170, seed=0)
+    batch = H.vit_collate_batch(V.synthetic_batch(4, 16, 20, 170, seed=1, masked_tail=3))
+    results = {}
+    for opt_type in ("AdamW", "VQAFusedAdamW"):
+        model = _vit_model(pkg)
+        model.load_state_dict(sd, strict=True)
+        model.to(cuda).eval()
+        tr = H.make_trainer(cls, model, total_train_batch=TOTAL, optimizer_type=opt_type)
+        data = {k: (v.to(cuda) if torch.is_tensor(v) else v) for k, v in batch.items()}
+        losses = []
+        for _ in range(3):
+            loss, logits = tr.train_one_step(data)
+            assert isinstance(loss, float) and loss == loss and logits.shape == (4, 170)
+            losses.append(loss)
+        torch.cuda.synchronize()
+        results[opt_type] = (losses, {k: p.detach().float().cpu().clone() for k, p in model.named_parameters()})
+        assert all(p.grad is None for p in model.vision_model.parameters())
+    la, lb = results["AdamW"][0], results["VQAFusedAdamW"][0]
+    assert la[0] == lb[0] and la[1] == la[0]            # warm-up step 0 runs at lr = 0
+    assert la[2] != la[0] and lb[2] != lb[0]
+    assert max(abs(a - b) for a, b in zip(la, lb)) < 5e-3 * abs(la[0])
+    pa, pb = results["AdamW"][1], results["VQAFusedAdamW"][1]
+    for k in pa:
+        da, db = pa[k] - sd[k].float(), pb[k] - sd[k].float()
+        if k.startswith("vision_model."):
+            assert float(da.abs().max()) == 0.0 and float(db.abs().max()) == 0.0, k
+        else:
+            assert float(da.norm()) > 0 and float((da - db).norm()) <= 0.1 * float(da.norm()), k
+    out = os.path.join(os.path.dirname(GOLD), "..", "..", "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "vit_trainer_dropin.json"), "w") as f:
+        json.dump(dict(trainer="reference ViTVQATrainer (staged at %s)" % H.REFERENCE_DIR,
+                       losses=dict(AdamW=la, VQAFusedAdamW=lb)), f)

@@ -35,8 +35,9 @@ def _stub(name, **attrs):
     return m
 
 
-def load_reference_trainer_class():
-    """FasterRcnnVQATrainer from the unmodified reference file (None when the reference is not on this machine)."""
+def load_reference_trainer_class(kind="cnn"):
+    """FasterRcnnVQATrainer (kind "cnn") or ViTVQATrainer (kind "vit") from the unmodified reference file (None when the
+    reference is not on this machine)."""
     if not reference_available():
         return None
     os.environ.setdefault("WANDB_MODE", "disabled")
@@ -62,6 +63,13 @@ def load_reference_trainer_class():
                 _stub("albumentations.pytorch", ToTensorV2=lambda *a, **k: None)
     if REFERENCE_DIR not in sys.path:
         sys.path.insert(0, REFERENCE_DIR)
+    if kind == "vit":      # trainer/vit_vqa_trainer.py:23 (drives VitVQAModel; same three methods)
+        # trainer/vit_vqa_trainer.py:10 imports dataset_utils.vit_vqa_dataset, a module the reference repository does not
+        # contain (its OK-VQA pipeline was never committed): stubbed, like the uninstalled packages above
+        if not os.path.exists(os.path.join(REFERENCE_DIR, "dataset_utils", "vit_vqa_dataset.py")):
+            importlib.import_module("dataset_utils")
+            _stub("dataset_utils.vit_vqa_dataset", VitT5CollateFn=None, OKVQADataset=None)
+        return importlib.import_module("trainer.vit_vqa_trainer").ViTVQATrainer
     mod = importlib.import_module("trainer.faster_rcnn_vqa_trainer")
     return mod.FasterRcnnVQATrainer
 
@@ -102,3 +110,18 @@ def collate_batch(batch, L_dec=20):
             "pixel_values": None, "image_tensors": batch["image_tensors"], "question_type_ids": None,
             "answer_input_ids": torch.randint(2, 32100, (B, 5), generator=g),
             "answer_attention_masks": torch.ones(B, 5, dtype=torch.long)}
+
+
+def vit_collate_batch(batch):
+    """The dict DaquarVitT5CollateFn returns in training mode (dataset_utils/vit_vqa_daquar_dataset.py:168-178) from an
+    oracle.vit_oracle.synthetic_batch: the keys VitVQAModel.forward uses plus the ones it must accept and ignore."""
+    import torch
+    B = batch["question_input_ids"].shape[0]
+    g = torch.Generator().manual_seed(7)
+    return {"question_input_ids": batch["question_input_ids"],
+            "decoder_question_input_ids": batch["decoder_question_input_ids"],
+            "question_attention_masks": batch["question_attention_masks"],
+            "decoder_question_attention_masks": batch["decoder_question_attention_masks"],
+            "annotation_ids": batch["annotation_ids"], "pixel_values": batch["pixel_values"], "image_tensors": None,
+            "answer_input_ids": torch.randint(2, 32100, (B, 20), generator=g),
+            "answer_attention_masks": torch.ones(B, 20, dtype=torch.long)}
