@@ -107,6 +107,8 @@ typedef struct {
      residual.  NULL / 0: plain bf16 GEMM. */
   const void* B_lo;
   long long a_lo_col;
+  int max_ctas;  /* > 0: the persistent grid uses at most this many CTAs (SMs).  A launch on a plan's side lane (weight
+                    gradients) can leave the rest of the GPU to the chain on the main lane.  0: all SMs */
 } vqa_gemm_args;
 long long vqa_gemm_ksplit_workspace(int M, int N, int bn, int ksplit);
 int vqa_gemm_bf16(void* plan, const vqa_gemm_args* a, void* stream);

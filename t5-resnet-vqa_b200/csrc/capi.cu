@@ -36,7 +36,7 @@ int vqa_gemm_bf16(void* plan, const vqa_gemm_args* a, void* stream) {
   e.residual = a->residual; e.ldr = a->ldr; e.res_fp32 = a->res_fp32; e.res_first = a->res_first;
   e.alpha = a->alpha; e.accumulate = a->accumulate;
   e.ksplit = a->ksplit; e.ks_ws = static_cast<float*>(a->ks_ws); e.ks_ws_bytes = static_cast<size_t>(a->ks_ws_bytes);
-  e.b_lo = a->B_lo; e.a_lo_col = a->a_lo_col;
+  e.b_lo = a->B_lo; e.a_lo_col = a->a_lo_col; e.max_ctas = a->max_ctas;
   GemmOp op;
   int r = gemm_op_init(&op, a->M, a->N, a->K, a->A, a->lda, a->a_mn, a->B, a->ldb, a->b_mn, a->out,
                        a->ldo, a->out_fp32, e, a->bn, a->split_k, a->cta_pair ? 2 : 1);

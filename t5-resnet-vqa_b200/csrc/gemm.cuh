@@ -81,6 +81,7 @@ struct GemmParams {
   // output tile: (A, B), [(A_lo, B),] (A, B_lo).  A_lo = columns [a_lo_col, a_lo_col + K) of A's rows; B_lo is read
   // through the residual tensor map (a split launch has no bf16 residual).  nseg <= 1: off.
   int nseg, kseg, a_lo_col;
+  int max_ctas;                // > 0: the persistent grid is capped at this many CTAs
   int dbg_mode;                // bring-up: 1 = skip the MMAs, 2 = skip the loads (VQA_B200_GEMM_DBG)
   long long* dbg_clk;          // bring-up: clock64 stamps of CTA 0 (vqa_debug_gemm_timing), else null
   int dbg_a_lbo, dbg_a_sbo, dbg_b_lbo, dbg_b_sbo;  // bring-up overrides of the MN-major descriptor strides (0 = default)

@@ -787,7 +787,9 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   const int units_m = (tiles_m + CTAS - 1) / CTAS;     // a pair owns two consecutive m-tiles
   const int ksp = (KS && CTAS == 1 && p.ksplit > 1) ? p.ksplit : 1;   // cluster split-K: a cluster of ksp CTAs per tile
   const int total = units_m * tiles_n * (ksp > 1 ? 1 : splits);
-  const int max_units = sm_count() / (CTAS * ksp);
+  int sms = sm_count();
+  if (p.max_ctas > 0 && p.max_ctas < sms) sms = p.max_ctas < CTAS * ksp ? CTAS * ksp : p.max_ctas;
+  const int max_units = sms / (CTAS * ksp);
   if (ksp > 1 && total > max_units) return -3;          // one tile per cluster (the workspace is not double-buffered)
   const int grid = (total < max_units ? total : max_units) * CTAS * ksp;
   cudaLaunchConfig_t cfg = {};

@@ -24,6 +24,7 @@ void fill_epilogue(GemmParams& p, const Epilogue& e) {
   p.alpha = e.alpha;
   p.ksplit = e.ksplit > 1 ? e.ksplit : 1;
   p.ks_ws = e.ks_ws;
+  p.max_ctas = e.max_ctas;
 }
 
 // cluster split-K preconditions (the kernel trusts them)

@@ -23,6 +23,7 @@ struct Epilogue {
   size_t ks_ws_bytes = 0;
   const void* b_lo = nullptr;   // two-term operand split (see vqa_gemm_args.B_lo / a_lo_col)
   long long a_lo_col = 0;
+  int max_ctas = 0;             // > 0: cap of the persistent grid (vqa_gemm_args.max_ctas)
 };
 
 struct GemmOp {

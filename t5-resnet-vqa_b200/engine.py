@@ -54,6 +54,7 @@ class _Rec:
     def __init__(self, lib, plan, stream_fn, ws_store=None):
         self.lib, self.plan, self.stream_fn = lib, plan, stream_fn
         self._lane = 0
+        self.wgrad_ctas = int(os.environ.get("VQA_B200_WGRAD_CTAS", "0"))
         # cluster split-K workspaces, one per lane: launches of different lanes / plans may run concurrently and
         # must not share one.  ws_store (a dict owned by the plan's State) keeps them alive with the plan.
         self._ws = ws_store if ws_store is not None else {}
@@ -102,7 +103,7 @@ class _Rec:
     # ---- contractions ----
     def gemm(self, M, N, K, A, lda, a_mn, B, ldb, b_mn, out, ldo, out_fp32, bias=None, relu=0, relu_mask=None,
              ldm=0, drop_p=0.0, sid=0, rng=None, residual=None, ldr=0, res_fp32=1, alpha=1.0, accumulate=0,
-             bn=None, split_k=1, pair=None, ksplit=None, b_lo=None, a_lo_col=0):
+             bn=None, split_k=1, pair=None, ksplit=None, b_lo=None, a_lo_col=0, max_ctas=0):
         nseg = 1 if b_lo is None else (3 if a_lo_col else 2)   # two-term operand split: the k-loop is nseg times as long
         if bn is None:
             bn, ks = pick_tile(M, N, K * nseg, allow_ksplit=not accumulate and split_k == 1 and not pair and nseg == 1)
@@ -125,6 +126,7 @@ class _Rec:
             ws = self._ks_workspace()
             a.ks_ws, a.ks_ws_bytes = ws.data_ptr(), ws.numel()
         a.B_lo, a.a_lo_col = L.ptr(b_lo), int(a_lo_col)
+        a.max_ctas = int(max_ctas)
         L.check(self.lib.vqa_gemm_bf16(self.plan, ctypes.byref(a), self._s()), "gemm")
 
     def linear(self, X, M, K, ldx, W, N, out, ldo, out_fp32=0, **kw):
@@ -137,6 +139,8 @@ class _Rec:
 
     def wgrad(self, dY, M, N, ldy, X, K, ldx, dW, **kw):
         """dW[N,K] (fp32) = dY[M,N]^T @ X[M,K]"""
+        if self.wgrad_ctas and self._lane == 1 and "max_ctas" not in kw:
+            kw = dict(kw, max_ctas=self.wgrad_ctas)      # side-lane weight gradients leave SMs to the main lane's chain
         if not kw:
             # few output tiles, deep contraction over the tokens: split K over CTAs (fp32 red.add into a zeroed dW)
             bn, split = pick_wgrad_split(N, K, M)

@@ -21,7 +21,7 @@ class GemmArgs(ctypes.Structure):
                 ("residual", c_vp), ("ldr", c_ll), ("res_fp32", c_int), ("res_first", c_int),
                 ("alpha", c_f), ("accumulate", c_int), ("bn", c_int), ("split_k", c_int), ("cta_pair", c_int),
                 ("ksplit", c_int), ("ks_ws", c_vp), ("ks_ws_bytes", c_ll),
-                ("B_lo", c_vp), ("a_lo_col", c_ll)]
+                ("B_lo", c_vp), ("a_lo_col", c_ll), ("max_ctas", c_int)]
 
 
 class ConvArgs(ctypes.Structure):
