@@ -16,6 +16,7 @@ the ViT (patch GEMM, LayerNorm, 197-token tcgen05 attention, exact GELU).  `hf:`
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -45,7 +46,9 @@ class VitEngine(Engine):
     def __init__(self, model):
         super().__init__(model)
         self.t5_split_blocks = 0
-        self.split_head = False
+        # VQA_B200_VIT_SPLIT=1: every forward GEMM of the two T5 stacks, the fusing layer and the classifier contracts two-term
+        # (hi + lo bf16) operands; 0: plain bf16
+        self.split_head = os.environ.get("VQA_B200_VIT_SPLIT", "0") == "1"
 
     # ---- flat layout: GEMM weights (classifier, fusing layer, decoder 11..0, encoder 11..0), then the small tensors ----
     def _layout(self):
@@ -73,7 +76,7 @@ class VitEngine(Engine):
         return big, small
 
     def _split_ranges(self, offs):
-        return []
+        return [(0, self.n_big)] if self.split_head else []
 
     ddp_shardable = False         # replicas + one all-reduce of the flat gradient after backward (one backward segment)
 
@@ -275,33 +278,45 @@ class _T5Stack:
         for bi, blk in enumerate(self.blocks):
             att, ff = blk.layer[0], blk.layer[-1]
             sa, dd = att.SelfAttention, ff.DenseReluDense
-            sv = dict(y1=al(M, D), rstd1=al(M, dtype=f32), qkv=al(M, 3 * inner), stats=al(B * nH * Lq, 2, dtype=f32),
-                      ctx=al(M, inner), hmid=al(M, D, dtype=f32), y2=al(M, D), rstd2=al(M, dtype=f32), h=al(M, dff),
-                      sid_p=self.new_sid(), sid_o=self.new_sid(), sid_h=self.new_sid(), sid_f=self.new_sid())
-            r.rmsnorm_fwd(self.hid[bi], eng.mp(att.layer_norm.weight), sv["y1"], None, sv["rstd1"], M, D, eps, 0.0, 0, None)
-            r.linear(sv["y1"], M, D, D, eng.sp(sa.q.weight), 3 * inner, sv["qkv"], 3 * inner)
+            split = eng.split_head
+            ldy = 2 * D if split else D
+            sv = dict(y1=al(M, ldy), rstd1=al(M, dtype=f32), qkv=al(M, 3 * inner), stats=al(B * nH * Lq, 2, dtype=f32),
+                      ctx=al(M, inner), hmid=al(M, D, dtype=f32), y2=al(M, ldy), rstd2=al(M, dtype=f32), h=al(M, dff),
+                      ldy=ldy, sid_p=self.new_sid(), sid_o=self.new_sid(), sid_h=self.new_sid(), sid_f=self.new_sid())
+
+            def norm(x, w, y, rstd):
+                if split:
+                    r.rmsnorm_fwd_split(x, eng.mp(w), y, rstd, M, D, eps)
+                else:
+                    r.rmsnorm_fwd(x, eng.mp(w), y, None, rstd, M, D, eps, 0.0, 0, None)
+
+            def lo(w, with_a):
+                return dict(b_lo=eng.lp(w), a_lo_col=D if with_a else 0) if split else {}
+            norm(self.hid[bi], att.layer_norm.weight, sv["y1"], sv["rstd1"])
+            r.linear(sv["y1"], M, D, ldy, eng.sp(sa.q.weight), 3 * inner, sv["qkv"], 3 * inner, **lo(sa.q.weight, True))
             qkv = sv["qkv"]
             r.attn_fwd(B, nH, Lq, Lq, dkv, qkv, 3 * inner, qkv.data_ptr() + 2 * inner, 3 * inner,
                        qkv.data_ptr() + 4 * inner, 3 * inner, sv["ctx"], inner, None, self.pos_bias, self.key_mask, 1.0,
                        p, sv["sid_p"], rng, stats=sv["stats"])
             r.linear(sv["ctx"], M, inner, inner, eng.sp(sa.o.weight), D, sv["hmid"], D, out_fp32=1,
-                     drop_p=p, sid=sv["sid_o"], rng=rng, residual=self.hid[bi], ldr=D, res_fp32=1)
+                     drop_p=p, sid=sv["sid_o"], rng=rng, residual=self.hid[bi], ldr=D, res_fp32=1, **lo(sa.o.weight, False))
             x = sv["hmid"]
             if self.dec:
                 # cross-attention onto the single fused token: ctx = dropout(1) * (fused W_v^T); q / k never run
                 ca = blk.layer[1].EncDecAttention
                 sv.update(vx=al(B, inner), ctxc=al(M, inner), hmid2=al(M, D, dtype=f32),
                           sid_pc=self.new_sid(), sid_co=self.new_sid())
-                r.linear(self.fused, B, D, D, eng.sp(ca.v.weight), inner, sv["vx"], inner, bn=64)
+                r.linear(self.fused, B, D, D, eng.sp(ca.v.weight), inner, sv["vx"], inner, bn=64, **lo(ca.v.weight, False))
                 r.xattn1_fwd(sv["vx"], sv["ctxc"], B, nH, Lq, dkv, p, sv["sid_pc"], rng)
                 r.linear(sv["ctxc"], M, inner, inner, eng.sp(ca.o.weight), D, sv["hmid2"], D, out_fp32=1,
-                         drop_p=p, sid=sv["sid_co"], rng=rng, residual=sv["hmid"], ldr=D, res_fp32=1)
+                         drop_p=p, sid=sv["sid_co"], rng=rng, residual=sv["hmid"], ldr=D, res_fp32=1, **lo(ca.o.weight, False))
                 x = sv["hmid2"]
             sv["xff"] = x
-            r.rmsnorm_fwd(x, eng.mp(ff.layer_norm.weight), sv["y2"], None, sv["rstd2"], M, D, eps, 0.0, 0, None)
-            r.linear(sv["y2"], M, D, D, eng.sp(dd.wi.weight), dff, sv["h"], dff, relu=1, drop_p=p, sid=sv["sid_h"], rng=rng)
+            norm(x, ff.layer_norm.weight, sv["y2"], sv["rstd2"])
+            r.linear(sv["y2"], M, D, ldy, eng.sp(dd.wi.weight), dff, sv["h"], dff, relu=1, drop_p=p, sid=sv["sid_h"], rng=rng,
+                     **lo(dd.wi.weight, True))
             r.linear(sv["h"], M, dff, dff, eng.sp(dd.wo.weight), D, self.hid[bi + 1], D, out_fp32=1,
-                     drop_p=p, sid=sv["sid_f"], rng=rng, residual=x, ldr=D, res_fp32=1)
+                     drop_p=p, sid=sv["sid_f"], rng=rng, residual=x, ldr=D, res_fp32=1, **lo(dd.wo.weight, False))
             self.saved.append(sv)
         self.out_f32, self.rstd_f = al(M, D, dtype=f32), al(M, dtype=f32)
         self.sid_final = self.new_sid()
@@ -340,7 +355,7 @@ class _T5Stack:
             side.before_write(dpre)
             r.dgrad(g_bf, M, D, D, eng.sp(dd.wo.weight), dff, dpre, dff, relu_mask=sv["h"], ldm=dff, drop_p=p,
                     sid=sv["sid_h"], rng=rng)
-            side.leaf([dpre], lambda: r.wgrad(dpre, M, dff, dff, sv["y2"], D, D, eng.gp(dd.wi.weight)))
+            side.leaf([dpre], lambda: r.wgrad(dpre, M, dff, dff, sv["y2"], D, sv["ldy"], eng.gp(dd.wi.weight)))
             side.before_write(dsm)
             r.dgrad(dpre, M, dff, dff, eng.sp(dd.wi.weight), D, dsm, D)
             g_bf = next_g()
@@ -372,7 +387,7 @@ class _T5Stack:
                        qkv.data_ptr() + 4 * inner, 3 * inner, None, dsm, inner,
                        dqkv, 3 * inner, dqkv.data_ptr() + 2 * inner, 3 * inner, dqkv.data_ptr() + 4 * inner, 3 * inner,
                        dbias_pos, 1.0, p, sv["sid_p"], rng, stats=sv["stats"], bias=self.pos_bias, key_mask=self.key_mask)
-            side.leaf([dqkv], lambda: r.wgrad(dqkv, M, 3 * inner, 3 * inner, sv["y1"], D, D, eng.gp(sa.q.weight)))
+            side.leaf([dqkv], lambda: r.wgrad(dqkv, M, 3 * inner, 3 * inner, sv["y1"], D, sv["ldy"], eng.gp(sa.q.weight)))
             side.before_write(dsm)
             r.dgrad(dqkv, M, 3 * inner, 3 * inner, eng.sp(sa.q.weight), D, dsm, D)
             if bi > 0:
@@ -479,14 +494,15 @@ def build_state(eng, B, Lt, Ld, H, W, training, has_labels, want_attn=False):
     cat_b, fused_b = al(B, 2 * D), al(B, D)
     r.vit_fuse_concat(pooled_pre, enc_out, Lt, cat_b, st.pooled, B, D)
     sid_fuse = new_sid()
+    hlo = (lambda w: dict(b_lo=eng.lp(w))) if eng.split_head else (lambda w: {})
     r.linear(cat_b, B, 2 * D, 2 * D, eng.sp(fl.weight), D, fused_b, D, bias=eng.mp(fl.bias), relu=1, drop_p=p_fuse,
-             sid=sid_fuse, rng=rng, bn=64)
+             sid=sid_fuse, rng=rng, bn=64, **hlo(fl.weight))
     dec = _T5Stack(eng, al, t5.decoder, B, Ld, st.dec_ids, st.dec_mask, training, new_sid, fused=fused_b)
     dec_out = dec.forward(r)
     ans_b = al(B, D)
     r.gather_rows(dec_out, st.dec_mask, ans_b, None, B, Ld, D)
     logits = al(B, Apad, dtype=f32, zero=True)
-    r.linear(ans_b, B, D, D, eng.sp(cls.weight), A, logits, Apad, out_fp32=1, bias=eng.mp(cls.bias), bn=64)
+    r.linear(ans_b, B, D, D, eng.sp(cls.weight), A, logits, Apad, out_fp32=1, bias=eng.mp(cls.bias), bn=64, **hlo(cls.weight))
     r.logsoftmax_nll_fwd(logits, Apad, st.labels if has_labels else None, st.logp, st.loss if has_labels else None, B, A)
     st.n_fwd_launches = sum(lib.vqa_plan_size(p) for p in st.fwd_plans)
 

@@ -17,7 +17,9 @@ LOGP_REL, LOSS_REL = 2e-2, 1e-3
 # Per-tensor gradient cosine vs the fp32 oracle.  This model runs plain bf16 operands everywhere (no two-term split: that
 # was added for the north-star ResnetVQAModel's bar only), and the whole gradient flows through ONE token per sample (the
 # decoder's last position / the encoder's token 0), so there is no averaging over tokens: the bar asserted here is the
-# measured floor of that configuration, 0.99 on every tensor and 0.998 in the median.
+# measured floor of that configuration, 0.99 on every tensor and 0.998 in the median (measured: worst 0.9949).  With two-term
+# operands in every forward GEMM (VQA_B200_VIT_SPLIT=1) the worst tensor reaches 0.9974 and the log-probs 4.3e-4: what remains
+# is the bf16 rounding of the BACKWARD operands (dpre, y2 of the FFN weight gradients), which only a handful of tokens average.
 GRAD_COS_MIN, GRAD_COS_MEDIAN = 0.99, 0.998
 
 
