@@ -20,13 +20,45 @@ if ROOT not in sys.path:
 LOSS_REL, GRAD_REL = 2e-3, 3e-2
 
 
+def _state_dict(pkg, kind):
+    """Deterministic weights from the PACKAGE's own initialisation under a fixed seed (identical on every rank; nothing under
+    oracle/ is touched: bench.py --gpus N runs this check).  The last BatchNorm gain of every residual block is scaled down as
+    in trained networks, so that sixteen residual additions keep the feature map O(1) and the guided attention stays soft."""
+    torch.manual_seed(0)
+    if kind == "vit":
+        m = pkg.VitVQAModel("google/vit-base-patch16-224-in21k", "t5-base", 170)
+    else:
+        m = pkg.ResnetVQAModel(kind, "t5-base", 170)
+        with torch.no_grad():
+            for layer in (m.vision_model.layer1, m.vision_model.layer2, m.vision_model.layer3, m.vision_model.layer4):
+                for blk in layer:
+                    (blk.bn3 if hasattr(blk, "bn3") else blk.bn2).weight.mul_(0.3)
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def _batch(n, L, H, W, masked_tail, seed=1, vit=False, Ld=20):
+    g = torch.Generator().manual_seed(seed)
+    b = dict(question_input_ids=torch.randint(2, 32100, (n, L), generator=g),
+             question_attention_masks=torch.ones(n, L, dtype=torch.long),
+             annotation_ids=torch.randint(0, 170, (n,), generator=g))
+    b["question_attention_masks"][:, L - masked_tail:] = 0
+    if vit:
+        b["pixel_values"] = torch.rand(n, 3, H, W, generator=g) * 2 - 1
+        b["decoder_question_input_ids"] = torch.randint(2, 32100, (n, Ld), generator=g)
+        b["decoder_question_attention_masks"] = torch.ones(n, Ld, dtype=torch.long)
+        for i in range(n):
+            b["decoder_question_attention_masks"][i, 3 + (5 * i) % (Ld - 2):] = 0
+    else:
+        b["image_tensors"] = torch.rand(n, 3, H, W, generator=g)
+    return b
+
+
 def check(dev, rank, world, per=4, vision="resnet18"):
     """Returns (on rank 0) dict(world, loss_mean_of_ranks, loss_single, worst_grad_rel_diff, identical_across_ranks, ok)."""
     os.environ.setdefault("VQA_B200_PRETRAINED", "0")
     import t5_resnet_vqa_b200 as pkg
-    from oracle import vqa_oracle as O      # test infrastructure: deterministic weights / inputs only
-    sd = O.random_state_dict(vision, 170, seed=0)
-    full = O.synthetic_batch(per * world, 16, 64, 64, 170, seed=1, masked_tail=3)
+    sd = _state_dict(pkg, vision)
+    full = _batch(per * world, 16, 64, 64, 3)
 
     def run(model, batch):
         kw = {k: v.to(dev) for k, v in batch.items()}
@@ -82,9 +114,8 @@ def check_vit(dev, rank, world, per=2):
     """The same gradient equivalence for VitVQAModel (replicas, one all-reduce of the flat gradient behind its backward)."""
     os.environ.setdefault("VQA_B200_PRETRAINED", "0")
     import t5_resnet_vqa_b200 as pkg
-    from oracle import vit_oracle as V      # test infrastructure: deterministic weights / inputs only
-    sd = V.random_state_dict(170, seed=0)
-    full = V.synthetic_batch(per * world, 16, 20, 170, seed=1, masked_tail=3)
+    sd = _state_dict(pkg, "vit")
+    full = _batch(per * world, 16, 224, 224, 3, vit=True)
 
     def run(model, batch):
         kw = {k: v.to(dev) for k, v in batch.items()}
@@ -139,9 +170,8 @@ def check_training(dev, rank, world, per=4, vision="resnet18", steps=3):
     bf16 wire format's.  Returns (rank 0) a dict with the worst tensors of both comparisons."""
     os.environ.setdefault("VQA_B200_PRETRAINED", "0")
     import t5_resnet_vqa_b200 as pkg
-    from oracle import vqa_oracle as O
-    sd = O.random_state_dict(vision, 170, seed=0)
-    full = O.synthetic_batch(per * world, 16, 64, 64, 170, seed=1, masked_tail=3)
+    sd = _state_dict(pkg, vision)
+    full = _batch(per * world, 16, 64, 64, 3)
 
     def train(batch, env):
         old = {k: os.environ.get(k) for k in env}
