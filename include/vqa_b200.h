@@ -84,7 +84,8 @@ typedef struct {
   const void* B; long long ldb; int b_mn;
   void* out; long long ldo; int out_fp32;
   const float* bias;
-  int relu;
+  int relu;                                      /* 1: ReLU; 2: exact (erf) GELU instead - bf16 output, no residual / mask /
+                                                    dropout / accumulate (the frozen ViT's fc1, vit: ViTIntermediate) */
   const void* relu_mask; long long ldm;          /* bf16 [M, ldm] */
   float drop_p; uint32_t drop_sid; const uint64_t* rng;   /* rng: device {seed, offset} */
   const void* residual; long long ldr; int res_fp32; int res_first;

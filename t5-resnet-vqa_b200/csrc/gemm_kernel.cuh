@@ -118,7 +118,7 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int t, cons
 }  // namespace
 
 // EPI: compile-time epilogue variant (bit 0 fp32 output, bits 1-2 residual: 0 none / 1 bf16 through the TMA ring /
-// 2 fp32 read directly, bit 3 ReLU-mask, bit 4 dropout, bit 5 fp32 reduce-add output).
+// 2 fp32 read directly, bit 3 ReLU-mask, bit 4 dropout, bit 5 fp32 reduce-add output, bit 6 exact GELU instead of ReLU).
 __host__ __device__ constexpr int epi_code(bool out_fp32, int res, bool mask, bool drop, bool atomic) {
   return (out_fp32 ? 1 : 0) | (res << 1) | (mask ? 8 : 0) | (drop ? 16 : 0) | (atomic ? 32 : 0);
 }
@@ -138,7 +138,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr bool kMask = (EPI & 8) != 0;
   constexpr bool kDrop = (EPI & 16) != 0;
   constexpr bool kAtomic = (EPI & 32) != 0;
+  constexpr bool kGelu = (EPI & 64) != 0;   // exact (erf) GELU after the bias instead of ReLU: the frozen ViT's fc1 (vit: ViTIntermediate)
   static_assert(!(kRes == 1 && kOutF32), "a bf16 residual (TMA ring) is only combined with bf16 output");
+  static_assert(!kGelu || (!kOutF32 && kRes == 0 && !kMask && !kDrop && !kAtomic && !KS), "GELU: plain bf16-output launches only");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -669,6 +671,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] += rs[i];
             }
+          } else if (kGelu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
           } else {
             if (p.relu) {
 #pragma unroll
@@ -817,7 +822,8 @@ template <int BN, int STAGES, int CTAS>
 int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmRes,
               const GemmParams& p, int tiles_m, int tiles_n, int splits, cudaStream_t stream) {
   const int res = p.residual == nullptr ? 0 : (p.res_fp32 ? 2 : 1);
-  const int code = epi_code(p.out_fp32 != 0, res, p.relu_mask != nullptr, p.drop_p > 0.f, p.atomic_out != 0);
+  const int code = epi_code(p.out_fp32 != 0, res, p.relu_mask != nullptr, p.drop_p > 0.f, p.atomic_out != 0) |
+                   (p.relu == 2 ? 64 : 0);
 #define VQA_EPI_CASE(o, r, m, d, a)                                                                   \
   case epi_code(o, r, m, d, a):                                                                       \
     if (CTAS == 1 && p.ksplit > 1)                                                                    \
@@ -837,6 +843,9 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     VQA_EPI_CASE(true, 0, false, false, false)   // fp32 out                      (wgrad, logits)
     VQA_EPI_CASE(true, 0, false, true, false)    // fp32 out + dropout
     VQA_EPI_CASE(true, 0, false, false, true)    // fp32 reduce-add               (split-K, accumulate)
+    case 64:                                     // bf16 out + bias + exact GELU   (the frozen ViT's fc1)
+      if (p.ksplit > 1) return -2;
+      return launch_impl<BN, STAGES, 64, CTAS, false>(tmA, tmB, tmOut, tmRes, p, tiles_m, tiles_n, splits, stream);
     default:
       return -2;   // combination not instantiated (gemm_op_run reports it)
   }

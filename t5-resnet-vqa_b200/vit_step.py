@@ -467,8 +467,7 @@ def build_state(eng, B, Lt, Ld, H, W, training, has_labels, want_attn=False):
         r.linear(ctx, Mv, Dv, Dv, eng.vw(pre + "o"), Dv, hid_b, Dv, out_fp32=1, bias=eng.vf(pre + "o_b"),
                  residual=hid_a, ldr=Dv, res_fp32=1)
         r.layernorm_fwd(hid_b, eng.vf(pre + "ln2_w"), eng.vf(pre + "ln2_b"), nrm, None, mean_s, rstd_s, Mv, Dv, veps)
-        r.linear(nrm, Mv, Dv, Dv, eng.vw(pre + "fc1"), Iv, hbuf, Iv, bias=eng.vf(pre + "fc1_b"))
-        r.gelu_bf16(hbuf, Mv * Iv)
+        r.linear(nrm, Mv, Dv, Dv, eng.vw(pre + "fc1"), Iv, hbuf, Iv, bias=eng.vf(pre + "fc1_b"), relu=2)   # bias + exact GELU
         r.linear(hbuf, Mv, Iv, Iv, eng.vw(pre + "fc2"), Dv, hid_a, Dv, out_fp32=1, bias=eng.vf(pre + "fc2_b"),
                  residual=hid_b, ldr=Dv, res_fp32=1)
     r.layernorm_fwd(hid_a, eng.vf("ln_w"), eng.vf("ln_b"), nrm, None, mean_s, rstd_s, Mv, Dv, veps)

@@ -62,6 +62,15 @@ def test_patchify_assemble_match_conv_embeddings(C):
     assert rel_fro(hidden, ref.reshape(B * (NP + 1), D)) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(12608, 3072, 768, 256), (394, 3072, 768, 128), (200, 192, 128, 64)])
+def test_linear_bias_gelu_epilogue(C, M, N, K, bn):
+    """fc1 of the ViT layer: bf16 out = gelu(x W^T + b) in the GEMM epilogue (vqa_gemm_args.relu = 2)."""
+    X, W, b = rnd(M, K, seed=1, dtype=BF), rnd(N, K, seed=2, scale=2.0 * K ** -0.5, dtype=BF), rnd(N, seed=3)
+    out = torch.zeros(M, N, dtype=BF, device="cuda")
+    C.linear(X, M, K, K, W, N, out, N, bias=b, relu=2, bn=bn)
+    assert rel_fro(out, F.gelu(X.float() @ W.float().t() + b)) < 6e-3
+
+
 def test_gelu_and_fuse_concat(C):
     x = rnd(1000, 3072, seed=1, scale=2.0, dtype=BF)
     y = x.clone()
