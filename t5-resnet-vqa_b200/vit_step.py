@@ -84,6 +84,10 @@ class VitEngine(Engine):
         return self.model.lang_model.shared.weight
 
     def _after_flatten(self, device):
+        # a new device (or a re-flattened model): the frozen ViT's caches are rebuilt there by the next prepare()
+        self.__dict__.pop("vit_w", None)
+        self.__dict__.pop("vit_f", None)
+        self.vision_sig = None
         from .ddp import maybe_enable
         maybe_enable(self)
 
