@@ -92,6 +92,23 @@ def test_wgrad(C, M, N, K, bn):
     assert rel_fro(dW, dY[:, :N].float().t() @ X.float()) < 2e-5
 
 
+@pytest.mark.parametrize("cap", [1, 40, 148, 500])
+def test_capped_persistent_grid(C, cap):
+    """vqa_gemm_args.max_ctas: the persistent grid walks the same tiles with fewer CTAs (side-lane weight gradients)."""
+    M, N, K = 2048, 768, 768
+    dY, X = rnd(M, N, seed=1, dtype=BF), rnd(M, K, seed=2, dtype=BF)
+    dW = torch.zeros(N, K, device="cuda")
+    C.wgrad(dY, M, N, N, X, K, K, dW, bn=128, max_ctas=cap)
+    assert rel_fro(dW, dY.float().t() @ X.float()) < 2e-5
+
+
+def test_memcpy_d2d_plan_step(C):
+    src = rnd(1000, 768, seed=1, dtype=BF)
+    dst = torch.zeros_like(src)
+    C.memcpy_d2d(dst, src, src.numel() * 2)
+    assert torch.equal(dst, src)
+
+
 # ------------------------------------------------------------------------------------------------
 # two-term operand split (hi + lo bf16): the early T5 blocks' forward GEMMs (vqa_gemm_args.B_lo / a_lo_col)
 # ------------------------------------------------------------------------------------------------
