@@ -247,6 +247,19 @@ def test_vit_vqa_model_surface_and_tied_table(pkg):
     m.load_state_dict(V.random_state_dict(170, seed=0), strict=True)
     for attr in ("vision_model", "lang_model", "fusing_layer", "classification_layer"):   # trainer/vit_vqa_trainer.py:300-318
         assert len(list(getattr(m, attr).parameters())) > 0
+    # flat layout: exactly the tensors the reference trains (oracle.trainable_keys), each once; fused q|k|v adjacent and in
+    # order in both stacks; GEMM weights first, the tied token table last
+    eng = m._engine
+    big, small = eng._layout()
+    names = {id(p): k for k, p in m.named_parameters()}
+    assert sorted(names[id(p)] for p in big + small) == sorted(V.trainable_keys(V.random_state_dict(170, seed=0)))
+    assert len(set(id(p) for p in big + small)) == len(big) + len(small) == 261
+    order = [names[id(p)] for p in big]
+    for stack in ("encoder", "decoder"):
+        i = order.index("lang_model.%s.block.5.layer.0.SelfAttention.q.weight" % stack)
+        assert order[i + 1].endswith("%s.block.5.layer.0.SelfAttention.k.weight" % stack)
+        assert order[i + 2].endswith("%s.block.5.layer.0.SelfAttention.v.weight" % stack)
+    assert all(p.dim() == 2 and p.numel() % 64 == 0 for p in big[2:]) and names[id(small[-1])] == "lang_model.shared.weight"
     with pytest.raises(ValueError):
         pkg.VitVQAModel("resnet50", "t5-base", 170)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
