@@ -8,7 +8,8 @@
 // walks are bank-conflict free), scores and probabilities never leave the SM (flash-style: no [B,H,L,L]
 // fp32 score round trip; the normalised fp32 probabilities are saved once for backward), and the backward kernel produces
 // dQ, dK, dV and the relative-position-bias gradient in one pass.
-// TODO(next round): move the two contractions onto tcgen05 by packing 4 (b,h) pairs per 128-row MMA.
+// Since round 2 this SIMT kernel only runs for key sequences longer than 64 tokens (the guided attention over the 196 vision
+// tokens of 448x448 images); everything up to 64 x 64 runs the tcgen05 kernels of attention_tc.cu.
 #include "../../include/vqa_b200.h"
 #include "common.cuh"
 
